@@ -1,0 +1,177 @@
+/*
+ * sy_env.h -- C ABI of the B200-native batched Scotland Yard environment (libsy_env.so).
+ *
+ * This is the drop-in boundary for the reference's environment hot path.  The reference has
+ * no FFI of its own (it is pure Python); the entry points below are what a binding for
+ *   /root/reference/src/environment/yard.py        CustomEnvironment.reset / step / observations
+ *   /root/reference/src/environment/action_mask.py compute_action_mask
+ *   /root/reference/src/environment/reward_calculator.py RewardCalculator
+ *   /root/reference/src/environment/pathfinding.py Pathfinder.get_distance
+ * would call (see INTEGRATION.md for the ctypes stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in signatures; `sy_stream_t` is a `cudaStream_t` passed as void*.
+ *   - every function returns SY_OK (0) or an error code; `sy_last_error()` gives the text
+ *     (thread-local).  Nothing throws across the ABI.  Invalid *actions* are data, not errors:
+ *     they mean "stay" exactly as in yard.py:171-178,223-229.
+ *   - ownership: the CALLER owns every state / observation / output buffer (device memory, e.g.
+ *     torch tensors) and passes raw pointers; the library owns only its opaque handle and the
+ *     per-graph tables it builds in `sy_load_graphs` (dense weights, all-pairs distances, CSR).
+ *   - all launches are asynchronous on the given stream; no host synchronisation inside
+ *     `sy_step` / `sy_reset` / `sy_sample_actions`.
+ *   - shapes: B envs on this device, N nodes, P police, A = P + 1 agents (agent 0 = MrX,
+ *     agent 1+k = Police k, as yard.py:54-56), G graphs in the pool.
+ */
+#ifndef SY_ENV_H
+#define SY_ENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SY_ABI_VERSION 1
+#define SY_NUM_REWARD_WEIGHTS 11 /* order = REWARD_WEIGHT_NAMES, src/reward_net.py:5-17 */
+#define SY_MAX_AGENTS 16
+#define SY_NUM_STATS 16
+#define SY_DEFAULT_ACTION (-1) /* yard.py:16 ; for police identical to `None` (yard.py:210-215) */
+
+enum {
+  SY_OK = 0,
+  SY_ERR_INVALID_ARGUMENT = 1,
+  SY_ERR_CUDA = 2,
+  SY_ERR_STATE = 3 /* call order violated, e.g. step before load_graphs */
+};
+
+enum { SY_REWARD_FP64 = 0, SY_REWARD_FP32 = 1 };
+enum { SY_WINNER_NONE = 0, SY_WINNER_MRX = 1, SY_WINNER_POLICE = 2 };
+
+/* indices into the int64 statistics vector (SyOut.stats); summed over ranks by the host */
+enum {
+  SY_STAT_ENV_STEPS = 0,
+  SY_STAT_EPISODES = 1,
+  SY_STAT_MRX_WINS = 2,
+  SY_STAT_POLICE_WINS = 3, /* captures, reward_calculator.py:63-67 */
+  SY_STAT_TRUNCATIONS = 4, /* timestep > max_timestep, reward_calculator.py:68-74 */
+  SY_STAT_OUT_OF_MONEY = 5, /* reward_calculator.py:75-79 */
+  SY_STAT_SUM_EPISODE_LENGTH = 6,
+  SY_STAT_SUM_BUDGET_SPENT = 7
+};
+
+typedef void* sy_stream_t;
+typedef struct SyEnv SyEnv;
+
+/* Replaces the constructor arguments of CustomEnvironment (yard.py:18-28) plus the knobs the
+ * reference only has as ablation YAML (src/configs/ablation/mechanism.yaml:1-26). */
+typedef struct SyConfig {
+  int32_t struct_bytes;    /* = sizeof(SyConfig); ABI guard */
+  int32_t device;          /* CUDA ordinal */
+  int32_t num_envs;        /* B: envs held by THIS handle (one shard of the global batch) */
+  int32_t num_nodes;       /* N  (graph_nodes) */
+  int32_t num_police;      /* P  (number_of_agents, yard.py:33) */
+  int32_t agent_money;     /* yard.py:42,117-119 */
+  int32_t mrx_money;       /* MAX_MONEY_LIMIT = 1000, yard.py:11 */
+  int32_t max_timestep;    /* 250, reward_calculator.py:68 */
+  int32_t reveal_interval; /* 0 = MrX always visible (reference behaviour) */
+  int32_t toll;            /* 0 = reference behaviour; else legality and police charge use w + toll */
+  int32_t belief;          /* 0/1: maintain belief_map */
+  int32_t reward_mode;     /* SY_REWARD_FP64 (python-float weights) | SY_REWARD_FP32 (0-dim fp32 tensors) */
+  int32_t auto_reset;      /* 0/1: same-step auto-reset of finished envs (Philox start nodes) */
+  int32_t resample_graph;  /* 0/1: on (auto-)reset draw graph_id uniformly from the pool */
+  int64_t env_offset;      /* global index of env 0: keeps Philox streams shard-invariant */
+  uint64_t seed;
+  double reward_weights[SY_NUM_REWARD_WEIGHTS];
+} SyConfig;
+
+/* Per-env state, device pointers, caller-owned (yard.py:111-127 state, batched). */
+typedef struct SyState {
+  int32_t* pos;      /* [B, A]  MrX_pos + police_positions */
+  int32_t* money;    /* [B, A]  agents_money */
+  int32_t* timestep; /* [B] */
+  int32_t* graph_id; /* [B] index into the graph pool */
+  int32_t* episode;  /* [B] episodes started (Philox counter) */
+  uint8_t* done;     /* [B] 1 = finished and frozen until reset (only without auto_reset) */
+  uint16_t* visits;  /* [B, N] node_visit_counts (yard.py:59,244-245) */
+  float* belief;     /* [B, N] belief_map, may be NULL when config.belief == 0 */
+} SyState;
+
+/* Dynamic observation tensors written every reset/step (yard.py:271-335).  Static graph
+ * tensors (adjacency_matrix, edge_index, edge_features) are per-graph and are built once by
+ * the host from the same CSR; belief_map is SyState.belief; agent_position is SyState.pos. */
+typedef struct SyObs {
+  uint8_t* action_mask;  /* [B, A, N] bool */
+  float* node_features;  /* [B, N, A] one-hot of positions, column 0 = MrX (blank while hidden) */
+  float* agent_budget;   /* [B, A]  yard.py:329-331 */
+  int32_t* mrx_revealed; /* [B] MrX node if visible this step else -1 */
+} SyObs;
+
+/* Step results (reward_calculator.py:26-92). */
+typedef struct SyOut {
+  float* reward;       /* [B, A] */
+  double* reward64;    /* [B, A] or NULL: the float64 value before the float32 cast (fp64 mode) */
+  uint8_t* terminated; /* [B, A] */
+  uint8_t* truncated;  /* [B, A] */
+  uint8_t* done;       /* [B, A] terminated | truncated */
+  int8_t* winner;      /* [B]   SY_WINNER_* (env.current_winner, yard.py:250) */
+  int64_t* stats;      /* [SY_NUM_STATS] device accumulators or NULL */
+} SyOut;
+
+int sy_abi_version(void);
+const char* sy_last_error(void);
+/* number of CUDA kernels this library has launched in this process (for bench `gpu_launches`) */
+int64_t sy_launch_count(void);
+
+/* replaces CustomEnvironment.__init__ (yard.py:18-78) */
+int sy_create(const SyConfig* config, SyEnv** out_env);
+void sy_destroy(SyEnv* env);
+
+/* Host-built float64 tables so that rewards are bit-identical to NumPy's:
+ * exp_neg[d] = np.exp(-d) (reward_calculator.py:186,199,214), coverage[c] = np.exp(-np.log1p(c))
+ * (reward_calculator.py:204-205).  HOST pointers; indices past the end read as exp(-inf) = 0
+ * (exp_neg) or clamp (coverage). */
+int sy_set_reward_tables(SyEnv* env, const double* exp_neg, int32_t n_exp, const double* coverage,
+                         int32_t n_cov, sy_stream_t stream);
+
+/* Upload the graph pool as CSR (HOST pointers; every undirected edge appears in both rows,
+ * neighbours ascending, weights 1..255) and build on device: the dense weight table
+ * (yard.py:404-418), the all-pairs shortest-path table that replaces Pathfinder.get_distance
+ * (pathfinding.py:34-137), the move-count table (yard.py:420-472) and 1/deg for the belief.
+ * row_ptr [G, N+1] (offsets local to each graph), col / w [G, nnz_stride]. */
+int sy_load_graphs(SyEnv* env, int32_t num_graphs, const int32_t* row_ptr, const int32_t* col,
+                   const int32_t* w, int32_t nnz_stride, sy_stream_t stream);
+/* copy graph g's tables to HOST buffers (any may be NULL): weights u8 [N, N], apsp u16 [N, N]
+ * (0xFFFF = unreachable).  Synchronises the stream.  For tests / get_distance parity. */
+int sy_read_graph_tables(SyEnv* env, int32_t g, uint8_t* weights, uint16_t* apsp, sy_stream_t stream);
+
+/* replaces CustomEnvironment.reset (yard.py:80-142) for the envs whose reset_mask byte is
+ * non-zero (NULL = all).  init_pos [B, A] / init_graph_id [B] (device, may be NULL) let a caller
+ * hand over the reference's own start nodes and graphs; otherwise Philox(seed; env, episode).
+ * restart != 0 sets the episode counter of the reset envs to 0, else it is incremented.
+ * Observations of every env in the batch are rewritten. */
+int sy_reset(SyEnv* env, const uint8_t* reset_mask, const int32_t* init_pos, const int32_t* init_graph_id,
+             int32_t restart, const SyState* state, const SyObs* obs, sy_stream_t stream);
+
+/* replaces CustomEnvironment.step (yard.py:144-269) for the whole batch.
+ * actions int64 [B, A] (device): target node per agent; -1 = DEFAULT_ACTION / None. */
+int sy_step(SyEnv* env, const int64_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
+            sy_stream_t stream);
+
+/* uniform random valid action per agent (Philox(seed; env, step_counter, agent)); -1 when the
+ * agent has no affordable move (gnn_trainer.py:227-229).  The `random policy` of the benchmarks. */
+int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, int64_t* actions,
+                      sy_stream_t stream);
+
+/* replaces compute_action_mask (action_mask.py:30-83) for Q queries on dense float64 inputs
+ * (device pointers): adj [N,N]; weights [N,N] or NULL (adjacency as unit costs, :99-113);
+ * toll_matrix [N,N] or NULL (then toll_scalar is used everywhere, :86-96); cur [Q]; budget [Q];
+ * out [Q, N] bool. */
+int sy_action_mask_dense(int32_t num_queries, int32_t num_nodes, const double* adjacency,
+                         const double* weights, const double* toll_matrix, double toll_scalar,
+                         const int32_t* current_node, const double* budget, uint8_t* out_mask,
+                         sy_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SY_ENV_H */
