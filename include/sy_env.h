@@ -125,6 +125,8 @@ int64_t sy_launch_count(void);
 /* replaces CustomEnvironment.__init__ (yard.py:18-78) */
 int sy_create(const SyConfig* config, SyEnv** out_env);
 void sy_destroy(SyEnv* env);
+/* new Philox key for subsequent (auto-)resets and action sampling (torchrl `set_seed`) */
+int sy_set_seed(SyEnv* env, uint64_t seed);
 
 /* Host-built float64 tables so that rewards are bit-identical to NumPy's:
  * exp_neg[d] = np.exp(-d) (reward_calculator.py:186,199,214), coverage[c] = np.exp(-np.log1p(c))

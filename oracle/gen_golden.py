@@ -232,9 +232,24 @@ def gen_belief():
     np.savez_compressed(os.path.join(OUT, "belief.npz"), **out)
 
 
+def gen_tables():
+    """The float64 tables NumPy produced on the host that generated the golden rewards.
+    NumPy's SIMD exp is not correctly rounded (e.g. exp(-26) differs from libm by 1 ulp on
+    AVX512 hosts), so `bit-exact with the reference` is relative to the host's NumPy; golden
+    replays therefore pass these recorded tables instead of recomputing them."""
+    np.savez_compressed(
+        os.path.join(OUT, "tables.npz"),
+        exp_neg=np.exp(-np.arange(1100, dtype=np.float64)),
+        coverage=np.exp(-np.log1p(np.arange(1024, dtype=np.float64))),
+    )
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["traces", "masks", "belief"]
+    which = sys.argv[1:] or ["tables", "traces", "masks", "belief"]
+    if "tables" in which:
+        gen_tables()
+        print("tables.npz written")
     if "masks" in which:
         gen_masks()
         print("masks.npz written")

@@ -354,6 +354,9 @@ class OracleConfig:
     reveal_interval: int = 0  # 0 -> reference behaviour (MrX always visible)
     toll: int = 0  # 0 -> reference behaviour
     belief: bool = False
+    # optional recorded float64 tables (tests/golden/tables.npz); None -> NumPy on this host
+    exp_table: Optional[np.ndarray] = None
+    cov_table: Optional[np.ndarray] = None
 
 
 class OracleEnv:
@@ -458,6 +461,18 @@ class OracleEnv:
         d = int(self.D[a, b])
         return math.inf if d >= INF_U16 else float(d)
 
+    def _exp_neg(self, d: float):
+        """np.exp(-d) (reward_calculator.py:186,199,214), optionally from the recorded table."""
+        if self.cfg.exp_table is None or math.isinf(d):
+            return np.exp(-d)
+        return np.float64(self.cfg.exp_table[int(d)]) if int(d) < len(self.cfg.exp_table) else np.float64(0.0)
+
+    def _coverage(self, c: int):
+        """np.exp(-np.log1p(c)) (reward_calculator.py:204-205)."""
+        if self.cfg.cov_table is None:
+            return np.exp(-np.log1p(c))
+        return np.float64(self.cfg.cov_table[min(c, len(self.cfg.cov_table) - 1)])
+
     def _terms(self):
         """The float64 quantities reward_calculator.py:126-205 computes before weighting."""
         P = self.P
@@ -474,7 +489,7 @@ class OracleEnv:
         police = []
         for k in range(P):
             p = pos[1 + k]
-            dx = np.exp(-self._dist(p, pos[0]))
+            dx = self._exp_neg(self._dist(p, pos[0]))
             grp = 0
             ov = 0
             prox = 0
@@ -482,14 +497,14 @@ class OracleEnv:
                 if j == k:
                     continue
                 dj = self._dist(p, pos[1 + j])
-                e = np.exp(-dj)
+                e = self._exp_neg(dj)
                 grp = grp + e
                 if dj <= 1:
                     ov = ov + 1.0
                 else:
                     prox = prox + e
             mob = self.n_moves(p, self.money[k])  # QUIRK reward_calculator.py:190: agent index k, not k+1
-            cov = np.exp(-np.log1p(int(self.visits[p])))
+            cov = self._coverage(int(self.visits[p]))
             police.append((dx, grp, mob, 0.05 * t, prox, ov, cov))
         return mrx, police
 

@@ -1,0 +1,92 @@
+"""ctypes binding of include/sy_env.h (libsy_env.so).  No CPU fallback: if the CUDA library
+has not been built this module raises, and so does everything that depends on it."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsy_env.so")
+
+SY_ABI_VERSION = 1
+SY_NUM_REWARD_WEIGHTS = 11
+SY_MAX_AGENTS = 16
+SY_NUM_STATS = 16
+SY_REWARD_FP64, SY_REWARD_FP32 = 0, 1
+STAT_NAMES = [
+    "env_steps", "episodes", "mrx_wins", "police_wins", "truncations", "out_of_money",
+    "sum_episode_length", "sum_budget_spent",
+]
+
+
+class SyConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_int32), ("device", C.c_int32), ("num_envs", C.c_int32), ("num_nodes", C.c_int32),
+        ("num_police", C.c_int32), ("agent_money", C.c_int32), ("mrx_money", C.c_int32), ("max_timestep", C.c_int32),
+        ("reveal_interval", C.c_int32), ("toll", C.c_int32), ("belief", C.c_int32), ("reward_mode", C.c_int32),
+        ("auto_reset", C.c_int32), ("resample_graph", C.c_int32), ("env_offset", C.c_int64), ("seed", C.c_uint64),
+        ("reward_weights", C.c_double * SY_NUM_REWARD_WEIGHTS),
+    ]
+
+
+class SyState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("pos", "money", "timestep", "graph_id", "episode", "done", "visits", "belief")]
+
+
+class SyObs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("action_mask", "node_features", "agent_budget", "mrx_revealed")]
+
+
+class SyOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "reward64", "terminated", "truncated", "done", "winner", "stats")]
+
+
+# name -> (restype, argtypes); must list every function include/sy_env.h declares
+SIGNATURES = {
+    "sy_abi_version": (C.c_int, []),
+    "sy_last_error": (C.c_char_p, []),
+    "sy_launch_count": (C.c_int64, []),
+    "sy_create": (C.c_int, [C.POINTER(SyConfig), C.POINTER(C.c_void_p)]),
+    "sy_destroy": (None, [C.c_void_p]),
+    "sy_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sy_set_reward_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sy_load_graphs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "sy_read_graph_tables": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SyState),
+                           C.POINTER(SyObs), C.c_void_p]),
+    "sy_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
+    "sy_sample_actions": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sy_action_mask_dense": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+class SyError(RuntimeError):
+    pass
+
+
+def load_library() -> C.CDLL:
+    """dlopen libsy_env.so (built in-tree by `__graft_entry__.build()`); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SyError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. There is no CPU fallback."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.sy_abi_version() != SY_ABI_VERSION:
+        raise SyError(f"ABI mismatch: library {lib.sy_abi_version()} vs binding {SY_ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise SyError(f"libsy_env error {rc}: {load_library().sy_last_error().decode()}")

@@ -1,0 +1,399 @@
+"""Batched Scotland Yard environment on one B200: host-side mirror of the reference's
+`CustomEnvironment` (/root/reference/src/environment/yard.py:14-607) over libsy_env.so.
+
+Same constructor names (`number_of_agents`, `agent_money`, `reward_weights`, `logger`, `epoch`,
+`graph_nodes`, `graph_edges`, `vis_configs`), same `reset` / `step` verbs, same observation keys
+(yard.py:319-332 plus `belief_map` / `MrX_revealed`), but every tensor carries a leading batch
+dimension B and lives on the GPU; all per-step work happens in the CUDA kernels of
+csrc/sy_env.cu.  PyTorch is used only to own device memory and streams.
+There is NO CPU fallback: constructing the env without the built library or without a CUDA
+device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .graphs import GraphSpec, generate_graph_pool, pack_csr
+
+# /root/reference/src/reward_net.py:5-17
+REWARD_WEIGHT_NAMES = [
+    "Police_distance", "Police_group", "Police_position", "Police_time", "Mrx_closest", "Mrx_average",
+    "Mrx_position", "Mrx_time", "Police_coverage", "Police_proximity", "Police_overlap_penalty",
+]
+# /root/reference/src/training/evaluator.py:59-71
+DEFAULT_REWARD_WEIGHTS = {
+    "Police_distance": 0.1, "Police_group": 0.1, "Police_position": 0.1, "Police_time": 0.0,
+    "Mrx_closest": 0.3, "Mrx_average": 0.2, "Mrx_position": 0.1, "Mrx_time": 0.0,
+    "Police_coverage": 0.05, "Police_proximity": 0.05, "Police_overlap_penalty": 0.0,
+}
+MAX_MONEY_LIMIT = 1000  # yard.py:11
+N_EXP_TABLE = 1100  # exp(-d) underflows to 0 beyond d = 745
+
+
+def numpy_reward_tables(max_timestep: int = 250):
+    """The two float64 tables the kernels read instead of calling exp/log1p, computed by NumPy
+    on this host so the rewards equal the reference's `np.exp` bit for bit
+    (reward_calculator.py:186,199,204-205,214)."""
+    exp_neg = np.exp(-np.arange(N_EXP_TABLE, dtype=np.float64))
+    coverage = np.exp(-np.log1p(np.arange(max(max_timestep + 8, 16), dtype=np.float64)))
+    return exp_neg, coverage
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class BatchedScotlandYardEnv:
+    """B independent games stepped by one kernel launch.
+
+    Parameters mirror yard.py:18-28; extras: `num_envs`, `graphs` (a pool of GraphSpec, or
+    None to generate `num_graphs` with the reference's distribution), `reveal_interval`,
+    `tolls`, `belief`, `reward_mode` ("fp64" | "fp32" | None = infer from the weight types, as
+    the reference's arithmetic follows them), `seed`, `auto_reset`, `resample_graph`,
+    `env_offset` (global index of env 0 when the batch is sharded over GPUs).
+    """
+
+    DEFAULT_ACTION = -1  # yard.py:16
+    metadata = {"name": "scotland_yard_env_b200"}
+
+    def __init__(self, num_envs: int, number_of_agents: int, agent_money: int, reward_weights: Optional[Dict] = None,
+                 logger=None, epoch: int = 0, graph_nodes: int = 50, graph_edges: Optional[int] = 110, vis_configs=None,
+                 *, graphs: Optional[Sequence[GraphSpec]] = None, num_graphs: int = 1, reveal_interval: int = 0,
+                 tolls: float = 0, belief: bool = False, reward_mode: Optional[str] = None, seed: int = 0,
+                 auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
+                 device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True):
+        if not torch.cuda.is_available():
+            raise _cabi.SyError("BatchedScotlandYardEnv needs a CUDA device; there is no CPU fallback")
+        self._lib = _cabi.load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _cabi.SyError(f"device must be a CUDA device, got {device}")
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        self.logger, self.epoch, self.vis_config = logger, epoch, vis_configs
+        self.num_envs = int(num_envs)
+        self.number_of_agents = int(number_of_agents)  # number of POLICE, yard.py:33
+        self.num_agents = self.number_of_agents + 1
+        self.agent_money = int(agent_money)
+        self.possible_agents = ["MrX"] + [f"Police{i}" for i in range(self.number_of_agents)]  # yard.py:54-56
+        self.agents = list(self.possible_agents)
+        if float(tolls) != int(tolls):
+            raise ValueError("tolls must be integral so budgets stay integers (mechanism.yaml:12 uses 1.0)")
+        reward_weights = dict(DEFAULT_REWARD_WEIGHTS) if reward_weights is None else dict(reward_weights)
+        missing = [k for k in REWARD_WEIGHT_NAMES if k not in reward_weights]
+        if missing:
+            raise KeyError(f"reward_weights lacks {missing}")
+        if reward_mode is None:  # reference arithmetic follows the weight types (gnn_trainer.py:98-110)
+            reward_mode = "fp32" if any(isinstance(v, torch.Tensor) for v in reward_weights.values()) else "fp64"
+        if reward_mode not in ("fp64", "fp32"):
+            raise ValueError("reward_mode must be 'fp64' or 'fp32'")
+        self.reward_mode = reward_mode
+        self.reward_weights = reward_weights
+        wvals = [float(reward_weights[k].detach()) if isinstance(reward_weights[k], torch.Tensor) else float(reward_weights[k])
+                 for k in REWARD_WEIGHT_NAMES]
+
+        # ---- graph pool
+        if graphs is None:
+            graphs = generate_graph_pool(num_graphs, graph_nodes, graph_edges, seed=seed)
+        self.graphs: List[GraphSpec] = list(graphs)
+        self.graph_nodes = self.graphs[0].num_nodes
+        self.graph_edges = graph_edges
+        self.actual_num_edges = len(self.graphs[0].edges)  # yard.py:70
+        self.num_graphs = len(self.graphs)
+        N, A, B = self.graph_nodes, self.num_agents, self.num_envs
+
+        cfg = _cabi.SyConfig()
+        cfg.struct_bytes = C.sizeof(_cabi.SyConfig)
+        cfg.device, cfg.num_envs, cfg.num_nodes, cfg.num_police = dev_index, B, N, self.number_of_agents
+        cfg.agent_money, cfg.mrx_money, cfg.max_timestep = self.agent_money, MAX_MONEY_LIMIT, int(max_timestep)
+        cfg.reveal_interval, cfg.toll, cfg.belief = int(reveal_interval or 0), int(tolls), int(bool(belief))
+        cfg.reward_mode = _cabi.SY_REWARD_FP32 if reward_mode == "fp32" else _cabi.SY_REWARD_FP64
+        cfg.auto_reset, cfg.resample_graph = int(bool(auto_reset)), int(bool(resample_graph))
+        cfg.env_offset, cfg.seed = int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
+        for i, v in enumerate(wvals):
+            cfg.reward_weights[i] = v
+        self.config = cfg
+        self.reveal_interval, self.tolls, self.belief_on = cfg.reveal_interval, cfg.toll, bool(cfg.belief)
+        self.auto_reset, self.seed, self.env_offset = bool(auto_reset), int(seed), int(env_offset)
+
+        self._handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_create(C.byref(cfg), C.byref(self._handle)))
+            stream = self._stream()
+            exp_neg, coverage = reward_tables if reward_tables is not None else numpy_reward_tables(max_timestep)
+            exp_neg = np.ascontiguousarray(exp_neg, dtype=np.float64)
+            coverage = np.ascontiguousarray(coverage, dtype=np.float64)
+            _cabi.check(self._lib.sy_set_reward_tables(self._handle, exp_neg.ctypes.data, len(exp_neg),
+                                                       coverage.ctypes.data, len(coverage), stream))
+            row_ptr, col, wgt, stride = pack_csr(self.graphs)
+            self._csr = (row_ptr, col, wgt)
+            _cabi.check(self._lib.sy_load_graphs(self._handle, self.num_graphs, row_ptr.ctypes.data, col.ctypes.data,
+                                                 wgt.ctypes.data, stride, stream))
+
+            dev = self.device
+            z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+            self.pos = z(B, A, dtype=torch.int32)
+            self.money = z(B, A, dtype=torch.int32)
+            self.timestep = z(B, dtype=torch.int32)
+            self.graph_id = z(B, dtype=torch.int32)
+            self.episode = z(B, dtype=torch.int32)
+            self.done = z(B, dtype=torch.uint8)
+            self.visits = z(B, N, dtype=torch.uint16)
+            self.belief_map = z(B, N, dtype=torch.float32) if self.belief_on else None
+            self.action_mask = z(B, A, N, dtype=torch.bool)
+            self.node_features = z(B, N, A, dtype=torch.float32)
+            self.agent_budget = z(B, A, dtype=torch.float32)
+            self.mrx_revealed = z(B, dtype=torch.int32)
+            self.reward = z(B, A, dtype=torch.float32)
+            self.reward64 = z(B, A, dtype=torch.float64) if keep_reward64 else None
+            self.terminated = z(B, A, dtype=torch.bool)
+            self.truncated = z(B, A, dtype=torch.bool)
+            self.done_flags = z(B, A, dtype=torch.bool)
+            self.winner = z(B, dtype=torch.int8)
+            self.stats_vec = z(_cabi.SY_NUM_STATS, dtype=torch.int64) if collect_stats else None
+        self._state = _cabi.SyState(_ptr(self.pos), _ptr(self.money), _ptr(self.timestep), _ptr(self.graph_id),
+                                    _ptr(self.episode), _ptr(self.done), _ptr(self.visits), _ptr(self.belief_map))
+        self._obs = _cabi.SyObs(_ptr(self.action_mask), _ptr(self.node_features), _ptr(self.agent_budget),
+                                _ptr(self.mrx_revealed))
+        self._out = _cabi.SyOut(_ptr(self.reward), _ptr(self.reward64), _ptr(self.terminated), _ptr(self.truncated),
+                                _ptr(self.done_flags), _ptr(self.winner), _ptr(self.stats_vec))
+        self._static = None
+        self._sample_counter = 0
+        self._is_reset = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle:
+            self._lib.sy_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _dev(self, x, dtype, shape):
+        t = torch.as_tensor(x)
+        t = t.to(device=self.device, dtype=dtype).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        return t
+
+    def set_seed(self, seed: int):
+        self.seed = int(seed)
+        self.config.seed = self.seed & 0xFFFFFFFFFFFFFFFF
+        _cabi.check(self._lib.sy_set_seed(self._handle, self.config.seed))
+
+    # ------------------------------------------------------------------ reference API, batched
+    def reset(self, reset_mask=None, init_pos=None, graph_id=None, restart: Optional[bool] = None, episode=0,
+              seed=None, options=None):
+        """yard.py:80-142 for the envs selected by `reset_mask` ([B] bool; None = all).
+        `init_pos` [B, A] / `graph_id` [B] hand over explicit start nodes / graphs (parity
+        harness); otherwise Philox(seed; env, episode).  Returns the observation dict."""
+        B, A = self.num_envs, self.num_agents
+        if seed is not None:  # the reference ignores `seed` (yard.py:80); here it re-keys Philox
+            self.set_seed(seed)
+            restart = True if restart is None else restart
+        m = None if reset_mask is None else self._dev(reset_mask, torch.uint8, (B,))
+        ip = None if init_pos is None else self._dev(init_pos, torch.int32, (B, A))
+        gi = None if graph_id is None else self._dev(graph_id, torch.int32, (B,))
+        if gi is not None and (int(gi.min()) < 0 or int(gi.max()) >= self.num_graphs):
+            raise ValueError("graph_id out of range")
+        if ip is not None and (int(ip.min()) < 0 or int(ip.max()) >= self.graph_nodes):
+            raise ValueError("init_pos out of range")
+        if restart is None:
+            restart = not self._is_reset
+        if not self._is_reset and m is not None:
+            raise _cabi.SyError("the first reset must cover every env")
+        if gi is None and not self._is_reset and not self.config.resample_graph:
+            gi = (torch.arange(B, device=self.device, dtype=torch.int64) + self.env_offset).remainder(self.num_graphs).to(torch.int32)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_reset(self._handle, _ptr(m), _ptr(ip), _ptr(gi), int(bool(restart)),
+                                           C.byref(self._state), C.byref(self._obs), self._stream()))
+        self._is_reset = True
+        self._keep = (m, ip, gi)  # keep inputs alive until the stream has consumed them
+        return self.observation()
+
+    def step(self, actions):
+        """yard.py:144-269 for the whole batch.  `actions`: int64 [B, A] (device tensor preferred),
+        -1 = DEFAULT_ACTION/None.  Returns (obs, reward f32[B,A], terminated, truncated bool[B,A], info)."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == torch.int64 and a.is_contiguous()
+                and tuple(a.shape) == (self.num_envs, self.num_agents)):
+            a = self._dev(actions, torch.int64, (self.num_envs, self.num_agents))
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_step(self._handle, a.data_ptr(), C.byref(self._state), C.byref(self._obs),
+                                          C.byref(self._out), self._stream()))
+        self._last_actions = a
+        info = {"winner": self.winner, "done": self.done_flags}
+        return self.observation(), self.reward, self.terminated, self.truncated, info
+
+    def sample_actions(self, out: Optional[torch.Tensor] = None, step_counter: Optional[int] = None) -> torch.Tensor:
+        """Uniform random valid action per agent on the device (-1 when an agent cannot move)."""
+        if out is None:
+            out = torch.empty(self.num_envs, self.num_agents, dtype=torch.int64, device=self.device)
+        if step_counter is None:
+            step_counter = self._sample_counter
+            self._sample_counter += 1
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_sample_actions(self._handle, C.byref(self._state), int(step_counter) & 0xFFFFFFFF,
+                                                    out.data_ptr(), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ observations
+    def _static_tensors(self):
+        if self._static is None:
+            N, G = self.graph_nodes, self.num_graphs
+            row_ptr, col, wgt = self._csr
+            adj = torch.zeros(G, N, N, dtype=torch.float32)
+            for g in range(G):
+                deg = np.diff(row_ptr[g])
+                rows = np.repeat(np.arange(N), deg)
+                adj[g, torch.from_numpy(rows), torch.from_numpy(col[g, : row_ptr[g, -1]].astype(np.int64))] = 1.0
+            same_e = all(len(g.edges) == self.actual_num_edges for g in self.graphs)
+            if same_e:
+                ei = torch.from_numpy(np.stack([g.edge_links.T for g in self.graphs]).astype(np.int64))  # [G,2,E]
+                ef = torch.from_numpy(np.stack([g.edges for g in self.graphs]).astype(np.int64))  # [G,E]
+            else:
+                ei = ef = None
+            self._static = (adj.to(self.device), None if ei is None else ei.to(self.device),
+                            None if ef is None else ef.to(self.device))
+        return self._static
+
+    def observation(self) -> Dict[str, torch.Tensor]:
+        """yard.py:319-332 keys with a leading batch dim.  Static graph tensors are stride-0 /
+        gathered views of one copy per graph; dynamic ones are the buffers the kernel wrote."""
+        adj, ei, ef = self._static_tensors()
+        B = self.num_envs
+        if self.num_graphs == 1:
+            adjacency = adj.expand(B, -1, -1)
+            edge_index = None if ei is None else ei.expand(B, -1, -1)
+            edge_features = None if ef is None else ef.expand(B, -1)
+        else:
+            gid = self.graph_id.long()
+            adjacency = _LazyGather(adj, gid)
+            edge_index = None if ei is None else _LazyGather(ei, gid)
+            edge_features = None if ef is None else _LazyGather(ef, gid)
+        obs = {
+            "adjacency_matrix": adjacency,
+            "node_features": self.node_features,
+            "edge_index": edge_index,
+            "edge_features": edge_features,
+            "action_mask": self.action_mask,
+            "agent_position": self.pos,
+            "agent_budget": self.agent_budget.unsqueeze(-1),
+            "MrX_pos": self.pos[:, 0],
+            "Polices_pos": self.pos[:, 1:],
+            "Currency": self.money[:, 1:],
+            "MrX_revealed": self.mrx_revealed,
+            "graph_id": self.graph_id,
+        }
+        if self.belief_on:
+            obs["belief_map"] = self.belief_map
+        return obs
+
+    # ------------------------------------------------------------------ helpers callers use
+    def action_space_n(self) -> int:
+        return self.graph_nodes  # Discrete(num_nodes), yard.py:482-498
+
+    def get_possible_moves(self, agent_idx: int, env_index: int = 0) -> np.ndarray:
+        """yard.py:474-480 as a view of the action mask."""
+        return torch.nonzero(self.action_mask[env_index, agent_idx]).flatten().to(torch.int32).cpu().numpy()
+
+    def graph_tables(self, g: int = 0):
+        """(weights u8[N,N], apsp u16[N,N]) of graph g copied to the host (get_distance parity)."""
+        N = self.graph_nodes
+        W = np.zeros((N, N), dtype=np.uint8)
+        D = np.zeros((N, N), dtype=np.uint16)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_read_graph_tables(self._handle, int(g), W.ctypes.data, D.ctypes.data, self._stream()))
+        return W, D
+
+    def get_distance(self, node1: int, node2: int, g: int = 0) -> float:
+        """yard.py:375-388 / pathfinding.py:34-137 from the device-built table."""
+        d = int(self.graph_tables(g)[1][node1, node2])
+        return float("inf") if d == 0xFFFF else float(d)
+
+    def stats(self, reduce_group=None) -> Dict[str, int]:
+        """Episode statistics accumulated on the device; with `reduce_group` (or an initialised
+        default process group and reduce_group=True) they are summed over ranks with one
+        all-reduce (NCCL over NVLink on a GPU box)."""
+        if self.stats_vec is None:
+            raise _cabi.SyError("collect_stats=False")
+        v = self.stats_vec
+        if reduce_group is not None:
+            import torch.distributed as dist
+
+            v = v.clone()
+            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=None if reduce_group is True else reduce_group)
+        h = v.cpu().tolist()
+        return {k: int(h[i]) for i, k in enumerate(_cabi.STAT_NAMES)}
+
+    def reset_stats(self):
+        if self.stats_vec is not None:
+            self.stats_vec.zero_()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        keys = ["pos", "money", "timestep", "graph_id", "episode", "done", "visits", "belief_map", "action_mask",
+                "node_features", "agent_budget", "mrx_revealed", "stats_vec"]
+        return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        for k, v in sd.items():
+            getattr(self, k).copy_(v)
+        self._is_reset = True
+
+
+class _LazyGather:
+    """Per-env view of a per-graph tensor, materialised only when a caller indexes it."""
+
+    def __init__(self, table: torch.Tensor, gid: torch.Tensor):
+        self.table, self.gid = table, gid
+        self.shape = (gid.shape[0],) + tuple(table.shape[1:])
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            return self.table[self.gid[idx[0]]][(slice(None),) + idx[1:]] if not isinstance(idx[0], int) else \
+                self.table[self.gid[idx[0]]][idx[1:]]
+        return self.table[self.gid[idx]]
+
+    def materialize(self) -> torch.Tensor:
+        return self.table[self.gid]
+
+
+def dense_action_mask(adjacency, current_node, budget, tolls=None, edge_weights=None, device="cuda:0") -> torch.Tensor:
+    """Batched drop-in for compute_action_mask (action_mask.py:30-83) on dense float64 inputs.
+    `current_node` [Q], `budget` [Q]; tolls: None | scalar | [N] per destination | [N,N]."""
+    lib = _cabi.load_library()
+    dev = torch.device(device)
+    adj = torch.as_tensor(np.asarray(adjacency), dtype=torch.float64, device=dev).contiguous()
+    N = adj.shape[0]
+    w = None if edge_weights is None else torch.as_tensor(np.asarray(edge_weights, dtype=float), dtype=torch.float64, device=dev).contiguous()
+    toll_s, toll_m = 0.0, None
+    if tolls is not None:
+        if np.isscalar(tolls):
+            toll_s = float(tolls)
+        else:
+            t = np.asarray(tolls, dtype=float)
+            if t.ndim == 1:
+                t = np.tile(t.reshape(1, -1), (N, 1))  # action_mask.py:92-95
+            toll_m = torch.as_tensor(t, dtype=torch.float64, device=dev).contiguous()
+    cur = torch.as_tensor(np.atleast_1d(current_node), dtype=torch.int32, device=dev).contiguous()
+    bud = torch.as_tensor(np.atleast_1d(budget), dtype=torch.float64, device=dev).contiguous()
+    out = torch.zeros(cur.shape[0], N, dtype=torch.bool, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(lib.sy_action_mask_dense(cur.shape[0], N, adj.data_ptr(), _ptr(w), _ptr(toll_m), toll_s,
+                                             cur.data_ptr(), bud.data_ptr(), out.data_ptr(),
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    return out
