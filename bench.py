@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""Benchmark of the batched Scotland Yard env hot path (BASELINE.json metric: batched env-steps/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm: the oracle port on the host cores
+
+One "step" = one pass of the hot path over the rank's whole batch: the on-device random-valid
+policy (`sy_sample_actions`) + `sy_step` (dynamics, budgets/tolls, capture/termination, rewards,
+reveal schedule, belief propagation, observation assembly, same-step auto-reset).  Workload at
+N=1 is BASELINE config 3 (200 nodes, 6 police, budgets+tolls, belief on, 65 536 envs); with N
+GPUs every rank holds its own 65 536 envs (weak scaling, batch sharded by env index, no data-path
+collective; one NCCL all-reduce of the statistics vector closes the timed region).
+
+Keys of the JSON line (see DESIGN.md "Measurement"): `value` = device-resident throughput;
+`e2e` = the same metric through the host-buffer API (`step_host`: pinned host actions -> H2D ->
+kernel -> D2H of rewards/flags, every step, synchronised); `roofline` = algorithmic bytes of
+`sy_step_kernel` (8849 B/env-step at c3) / its CUDA-event duration / measured HBM
+peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, E, P, money, toll, belief, reveal, B per GPU
+    "c2": dict(N=50, E=110, P=3, money=10, toll=0, belief=False, reveal=5, B=1024,
+               desc="50-node graph, 3 police, reveal every 5 steps, 1024 envs, random policy"),
+    "c3": dict(N=200, E=400, P=6, money=20, toll=1, belief=True, reveal=5, B=65536,
+               desc="200-node graph, 6 police, budgets+tolls, 65536 envs per GPU, belief_map on, reveal every 5"),
+    "c4": dict(N=1000, E=2000, P=6, money=20, toll=1, belief=True, reveal=5, B=32768,
+               desc="1000-node synthetic random graph, 6 police, 32768 envs per GPU (262144 over 8)"),
+}
+METRIC, UNIT = "batched_env_steps_per_sec", "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(N, P, belief):
+    """actions R + pos/money/t R+W + visit RMW + belief R+W + reward/flags W
+    + action_mask W + node_features W (static graph tables are L2-resident and excluded)."""
+    A = P + 1
+    return 8 * A + 2 * (4 * A + 4 * A + 4) + 2 * 2 * P + (2 * 4 * N if belief else 0) + 4 * A + 3 * A + A * N + 4 * N * A
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi/NVML clocks + throttle reasons sampled DURING the timed regions."""
+
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.active, self.stop = [], set(), False, False
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while not self.stop:
+            if self.nv is not None and self.active:
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    get = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                        self.nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                    r = get(self.h)
+                    for bit, name in self.BITS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def summary(self):
+        self.stop = True
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (the reference itself is Python and does not travel to the GPU box)
+# --------------------------------------------------------------------------------------------
+def cpu_oracle_throughput(wl, budget_s, all_cores):
+    """env-steps/s of the CPU oracle on a bounded sample of the workload.  Prefers the C restatement
+    (oracle/sy_oracle.c, OpenMP over envs) and falls back to the numpy/Python one (1 core)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+
+    from student_mechanism_design_b200.graphs import generate_graph_pool
+
+    pool = generate_graph_pool(1, wl["N"], wl["E"], seed=0)
+    try:
+        import sy_oracle_c as oc
+
+        have_c = oc.available()
+    except Exception:
+        have_c = False
+    if have_c:
+        cores = (os.cpu_count() or 1) if all_cores else 1
+        B = 4096 * max(1, min(cores, 16))
+        run = oc.CBatch(wl, pool[0], B, seed=0, threads=cores)
+        run.steps(3)
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s:
+            run.steps(5)
+            n += 5
+        dt = time.perf_counter() - t0
+        return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
+                    sample=f"C oracle (oracle/sy_oracle.c, OpenMP), {B} envs x {n} steps of {wl['name']}, {dt:.1f} s")
+    import sy_oracle as so
+
+    B = 64
+    cfg = so.OracleConfig(num_police=wl["P"], agent_money=wl["money"], toll=wl["toll"], belief=wl["belief"],
+                          reveal_interval=wl["reveal"])
+    ob = so.OracleBatch.from_seed(cfg, [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in pool], B, seed=0)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        acts = ob.sample_actions(n)
+        ob.step(acts)
+        ob.masks(), ob.node_features()
+        n += 1
+    dt = time.perf_counter() - t0
+    return dict(value=B * n / dt, unit=UNIT, cores=1, kind="port",
+                sample=f"numpy/Python oracle (oracle/sy_oracle.py), {B} envs x {n} steps of {wl['name']}, {dt:.1f} s")
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step_s = 2.0
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        last = cpu_oracle_throughput(wl, per_step_s if i >= args.warmup else 0.5, all_cores=True)
+        if i >= args.warmup:
+            vals.append(last["value"])
+        if len(vals) * per_step_s > 120:
+            break
+    v = statistics.mean(vals)
+    last["value"] = v
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": args.warmup, "ms_per_step": per_step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+        "config": {"workload": f"{wl['name']}: {wl['desc']}", "note": "CPU arm = oracle port of the reference env "
+                   "(the reference is Python and cannot run on the GPU box); each step is a bounded 2 s sample"},
+        "cpu_baseline": last,
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA arm
+# --------------------------------------------------------------------------------------------
+def run_cuda_arm(args, wl):
+    import torch
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        ge.build()
+    if dist is not None:
+        dist.barrier()
+    from student_mechanism_design_b200 import BatchedScotlandYardEnv, _cabi
+
+    lib = _cabi.load_library()
+    N, P, B = wl["N"], wl["P"], args.envs or wl["B"]
+    A = P + 1
+    env = BatchedScotlandYardEnv(B, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], num_graphs=1, seed=0,
+                                 tolls=wl["toll"], belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True,
+                                 env_offset=rank * B, device=f"cuda:{local}")
+    env.reset()
+    dev = env.device
+    actions = torch.empty(B, A, dtype=torch.int64, device=dev)
+    K, W = args.steps, args.warmup
+    sampler = ClockSampler(local)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput (`value`)
+    counter = 0
+    for _ in range(W):
+        env.sample_actions(out=actions, step_counter=counter)
+        env.step(actions)
+        counter += 1
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    sampler.active = True
+    launches0 = lib.sy_launch_count()
+    ev0.record()
+    for k in range(K):
+        env.sample_actions(out=actions, step_counter=counter)
+        kev[k][0].record()
+        env.step(actions)
+        kev[k][1].record()
+        counter += 1
+    stats_total = env.stats(reduce_group=True if dist is not None else None)  # the one collective (NCCL)
+    ev1.record()
+    barrier()
+    sampler.active = False
+    launches = lib.sy_launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    value = world * B * K / (ms_total * 1e-3)
+
+    # ---- end to end through the host-buffer API
+    Ke = max(3, min(K, args.e2e_steps))
+    for _ in range(3):
+        env.step_host(env.sample_actions_host(step_counter=counter))
+        counter += 1
+    barrier()
+    sampler.active = True
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(Ke):
+        host_actions = env.sample_actions_host(step_counter=counter)  # the "policy" hands over HOST actions
+        res = env.step_host(host_actions)  # H2D actions, kernel, D2H reward/flags, synchronised
+        counter += 1
+    ev1.record()
+    barrier()
+    sampler.active = False
+    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
+    e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": env.host_h2d_bytes_per_step, "d2h_bytes_per_step": env.host_d2h_bytes_per_step,
+           "steps": Ke, "note": "actions int64[B,A] from pinned host memory in; reward f32 + terminated/truncated/done "
+           "u8 [B,A] + winner out to pinned host memory; observations stay on the device for the GPU policy; the D2H "
+           "count includes the random policy's actions coming back to the host"}
+
+    clocks = sampler.summary()
+    if rank == 0:
+        bstep = algorithmic_bytes_per_env_step(N, P, wl["belief"])
+        peak, peak_src = measured_hbm_peak()
+        achieved = bstep * B / (step_kernel_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+        if os.path.isfile(tp):
+            try:
+                traffic = json.load(open(tp)).get(wl["name"], {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32/f64", "data": "synthetic",
+            "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
+                       "envs_per_gpu": B, "global_envs": world * B, "policy": "on-device Philox random valid",
+                       "auto_reset": True, "parallelism": f"batch-sharded x{world}",
+                       "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "sy_step_kernel", "kernel_ms": step_kernel_ms,
+                         "algorithmic_bytes_per_env_step": bstep, "peak_source": peak_src},
+            "episode_stats": stats_total,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_oracle_throughput(wl, args.cpu_seconds, all_cores=True)
+        print(json.dumps(line), flush=True)
+    env.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    wl = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_cuda_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,22 @@ int sy_reset(SyEnv* env, const uint8_t* reset_mask, const int32_t* init_pos, con
 int sy_step(SyEnv* env, const int64_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
             sy_stream_t stream);
 
+/* HOST pointers (pinned memory recommended) that `sy_step_host` fills; any member may be NULL. */
+typedef struct SyHostOut {
+  float* reward;       /* [B, A] */
+  uint8_t* terminated; /* [B, A] */
+  uint8_t* truncated;  /* [B, A] */
+  uint8_t* done;       /* [B, A] */
+  int8_t* winner;      /* [B] */
+} SyHostOut;
+
+/* Host-buffer form of sy_step, the shape of the reference's own call (yard.py:144: python ints in,
+ * python dicts out): copies actions_host [B, A] to the caller's device staging buffer actions_dev,
+ * runs the step, copies rewards / flags / winner back into host_out and SYNCHRONISES the stream.
+ * Observations stay in the caller's device buffers (SyObs) for a device-side policy. */
+int sy_step_host(SyEnv* env, const int64_t* actions_host, int64_t* actions_dev, const SyState* state,
+                 const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
+
 /* uniform random valid action per agent (Philox(seed; env, step_counter, agent)); -1 when the
  * agent has no affordable move (gnn_trainer.py:227-229).  The `random policy` of the benchmarks. */
 int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, int64_t* actions,

@@ -41,6 +41,10 @@ class SyOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("reward", "reward64", "terminated", "truncated", "done", "winner", "stats")]
 
 
+class SyHostOut(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "truncated", "done", "winner")]
+
+
 # name -> (restype, argtypes); must list every function include/sy_env.h declares
 SIGNATURES = {
     "sy_abi_version": (C.c_int, []),
@@ -55,6 +59,8 @@ SIGNATURES = {
     "sy_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SyState),
                            C.POINTER(SyObs), C.c_void_p]),
     "sy_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
+    "sy_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut),
+                               C.POINTER(SyHostOut), C.c_void_p]),
     "sy_sample_actions": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_action_mask_dense": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -1008,6 +1008,24 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   return SY_OK;
 }
 
+int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, const SyState* st, const SyObs* ob,
+                 const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
+  if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)e->cfg.num_envs * e->A;
+  CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  const int rc = sy_step(e, actions_dev, st, ob, out, stream);
+  if (rc) return rc;
+  if (ho->reward) CUDA_TRY(cudaMemcpyAsync(ho->reward, out->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (ho->terminated) CUDA_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, n, cudaMemcpyDeviceToHost, s));
+  if (ho->truncated) CUDA_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, n, cudaMemcpyDeviceToHost, s));
+  if (ho->done) CUDA_TRY(cudaMemcpyAsync(ho->done, out->done, n, cudaMemcpyDeviceToHost, s));
+  if (ho->winner) CUDA_TRY(cudaMemcpyAsync(ho->winner, out->winner, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return SY_OK;
+}
+
 int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_t* actions, sy_stream_t stream) {
   if (!e || !actions) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   Params p;

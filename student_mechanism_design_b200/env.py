@@ -251,6 +251,57 @@ class BatchedScotlandYardEnv:
                                                     out.data_ptr(), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ host-buffer API (the reference's call shape)
+    def _host_buffers(self):
+        if getattr(self, "_host", None) is None:
+            B, A = self.num_envs, self.num_agents
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, pin_memory=True)  # noqa: E731
+            self._host = dict(reward=pin(B, A, dtype=torch.float32), terminated=pin(B, A, dtype=torch.bool),
+                              truncated=pin(B, A, dtype=torch.bool), done=pin(B, A, dtype=torch.bool),
+                              winner=pin(B, dtype=torch.int8), actions=pin(B, A, dtype=torch.int64))
+            self._actions_dev = torch.empty(B, A, dtype=torch.int64, device=self.device)
+            self._host_out = _cabi.SyHostOut(*[self._host[k].data_ptr() for k in
+                                               ("reward", "terminated", "truncated", "done", "winner")])
+        return self._host
+
+    @property
+    def host_h2d_bytes_per_step(self) -> int:
+        return self.num_envs * self.num_agents * 8
+
+    @property
+    def host_d2h_bytes_per_step(self) -> int:
+        """step_host results (+ the sampled actions when sample_actions_host feeds it)"""
+        B, A = self.num_envs, self.num_agents
+        return B * A * (4 + 3) + B + B * A * 8
+
+    def step_host(self, actions) -> Dict[str, torch.Tensor]:
+        """`step` with HOST buffers on both sides, as the reference's env is called (python ints in,
+        numpy/python values out, yard.py:144,269): actions int64 [B, A] in host memory (pinned is
+        fastest) -> H2D -> kernel -> D2H of reward / terminated / truncated / done / winner into
+        pinned host tensors; synchronous.  Observations stay on the device (`observation()`)."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        host = self._host_buffers()
+        a = torch.as_tensor(actions)
+        if a.is_cuda or a.dtype != torch.int64 or not a.is_contiguous() or \
+                tuple(a.shape) != (self.num_envs, self.num_agents):
+            a = torch.as_tensor(np.asarray(a.cpu() if a.is_cuda else a), dtype=torch.int64).contiguous()
+            if tuple(a.shape) != (self.num_envs, self.num_agents):
+                raise ValueError(f"expected shape {(self.num_envs, self.num_agents)}, got {tuple(a.shape)}")
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_step_host(self._handle, a.data_ptr(), self._actions_dev.data_ptr(),
+                                               C.byref(self._state), C.byref(self._obs), C.byref(self._out),
+                                               C.byref(self._host_out), self._stream()))
+        return {k: host[k] for k in ("reward", "terminated", "truncated", "done", "winner")}
+
+    def sample_actions_host(self, step_counter: Optional[int] = None) -> torch.Tensor:
+        """random valid actions delivered in pinned HOST memory (stands in for a host-side policy)"""
+        host = self._host_buffers()
+        dev_actions = self.sample_actions(out=self._actions_dev, step_counter=step_counter)
+        host["actions"].copy_(dev_actions, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return host["actions"]
+
     # ------------------------------------------------------------------ observations
     def _static_tensors(self):
         if self._static is None:

@@ -1,0 +1,432 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, via the host mirror) against
+(i) the vectors recorded from the UNMODIFIED reference (tests/golden/*.npz) and (ii) the CPU
+oracle on the same seeded inputs.  Bar: bit-exact for positions, budgets, masks, flags, visit
+counts and rewards (fp64 and fp32 modes); belief_map within 1e-6 abs (north_star)."""
+import os
+
+import numpy as np
+import pytest
+
+import sy_oracle as so
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+BELIEF_TOL = 1e-6  # north_star: "belief_map must match within 1e-6 abs"
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def tables():
+    t = np.load(os.path.join(GOLDEN, "tables.npz"))
+    return t["exp_neg"], t["coverage"]
+
+
+def _pkg():
+    import student_mechanism_design_b200 as pkg
+
+    return pkg
+
+
+def _trace(gt, name):
+    keys = ["edge_links", "edges", "start", "obs0_mask", "actions", "pos", "money", "masks", "reward", "reward32",
+            "terminated", "truncated", "winner", "visits_at_police", "final_visits", "weights", "config"]
+    return {k: gt[f"{name}/{k}"] for k in keys}
+
+
+def _groups(gt):
+    """golden traces grouped into batches that can share one env handle"""
+    groups = {}
+    for n in [str(x) for x in gt["names"]]:
+        t = _trace(gt, n)
+        seed, N, E, P, money = [int(x) for x in t["config"]]
+        key = (N, P, money, t["weights"].tobytes(), t["edge_links"].shape[0])
+        groups.setdefault(key, []).append(t)
+    return list(groups.values())
+
+
+def test_library_loaded_is_in_tree(torch_cuda):
+    pkg = _pkg()
+    lib = pkg.load_library()
+    assert os.path.dirname(pkg.LIB_PATH).endswith("student_mechanism_design_b200")
+    assert lib.sy_abi_version() == 1
+
+
+def test_graph_tables_match_oracle(torch_cuda, golden_traces):
+    """sy_load_graphs: dense weights (yard.py:404-418) and the all-pairs table that replaces
+    Pathfinder.get_distance (pathfinding.py:34-137), incl. the 200-node golden graph."""
+    pkg = _pkg()
+    gt = golden_traces
+    names = [str(x) for x in gt["names"]]
+    for n in names[::9] + [names[-1]]:
+        t = _trace(gt, n)
+        N, P = int(t["config"][1]), int(t["config"][3])
+        g = so.Graph(N, t["edge_links"], t["edges"])
+        env = pkg.BatchedScotlandYardEnv(1, P, 5, graphs=[pkg.GraphSpec(N, t["edge_links"], t["edges"])])
+        W, D = env.graph_tables(0)
+        assert np.array_equal(W.astype(np.int64), g.weight_matrix()), n
+        assert np.array_equal(D.astype(np.int64), g.apsp()), n
+        assert env.get_distance(0, 0) == 0.0
+        env.close()
+
+
+def test_apsp_disconnected_graph(torch_cuda):
+    """pathfinding.py:133-137: unreachable -> inf (0xFFFF in the table)."""
+    pkg = _pkg()
+    g = pkg.GraphSpec(6, [[0, 1], [1, 2], [3, 4]], [2, 3, 1])
+    env = pkg.BatchedScotlandYardEnv(1, 1, 5, graphs=[g])
+    _, D = env.graph_tables(0)
+    assert D[0, 2] == 5 and D[3, 4] == 1 and D[0, 3] == 0xFFFF and D[5, 0] == 0xFFFF and D[5, 5] == 0
+    assert env.get_distance(0, 5) == float("inf")
+    env.close()
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_golden_trace_replay(torch_cuda, golden_traces, tables, mode):
+    """Replay of the reference's recorded episodes (yard.py:144-269, reward_calculator.py:26-266,
+    action_mask.py:54-83): every step bit-exact, batched with one graph per env."""
+    torch = torch_cuda
+    pkg = _pkg()
+    total = 0
+    for group in _groups(golden_traces):
+        t0 = group[0]
+        seed, N, E, P, money = [int(x) for x in t0["config"]]
+        A, B = P + 1, len(group)
+        weights = dict(zip(so.REWARD_WEIGHT_NAMES, t0["weights"].tolist()))
+        graphs = [pkg.GraphSpec(N, t["edge_links"], t["edges"]) for t in group]
+        env = pkg.BatchedScotlandYardEnv(B, P, money, weights, graphs=graphs, reward_mode=mode, reward_tables=tables,
+                                         keep_reward64=True)
+        start = np.stack([t["start"] for t in group])
+        obs = env.reset(init_pos=start, graph_id=np.arange(B))
+        assert np.array_equal(obs["action_mask"].cpu().numpy(), np.stack([t["obs0_mask"] for t in group]))
+        assert np.array_equal(obs["agent_position"].cpu().numpy(), start)
+        lens = [len(t["actions"]) for t in group]
+        for s in range(max(lens)):
+            acts = np.full((B, A), -1, dtype=np.int64)
+            for b, t in enumerate(group):
+                if s < lens[b]:
+                    acts[b] = t["actions"][s]
+            obs, rew, term, trunc, info = env.step(torch.from_numpy(acts).cuda())
+            pos, mon = env.pos.cpu().numpy(), env.money.cpu().numpy()
+            mask = obs["action_mask"].cpu().numpy()
+            r32, r64 = rew.cpu().numpy(), env.reward64.cpu().numpy()
+            te, tr, win = term.cpu().numpy(), trunc.cpu().numpy(), info["winner"].cpu().numpy()
+            nf = obs["node_features"].cpu().numpy()
+            vis = env.visits.cpu().numpy()
+            for b, t in enumerate(group):
+                if s >= lens[b]:
+                    continue
+                tag = (int(t["config"][0]), s)
+                assert pos[b].tolist() == t["pos"][s].tolist(), tag
+                assert mon[b].tolist() == t["money"][s].tolist(), tag
+                want_mask = np.unpackbits(t["masks"][s], axis=-1)[..., :N].astype(bool)
+                assert np.array_equal(mask[b], want_mask), tag
+                assert bool(te[b, 0]) == bool(t["terminated"][s]) and bool(tr[b, 0]) == bool(t["truncated"][s]), tag
+                assert te[b].all() == te[b].any() and tr[b].all() == tr[b].any(), tag
+                assert int(win[b]) == int(t["winner"][s]), tag
+                if mode == "fp64":
+                    assert r64[b].tobytes() == t["reward"][s].tobytes(), (tag, r64[b], t["reward"][s])
+                    assert r32[b].tobytes() == t["reward"][s].astype(np.float32).tobytes(), tag
+                else:
+                    assert r32[b].tobytes() == t["reward32"][s].tobytes(), (tag, r32[b], t["reward32"][s])
+                assert [int(vis[b, p]) for p in pos[b, 1:]] == t["visits_at_police"][s].tolist(), tag
+                assert nf[b].sum() == A and all(nf[b, pos[b, a], a] == 1 for a in range(A)), tag
+                if s == lens[b] - 1:
+                    assert np.array_equal(vis[b].astype(np.int64), t["final_visits"]), tag
+                total += 1
+        env.close()
+    assert total > 800
+
+
+CASES = [
+    # N, E, P, money, G, B, kw, mode, steps
+    dict(N=15, E=20, P=2, money=10, G=3, B=200, kw={}, mode="fp64", steps=40),
+    dict(N=50, E=110, P=3, money=10, G=2, B=97, kw=dict(reveal_interval=5), mode="fp32", steps=40),
+    dict(N=30, E=55, P=6, money=12, G=4, B=130, kw=dict(reveal_interval=3, tolls=1, belief=True), mode="fp64", steps=45),
+    dict(N=40, E=70, P=1, money=6, G=1, B=64, kw=dict(belief=True), mode="fp32", steps=30),
+    dict(N=24, E=40, P=15, money=9, G=2, B=33, kw=dict(tolls=2, belief=True, reveal_interval=4), mode="fp64", steps=25),
+    dict(N=200, E=400, P=6, money=20, G=1, B=96, kw=dict(tolls=1, belief=True, reveal_interval=5), mode="fp64", steps=12),
+]
+
+
+def _make_pair(pkg, c, tables, auto_reset=True, seed=17, env_offset=0, max_timestep=250, resample_graph=False, B=None):
+    pool = pkg.generate_graph_pool(c["G"], c["N"], c["E"], seed=3)
+    B = B or c["B"]
+    env = pkg.BatchedScotlandYardEnv(B, c["P"], c["money"], graphs=pool, seed=seed, auto_reset=auto_reset,
+                                     reward_mode=c["mode"], keep_reward64=True, reward_tables=tables,
+                                     env_offset=env_offset, max_timestep=max_timestep, resample_graph=resample_graph,
+                                     **c["kw"])
+    ocfg = so.OracleConfig(num_police=c["P"], agent_money=c["money"], reward_mode=c["mode"],
+                           reveal_interval=c["kw"].get("reveal_interval", 0), toll=c["kw"].get("tolls", 0),
+                           belief=c["kw"].get("belief", False), max_timestep=max_timestep,
+                           exp_table=tables[0], cov_table=tables[1])
+    ograph = [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in pool]
+    ob = so.OracleBatch.from_seed(ocfg, ograph, B, seed=seed, env_offset=env_offset, auto_reset=auto_reset,
+                                  resample_graph=resample_graph)
+    return env, ob
+
+
+def _compare_state(env, ob, c, tag):
+    assert np.array_equal(env.pos.cpu().numpy(), ob.pos()), tag
+    assert np.array_equal(env.money.cpu().numpy(), ob.money()), tag
+    assert np.array_equal(env.timestep.cpu().numpy(), ob.timestep()), tag
+    assert np.array_equal(env.graph_id.cpu().numpy(), np.asarray(ob.graph_id, dtype=np.int32)), tag
+    assert np.array_equal(env.episode.cpu().numpy(), np.asarray(ob.episode, dtype=np.int32)), tag
+    assert np.array_equal(env.visits.cpu().numpy(), ob.visits()), tag
+    assert np.array_equal(env.action_mask.cpu().numpy(), ob.masks()), tag
+    assert np.array_equal(env.node_features.cpu().numpy(), ob.node_features()), tag
+    assert np.array_equal(env.agent_budget.cpu().numpy(), ob.money().astype(np.float32)), tag
+    assert np.array_equal(env.mrx_revealed.cpu().numpy(), ob.revealed()), tag
+    if c["kw"].get("belief"):
+        got = env.belief_map.cpu().numpy().astype(np.float64)
+        err = np.abs(got - ob.belief()).max()
+        assert err <= BELIEF_TOL, (tag, err)
+        assert np.abs(got.sum(axis=1) - 1.0).max() < 1e-5, tag
+
+
+def _compare_out(env, want, c, tag):
+    r64 = env.reward64.cpu().numpy()
+    r32 = env.reward.cpu().numpy()
+    if c["mode"] == "fp64":
+        assert r64.tobytes() == want["reward"].tobytes(), tag
+        assert r32.tobytes() == want["reward"].astype(np.float32).tobytes(), tag
+    else:
+        assert r32.tobytes() == want["reward"].tobytes(), tag
+    te, tr = env.terminated.cpu().numpy(), env.truncated.cpu().numpy()
+    assert np.array_equal(te, np.repeat(want["terminated"][:, None], te.shape[1], 1)), tag
+    assert np.array_equal(tr, np.repeat(want["truncated"][:, None], tr.shape[1], 1)), tag
+    assert np.array_equal(env.winner.cpu().numpy(), want["winner"]), tag
+
+
+@pytest.mark.parametrize("ci", range(len(CASES)))
+def test_random_policy_rollout_matches_oracle(torch_cuda, tables, ci):
+    """Batched rollout with the on-device Philox random-valid policy and same-step auto-reset:
+    sampler, dynamics, budgets (with tolls), rewards, flags, visit counts, masks, node features,
+    reveal schedule and belief map against the CPU oracle.  B is not a multiple of the tile."""
+    c = CASES[ci]
+    pkg = _pkg()
+    env, ob = _make_pair(pkg, c, tables, max_timestep=20 if ci == 0 else 250)
+    env.reset()
+    _compare_state(env, ob, c, "reset")
+    n_done = 0
+    for s in range(c["steps"]):
+        acts = env.sample_actions(step_counter=s)
+        a_h = acts.cpu().numpy()
+        assert np.array_equal(a_h, ob.sample_actions(s)), ("sampler", s)
+        env.step(acts)
+        want = ob.step(a_h)
+        _compare_out(env, want, c, ("out", s))
+        _compare_state(env, ob, c, ("state", s))
+        n_done += int(want["terminated"].sum() + want["truncated"].sum())
+    st = env.stats()
+    assert st["env_steps"] == c["B"] * c["steps"] and st["episodes"] == n_done
+    assert st["mrx_wins"] + st["police_wins"] == n_done
+    assert n_done > 0
+    env.close()
+
+
+def test_arbitrary_actions_and_freeze_without_auto_reset(torch_cuda, tables):
+    """Invalid actions are data, not errors (yard.py:171-178,223-229): out-of-range, negative,
+    huge int64, non-adjacent and unaffordable targets all mean `stay`; -1 means `skipped` for
+    police.  Without auto-reset finished envs freeze until reset(reset_mask)."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=20, E=34, P=4, money=7, G=3, B=150, kw=dict(belief=True, reveal_interval=2), mode="fp64")
+    env, ob = _make_pair(pkg, c, tables, auto_reset=False, max_timestep=12)
+    env.reset()
+    rng = np.random.default_rng(5)
+    B, A, N = c["B"], c["P"] + 1, c["N"]
+    for s in range(30):
+        valid = ob.sample_actions(s)
+        junk = rng.integers(-4, N + 4, size=(B, A))
+        huge = rng.choice(np.asarray([2**40, -2**40, 2**63 - 1, -2**63, N, -2], dtype=np.int64), size=(B, A))
+        u = rng.random((B, A))
+        acts = np.where(u < 0.6, valid, np.where(u < 0.85, junk, np.where(u < 0.93, huge, -1))).astype(np.int64)
+        env.step(torch.from_numpy(acts).cuda())
+        want = ob.step(acts)
+        _compare_out(env, want, c, ("out", s))
+        _compare_state(env, ob, c, ("state", s))
+        assert np.array_equal(env.done.cpu().numpy().astype(bool), np.asarray(ob.done)), s
+        if s in (9, 19):  # partial reset of the finished envs (torchrl "_reset" semantics)
+            m = np.asarray(ob.done)
+            assert m.any()
+            env.reset(reset_mask=m)
+            for b in np.nonzero(m)[0]:
+                ob.episode[b] += 1
+                e = ob.envs[b]
+                e.reset(ob.graphs[ob.graph_id[b]], so.philox_start_positions(ob.seed, b, ob.episode[b], N, A))
+                ob.done[b] = False
+            _compare_state(env, ob, c, ("after partial reset", s))
+    env.close()
+
+
+def test_timeout_branch_batched(torch_cuda, tables):
+    """reward_calculator.py:68-74: `timestep > max_timestep` truncates; the pre-increment
+    timestep is compared (yard.py:345,355), so with max_timestep=3 step index 4 truncates."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=15, E=20, P=2, money=1000, G=1, B=40, kw={}, mode="fp64")
+    env, ob = _make_pair(pkg, c, tables, auto_reset=False, max_timestep=3)
+    env.reset()
+    seen_trunc = False
+    for s in range(6):
+        # police send their own node (not skipped, never move), MrX stays: only timeouts can end it
+        acts = ob.pos().astype(np.int64)
+        env.step(torch.from_numpy(acts).cuda())
+        want = ob.step(acts)
+        _compare_out(env, want, c, s)
+        if want["truncated"].any():
+            assert s == 4
+            seen_trunc = True
+    assert seen_trunc
+    env.close()
+
+
+def test_shard_invariance(torch_cuda, tables):
+    """Sharding by batch: a shard created with env_offset=k reproduces envs
+    [k, k+b) of the full batch bit for bit (Philox streams are keyed by the global env index)."""
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=10, G=4, B=160, kw=dict(belief=True, reveal_interval=4, tolls=1), mode="fp64")
+    pool = pkg.generate_graph_pool(c["G"], c["N"], c["E"], seed=3)
+    mk = lambda B, off: pkg.BatchedScotlandYardEnv(B, c["P"], c["money"], graphs=pool, seed=9, auto_reset=True,  # noqa: E731
+                                                   resample_graph=True, env_offset=off, keep_reward64=True,
+                                                   reward_tables=tables, **c["kw"])
+    full, shard = mk(160, 0), mk(50, 100)
+    full.reset()
+    shard.reset()
+    for s in range(30):
+        full.step(full.sample_actions(step_counter=s))
+        shard.step(shard.sample_actions(step_counter=s))
+        for k in ("pos", "money", "timestep", "graph_id", "visits", "belief_map", "reward64", "terminated",
+                  "action_mask", "node_features"):
+            a, b = getattr(full, k)[100:150].cpu().numpy(), getattr(shard, k).cpu().numpy()
+            assert a.tobytes() == b.tobytes(), (k, s)
+    sf, ss = full.stats(), shard.stats()
+    assert sf["env_steps"] == 160 * 30 and ss["env_steps"] == 50 * 30
+    full.close()
+    shard.close()
+
+
+def test_dense_action_mask_matches_reference_vectors(torch_cuda):
+    """sy_action_mask_dense == compute_action_mask (action_mask.py:30-113) on the vectors recorded
+    from the reference function and on the reference's known-answer cases
+    (test/test_action_mask.py:9-124)."""
+    pkg = _pkg()
+    gm = np.load(os.path.join(GOLDEN, "masks.npz"))
+    for ci in range(int(gm["n_cases"])):
+        kind = int(gm[f"{ci}/toll_kind"])
+        tolls = None if kind in (0, 4) else (float(gm[f"{ci}/tolls"]) if kind == 1 else gm[f"{ci}/tolls"])
+        w = None if kind == 4 else gm[f"{ci}/w"]
+        got = pkg.dense_action_mask(gm[f"{ci}/adj"], int(gm[f"{ci}/cur"]), float(gm[f"{ci}/budget"]), tolls, w)
+        assert np.array_equal(got[0].cpu().numpy(), gm[f"{ci}/mask"]), ci
+    adj = np.array([[0, 1, 1], [1, 0, 0], [1, 0, 0]])
+    w = np.array([[0, 2, 4], [2, 0, 0], [4, 0, 0]])
+    assert pkg.dense_action_mask(adj, 0, 3, edge_weights=w)[0].tolist() == [False, True, False]
+    adj2 = np.ones((2, 2)) - np.eye(2)
+    assert pkg.dense_action_mask(adj2, 0, 0.5, tolls=0.25).sum().item() == 0
+    assert pkg.dense_action_mask(adj2, 0, 1.5, tolls=0.25)[0].tolist() == [False, True]
+    star = np.array([[0, 1, 1, 1], [1, 0, 0, 0], [1, 0, 0, 0], [1, 0, 0, 0]])
+    assert pkg.dense_action_mask(star, 0, 100)[0].tolist() == [False, True, True, True]
+    assert pkg.dense_action_mask(np.array([[0, 1], [1, 0]]), 0, 1, edge_weights=np.array([[0, 100], [100, 0]])).sum().item() == 0
+    assert pkg.dense_action_mask(np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0]]), 0, 100).sum().item() == 0
+    # batched queries: every node of a graph at two budgets
+    q = pkg.dense_action_mask(adj, [0, 1, 2, 0], [3, 3, 3, 10], edge_weights=w).cpu().numpy()
+    for i, (cur, bud) in enumerate([(0, 3), (1, 3), (2, 3), (0, 10)]):
+        assert np.array_equal(q[i], so.action_mask_dense(adj, cur, bud, edge_weights=w))
+
+
+def test_full_size_properties(torch_cuda):
+    """BASELINE config 3 at full size (N=200, P=6, B=65536, tolls + belief + reveal): properties
+    that do not need the oracle -- one-hot node features, masks == affordable neighbours recomputed
+    from the state with torch, police on distinct nodes, budgets never increase inside an episode,
+    belief rows sum to 1, flags consistent, statistics add up."""
+    torch = torch_cuda
+    pkg = _pkg()
+    N, P, B = 200, 6, 65536
+    A = P + 1
+    env = pkg.BatchedScotlandYardEnv(B, P, 20, graph_nodes=N, graph_edges=400, seed=1, auto_reset=True, tolls=1,
+                                     belief=True, reveal_interval=5)
+    env.reset()
+    W = torch.from_numpy(env.graph_tables(0)[0].astype(np.int32)).cuda()  # [N, N]
+    prev_money, prev_ep = env.money.clone(), env.episode.clone()
+    for s in range(25):
+        env.step(env.sample_actions())
+        pos, money = env.pos.long(), env.money
+        assert int(pos.min()) >= 0 and int(pos.max()) < N
+        pol = pos[:, 1:].sort(dim=1).values
+        assert bool((pol[:, 1:] != pol[:, :-1]).all()), "police share a node"
+        rows = W[pos]  # [B, A, N]
+        want_mask = (rows > 0) & (rows + 1 <= money.unsqueeze(-1))
+        assert bool((want_mask == env.action_mask).all())
+        nf = env.node_features
+        hidden = env.mrx_revealed < 0
+        assert bool((nf.sum(dim=1)[:, 1:] == 1).all())
+        assert bool((nf.sum(dim=1)[:, 0] == (~hidden).float()).all())
+        assert bool((nf[:, :, 1:].gather(1, pos[:, None, 1:]) == 1).all())
+        same_ep = env.episode == prev_ep
+        assert bool((money[same_ep] <= prev_money[same_ep]).all())
+        assert bool((money[~same_ep][:, 1:] == 20).all()) and bool((env.timestep[~same_ep] == 0).all())
+        bsum = env.belief_map.sum(dim=1)
+        assert float((bsum - 1).abs().max()) < 1e-5 and float(env.belief_map.min()) >= 0
+        rev = env.mrx_revealed >= 0
+        assert bool((env.timestep[rev] % 5 == 0).all()) and bool((env.timestep[rev] > 0).all())
+        assert bool((env.belief_map[rev].max(dim=1).values == 1).all())
+        assert bool(((env.terminated | env.truncated) == env.done_flags).all())
+        assert bool(torch.isfinite(env.reward).all())
+        prev_money, prev_ep = money.clone(), env.episode.clone()
+    st = env.stats()
+    assert st["env_steps"] == B * 25
+    assert st["episodes"] == int(env.episode.sum()) == st["mrx_wins"] + st["police_wins"]
+    env.close()
+
+
+def test_error_conventions(torch_cuda):
+    """C-ABI status codes surface as SyError with the library's message; nothing crashes."""
+    torch = torch_cuda
+    pkg = _pkg()
+    with pytest.raises(pkg.SyError):
+        pkg.BatchedScotlandYardEnv(4, 0, 10, graph_nodes=10, graph_edges=12)  # no police
+    with pytest.raises(pkg.SyError):
+        pkg.BatchedScotlandYardEnv(4, 9, 10, graph_nodes=8, graph_edges=10)  # more agents than nodes
+    env = pkg.BatchedScotlandYardEnv(4, 2, 10, graph_nodes=10, graph_edges=12)
+    with pytest.raises(pkg.SyError):
+        env.step(torch.zeros(4, 3, dtype=torch.int64, device="cuda"))  # step before reset
+    env.reset()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros(4, 2, dtype=torch.int64, device="cuda"))  # wrong shape
+    with pytest.raises(ValueError):
+        env.reset(init_pos=np.full((4, 3), 99))
+    env.close()
+
+
+def test_step_host_equals_step(torch_cuda, tables):
+    """sy_step_host (host buffers in/out, the reference's call shape) == sy_step on device buffers."""
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=10, G=2, B=70, kw=dict(belief=True, reveal_interval=4), mode="fp64")
+    a, _ = _make_pair(pkg, c, tables)
+    b, _ = _make_pair(pkg, c, tables)
+    a.reset()
+    b.reset()
+    for s in range(20):
+        acts = a.sample_actions(step_counter=s)
+        host_acts = b.sample_actions_host(step_counter=s)
+        assert not host_acts.is_cuda and np.array_equal(host_acts.numpy(), acts.cpu().numpy())
+        _, rew, term, trunc, info = a.step(acts)
+        res = b.step_host(host_acts if s % 2 == 0 else host_acts.numpy().copy())
+        assert not res["reward"].is_cuda
+        assert res["reward"].numpy().tobytes() == rew.cpu().numpy().tobytes()
+        assert np.array_equal(res["terminated"].numpy(), term.cpu().numpy())
+        assert np.array_equal(res["truncated"].numpy(), trunc.cpu().numpy())
+        assert np.array_equal(res["done"].numpy(), info["done"].cpu().numpy())
+        assert np.array_equal(res["winner"].numpy(), info["winner"].cpu().numpy())
+        assert np.array_equal(a.pos.cpu().numpy(), b.pos.cpu().numpy())
+        assert np.array_equal(a.belief_map.cpu().numpy(), b.belief_map.cpu().numpy())
+    a.close()
+    b.close()
