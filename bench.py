@@ -101,72 +101,87 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle port (the reference itself is Python and does not travel to the GPU box)
 # --------------------------------------------------------------------------------------------
-def cpu_oracle_throughput(wl, budget_s, all_cores):
-    """env-steps/s of the CPU oracle on a bounded sample of the workload.  Prefers the C restatement
-    (oracle/sy_oracle.c, OpenMP over envs) and falls back to the numpy/Python one (1 core)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import numpy as np
+class CpuRunner:
+    """The CPU oracle on a bounded sample of the workload: the C restatement (oracle/sy_oracle.c,
+    OpenMP over envs, all host threads) or, if gcc is unavailable, the numpy/Python one (1 core).
+    One `step()` = random-valid policy + env step + masks + node features + belief for `B` envs."""
 
-    from student_mechanism_design_b200.graphs import generate_graph_pool
+    def __init__(self, wl, all_cores=True):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import sy_oracle as so
 
-    pool = generate_graph_pool(1, wl["N"], wl["E"], seed=0)
-    try:
-        import sy_oracle_c as oc
+        from student_mechanism_design_b200.graphs import generate_graph_pool
 
-        have_c = oc.available()
-    except Exception:
-        have_c = False
-    if have_c:
-        cores = (os.cpu_count() or 1) if all_cores else 1
-        B = 4096 * max(1, min(cores, 16))
-        run = oc.CBatch(wl, pool[0], B, seed=0, threads=cores)
-        run.steps(3)
+        self.wl = wl
+        pool = [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in generate_graph_pool(1, wl["N"], wl["E"], seed=0)]
+        cfg = so.OracleConfig(num_police=wl["P"], agent_money=wl["money"], toll=wl["toll"], belief=wl["belief"],
+                              reveal_interval=wl["reveal"])
+        try:
+            import sy_oracle_c as oc
+
+            have_c = oc.available()
+        except Exception:
+            have_c = False
+        self.n = 0
+        if have_c:
+            cores = (os.cpu_count() or 1) if all_cores else 1
+            try:
+                cores = min(cores, len(os.sched_getaffinity(0)))
+            except Exception:
+                pass
+            self.cores, self.B = cores, 1024 * max(1, cores)
+            self.run = oc.CBatch(cfg, pool, self.B, seed=0, threads=cores)
+            self.what = f"C oracle (oracle/sy_oracle.c, OpenMP, {cores} threads)"
+            self.step = self._step_c
+        else:
+            self.cores, self.B = 1, 64
+            self.run = so.OracleBatch.from_seed(cfg, pool, self.B, seed=0)
+            self.what = "numpy/Python oracle (oracle/sy_oracle.py)"
+            self.step = self._step_py
+
+    def _step_c(self):
+        self.run.steps(1, first_step=self.n)
+        self.n += 1
+
+    def _step_py(self):
+        self.run.step(self.run.sample_actions(self.n))
+        self.run.masks(), self.run.node_features()
+        self.n += 1
+
+    def timed(self, budget_s, max_steps=None):
+        for _ in range(3):
+            self.step()
         n, t0 = 0, time.perf_counter()
-        while time.perf_counter() - t0 < budget_s:
-            run.steps(5)
-            n += 5
+        while time.perf_counter() - t0 < budget_s and (max_steps is None or n < max_steps):
+            self.step()
+            n += 1
         dt = time.perf_counter() - t0
-        return dict(value=B * n / dt, unit=UNIT, cores=cores, kind="port",
-                    sample=f"C oracle (oracle/sy_oracle.c, OpenMP), {B} envs x {n} steps of {wl['name']}, {dt:.1f} s")
-    import sy_oracle as so
-
-    B = 64
-    cfg = so.OracleConfig(num_police=wl["P"], agent_money=wl["money"], toll=wl["toll"], belief=wl["belief"],
-                          reveal_interval=wl["reveal"])
-    ob = so.OracleBatch.from_seed(cfg, [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in pool], B, seed=0)
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
-        acts = ob.sample_actions(n)
-        ob.step(acts)
-        ob.masks(), ob.node_features()
-        n += 1
-    dt = time.perf_counter() - t0
-    return dict(value=B * n / dt, unit=UNIT, cores=1, kind="port",
-                sample=f"numpy/Python oracle (oracle/sy_oracle.py), {B} envs x {n} steps of {wl['name']}, {dt:.1f} s")
+        return dict(value=self.B * n / dt, unit=UNIT, cores=self.cores, kind="port",
+                    sample=f"{self.what}: {self.B} envs x {n} steps of {self.wl['name']} (random policy + step + masks + "
+                           f"node features + belief), {dt:.1f} s"), dt, n
 
 
 def run_reference_arm(args, wl):
+    """`--impl reference`: the reference's CPU implementation of the path is Python and cannot travel
+    to the GPU box, so this arm times its oracle port (bit-exact with it on the golden traces) on all
+    host threads.  One step = one pass over a bounded sample batch; the run is capped at ~2 minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step_s = 2.0
-    vals = []
-    last = None
-    for i in range(args.warmup + args.steps):
-        last = cpu_oracle_throughput(wl, per_step_s if i >= args.warmup else 0.5, all_cores=True)
-        if i >= args.warmup:
-            vals.append(last["value"])
-        if len(vals) * per_step_s > 120:
-            break
-    v = statistics.mean(vals)
-    last["value"] = v
+    r = CpuRunner(wl, all_cores=True)
+    for _ in range(min(args.warmup, 20)):
+        r.step()
+    base, dt, n = r.timed(120.0, max_steps=args.steps)
+    v = base["value"]
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals),
-        "warmup": args.warmup, "ms_per_step": per_step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": min(args.warmup, 20) + 3, "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
-        "config": {"workload": f"{wl['name']}: {wl['desc']}", "note": "CPU arm = oracle port of the reference env "
-                   "(the reference is Python and cannot run on the GPU box); each step is a bounded 2 s sample"},
-        "cpu_baseline": last,
+        "config": {"workload": f"{wl['name']}: {wl['desc']}", "sample_envs": r.B,
+                   "note": "CPU arm = oracle port of the reference env on all host threads (the reference is pure Python "
+                           "and is not present on the GPU box; survey-measured reference speed at this config: 0.6 "
+                           "env-steps/s/core); a step is one pass over a bounded sample batch"},
+        "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -294,12 +309,12 @@ def run_cuda_arm(args, wl):
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "sy_step_kernel", "kernel_ms": step_kernel_ms,
+                         "traffic": traffic, "kernel": "sy_step = sy_logic_kernel + sy_observe_kernel", "kernel_ms": step_kernel_ms,
                          "algorithmic_bytes_per_env_step": bstep, "peak_source": peak_src},
             "episode_stats": stats_total,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_oracle_throughput(wl, args.cpu_seconds, all_cores=True)
+            line["cpu_baseline"] = CpuRunner(wl, all_cores=True).timed(args.cpu_seconds)[0]
         print(json.dumps(line), flush=True)
     env.close()
     if dist is not None:

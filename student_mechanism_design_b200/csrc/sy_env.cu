@@ -1,24 +1,26 @@
 // sy_env.cu -- B200 (sm_100a) kernels + C ABI of the batched Scotland Yard environment.
 //
 // Reference behaviour restated here (paths relative to /root/reference):
-//   src/environment/yard.py:80-142   reset          -> sy_reset_kernel
-//   src/environment/yard.py:144-269  step           -> sy_step_kernel (phases 1a-1c)
-//   src/environment/yard.py:271-335  observations   -> assemble_tile (phase 2)
+//   src/environment/yard.py:80-142   reset          -> sy_reset_kernel (+ sy_observe_kernel)
+//   src/environment/yard.py:144-269  step           -> sy_logic_kernel
+//   src/environment/yard.py:271-335  observations   -> sy_observe_kernel (writer warps)
 //   src/environment/yard.py:420-472  possible moves -> dense weight table + move-count table
-//   src/environment/action_mask.py:30-83            -> mask scatter in assemble_tile, sy_mask_dense_kernel
-//   src/environment/reward_calculator.py:26-266     -> phases 1a (status) and 1b (rewards)
+//   src/environment/action_mask.py:30-83            -> writer_role (mask rows), sy_mask_dense_kernel
+//   src/environment/reward_calculator.py:26-266     -> move_phase (ending) and agent_reward
 //   src/environment/pathfinding.py:34-137           -> sy_apsp_kernel (all-pairs table, built once per graph)
-//   src/environment/belief_module.py:69-111         -> belief propagation in assemble_tile (expectation)
+//   src/environment/belief_module.py:69-111         -> belief_role in sy_observe_kernel (expectation)
 //
-// Kernel shape: one CTA of 256 threads owns a tile of 32 consecutive envs.
-//   phase 0  cooperative, coalesced staging of the tile's AoS state ([B,A] int32/int64) into smem
-//   phase 1a warp 0, lane = env: the order-dependent MrX -> Police0..P-1 move rule, capture/timeout/no-money
-//   phase 1b warp a, lane = env: agent a's reward (fp64 or no-FMA fp32) + visit-count RMW  (no divergence)
-//   phase 1c warp 0, lane = env: timestep, reveal schedule, same-step auto-reset (Philox), statistics
-//   phase 2  all warps: coalesced write-back of state/results, 16-byte zero-fill of the tile's contiguous
-//            mask / node_feature regions followed by a sparse scatter of the few ones, warp-per-env belief.
-// The kernel is bound by the HBM writes of phase 2; graph tables are a few hundred KB
-// and are read through L1/L2 with ld.global.nc.
+// Two launches per step (measured on B200: a fused per-tile kernel ran its phases in lockstep over the whole
+// chip -- every phase added its full latency and HBM idled during the game logic):
+//   sy_logic_kernel    thread per env (warp = 32 envs, agents in a conflict-free smem row), no CTA barrier; all
+//                      65 536 envs of a batch are resident in one wave so their dependent table lookups overlap.
+//                      Moves -> ending -> visit counts + rewards (fp64 / no-FMA fp32) -> timestep, reveal schedule,
+//                      same-step auto-reset (Philox) -> coalesced state / result write-back, statistics.
+//   sy_observe_kernel  CTA per 32-env tile, warp-specialised, no barrier between the roles: writer warps stream the
+//                      dense observations (16-byte zero stores + the few ones while the lines sit in L2); belief
+//                      warps run the belief propagation as a lane = env SpMM over a transposed smem tile (LDGSTS).
+// The step is bound by the HBM writes of the observations; graph tables are a few hundred
+// KB and are read through L1/L2 with ld.global.nc.
 #include "../../include/sy_env.h"
 
 #include <cuda_runtime.h>
@@ -26,6 +28,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -52,9 +55,13 @@ int fail(int code, const char* fmt, ...) {
       return fail(SY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
-constexpr int TILE = 32;       // envs per CTA (one warp-width, so phase 1 is lane = env)
-constexpr int THREADS = 256;   // 8 warps
-constexpr int NWARPS = THREADS / 32;
+constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = env)
+constexpr int BEL_WARPS = 8;   // observe kernel: warps 0..7 propagate the belief ...
+constexpr int WR_WARPS = 8;    // ... warps 8..15 stream the dense observations
+constexpr int THREADS = (BEL_WARPS + WR_WARPS) * 32;
+constexpr int EXP_SMEM = 128;  // logic kernel: exp(-d) entries staged in shared memory
+constexpr int COV_SMEM = 256;  // logic kernel: coverage entries staged in shared memory
+constexpr int LOGIC_THREADS = 128;  // logic / reset kernels: 4 warps x 32 envs, no CTA barrier
 constexpr int AS = SY_MAX_AGENTS + 1;  // odd smem row stride -> conflict-free lane = env access
 constexpr unsigned FULL = 0xffffffffu;
 enum { DIST_INF = 0xFFFF };
@@ -71,9 +78,11 @@ struct Tables {
   const uint8_t* wgt;    // [G, nnz_stride]
   const uint8_t* cnt;    // [G, N, wcap+1] #neighbours with weight <= c
   const float* inv_deg;  // [G, N]
+  const int4* nbr_pack;  // [G, pack_stride] per CSR entry {byte offset of the nbr's tile row, bits of 1/deg(nbr), byte offset of the
+                         //  output row on the row's last entry else -1, 0}
   const double* exp_neg; // [n_exp]
   const double* coverage;  // [n_cov]
-  int n_exp, n_cov, G, Ns, nnz_stride, wcap;
+  int n_exp, n_cov, G, Ns, nnz_stride, wcap, pack_stride;
 };
 
 struct Params {
@@ -88,6 +97,10 @@ struct Params {
   SyObs ob;
   SyOut out;
   const long long* actions;
+  int bel_fast, bel_off_out, bel_off_part, bel_off_pack;  // belief fast path: dynamic smem layout (bytes)
+  int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr, wr_nf_fast;  // writer warps: smem staging layout (bytes) and path flags
+  int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
+  uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
   // reset-only inputs
   const uint8_t* reset_mask;
   const int32_t* init_pos;
@@ -95,22 +108,6 @@ struct Params {
   int restart;
 };
 
-struct TileSmem {
-  int act[TILE * AS];
-  int pos[TILE * AS];
-  int money[TILE * AS];
-  float rew[TILE * AS];
-  double rew64[TILE * AS];
-  int t[TILE];
-  int gid[TILE];
-  int episode[TILE];
-  int status[TILE];
-  int frozen[TILE];
-  int done[TILE];
-  int clear_visits[TILE];
-  int bel_op[TILE];
-  int revealed[TILE];
-};
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (same constants / counter layout as oracle/sy_oracle.py:philox4x32)
@@ -132,8 +129,7 @@ __device__ __forceinline__ unsigned word_of(const uint4& r, int i) {
 }
 
 // A distinct uniform nodes (distribution of np.random.choice(N, A, replace=False), yard.py:112-116)
-__device__ void philox_start_positions(const Params& p, unsigned env, unsigned episode, int* out /*stride 1*/) {
-  int chosen[SY_MAX_AGENTS];
+__device__ void philox_start_positions(const Params& p, unsigned env, unsigned episode, int* out, int* chosen /*A ints of scratch*/) {
   uint4 r = make_uint4(0, 0, 0, 0);
   const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
   for (int a = 0; a < p.A; ++a) {
@@ -177,444 +173,718 @@ __device__ __forceinline__ double exp_neg(const Tables& tb, int d) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 2: everything that is written per env and is a pure function of the tile state in smem
+// small device helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void zero_fill_bytes(uint8_t* base, size_t nbytes, int tid) {
-  // base is 16-byte aligned (tile starts are multiples of 32 envs); the tail of the last tile is bytewise
-  const size_t nvec = nbytes >> 4;
-  uint4* v = reinterpret_cast<uint4*>(base);
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {  // LDGSTS: global -> shared, no staging register
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// warp-cooperative streaming zero-fill of n bytes at any alignment: byte head, 16-byte body, byte tail
+__device__ __forceinline__ void warp_zero_bytes(uint8_t* ptr, int n, int lane) {
+  const int head = min(n, (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(ptr) & 15u)) & 15u));
+  if (lane < head) ptr[lane] = 0;
+  uint4* v = reinterpret_cast<uint4*>(ptr + head);
+  const int nvec = (n - head) >> 4;
   const uint4 z = make_uint4(0, 0, 0, 0);
-  for (size_t i = tid; i < nvec; i += THREADS) __stcs(v + i, z);
-  for (size_t i = (nvec << 4) + tid; i < nbytes; i += THREADS) base[i] = 0;
-}
-
-__device__ void assemble_tile(const Params& p, TileSmem& s, float* sbel_all, int tile0, int nEnv) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, A = p.A;
-  const Tables& tb = p.tb;
-
-  // ---- state write-back + small per-agent observations (coalesced from smem)
-  for (int i = tid; i < nEnv * A; i += THREADS) {
-    const int e = i / A, a = i - e * A;
-    const size_t o = (size_t)tile0 * A + i;
-    const int m = s.money[e * AS + a];
-    p.st.pos[o] = s.pos[e * AS + a];
-    p.st.money[o] = m;
-    p.ob.agent_budget[o] = (float)m;
-  }
-  if (tid < nEnv) {
-    const int b = tile0 + tid;
-    p.st.timestep[b] = s.t[tid];
-    p.st.graph_id[b] = s.gid[tid];
-    p.st.episode[b] = s.episode[tid];
-    p.st.done[b] = (uint8_t)s.done[tid];
-    p.ob.mrx_revealed[b] = s.revealed[tid];
-  }
-
-  // ---- dense observations: zero the tile's contiguous regions, then scatter the ones
-  uint8_t* mask_base = p.ob.action_mask + (size_t)tile0 * A * N;
-  float* nf_base = p.ob.node_features + (size_t)tile0 * N * A;
-  zero_fill_bytes(mask_base, (size_t)nEnv * A * N, tid);
-  zero_fill_bytes(reinterpret_cast<uint8_t*>(nf_base), (size_t)nEnv * N * A * sizeof(float), tid);
-  __syncthreads();  // orders the zero stores before the ones below (same CTA)
-  for (int i = tid; i < nEnv * A; i += THREADS) {
-    const int e = i / A, a = i - e * A;
-    const int g = s.gid[e], u = s.pos[e * AS + a], m = s.money[e * AS + a];
-    // action_mask.py:65-76: adjacent and weight + toll <= budget
-    const int r0 = __ldg(tb.row_ptr + (size_t)g * (N + 1) + u), r1 = __ldg(tb.row_ptr + (size_t)g * (N + 1) + u + 1);
-    uint8_t* row = mask_base + (size_t)i * N;
-    for (int k = r0; k < r1; ++k) {
-      const int v = __ldg(tb.col + (size_t)g * tb.nnz_stride + k);
-      const int w = __ldg(tb.wgt + (size_t)g * tb.nnz_stride + k);
-      if (w + p.toll <= m) row[v] = 1;
-    }
-    // yard.py:279-290: one-hot positions; the MrX column stays blank while he is hidden
-    if (a > 0 || s.revealed[e] >= 0) nf_base[((size_t)e * N + u) * A + a] = 1.0f;
-  }
-
-  // ---- visit counts are cleared on reset (yard.py:85)
-  for (int e = warp; e < nEnv; e += NWARPS) {
-    if (s.clear_visits[e]) {
-      uint16_t* v = p.st.visits + (size_t)(tile0 + e) * N;
-      for (int j = lane; j < N; j += 32) v[j] = 0;
-    }
-  }
-
-  // ---- belief_map (belief_module.py:69-111 in expectation), one warp per env
-  if (p.belief_on) {
-    float* sb = sbel_all + (size_t)warp * 2 * N;  // [0,N): b[i]/deg(i)   [N,2N): un-normalised result
-    for (int e = warp; e < nEnv; e += NWARPS) {
-      const int op = s.bel_op[e];
-      float* bel = p.st.belief + (size_t)(tile0 + e) * N;
-      if (op == BEL_UNIFORM) {
-        const float u = 1.0f / (float)N;
-        for (int j = lane; j < N; j += 32) bel[j] = u;
-      } else if (op == BEL_DELTA) {
-        const int x = s.pos[e * AS + 0];
-        for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
-      } else if (op == BEL_PROPAGATE) {
-        const int g = s.gid[e];
-        const float* idg = tb.inv_deg + (size_t)g * N;
-        const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1);
-        const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
-        __syncwarp();
-        for (int j = lane; j < N; j += 32) sb[j] = bel[j] * __ldg(idg + j);
-        __syncwarp();
-        float part = 0.0f;
-        for (int j = lane; j < N; j += 32) {
-          const int r0 = __ldg(rp + j), r1 = __ldg(rp + j + 1);
-          float acc = 0.0f;
-          for (int k = r0; k < r1; ++k) acc += sb[__ldg(cl + k)];
-          if (r1 == r0) acc = bel[j];  // isolated node keeps its mass (belief_module.py:93-97)
-          sb[N + j] = acc;
-          part += acc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-        if (part == 0.0f) {  // belief_module.py:36-37
-          const float u = 1.0f / (float)N;
-          for (int j = lane; j < N; j += 32) bel[j] = u;
-        } else {
-          for (int j = lane; j < N; j += 32) bel[j] = sb[N + j] / part;
-        }
-      }
-    }
-  }
+  for (int i = lane; i < nvec; i += 32) __stcs(v + i, z);
+  const int done = head + (nvec << 4);
+  if (lane < n - done) ptr[done + lane] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// step kernel
+// logic kernel pieces.  lane = env; the env's agents live in a shared-memory row (stride AS, conflict-free)
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
-__device__ __forceinline__ void agent_reward(const Params& p, TileSmem& s, int e, int b, int a) {
-  // lane = env e, this warp = agent a.  reward_calculator.py:26-92 (status decided in phase 1a).
+struct WarpTile {
+  int act[32 * AS];    // normalised actions; reused as reward bits / Philox scratch; slot [AS-1] = status word
+  int pos[32 * AS];
+  int money[32 * AS];
+};
+
+// the order-dependent move rule (yard.py:155-243) and the ending (reward_calculator.py:63-79).  An agent's own node
+// does not change before its own move, so all A edge-weight lookups are issued up front (one round trip).
+__device__ __forceinline__ int move_phase(const Params& p, int* pos, int* money, const int* act, int g, int t, int& spent) {
   const Tables& tb = p.tb;
   const int N = p.N, P = p.P;
-  const int g = s.gid[e];
-  const int status = s.status[e];
-  const int u = s.pos[e * AS + a];
-  int visits_here = 0;
-  if (a > 0) {  // yard.py:244-245: node_visit_counts[pos] += 1 for every police, before the rewards
-    uint16_t* vp = p.st.visits + (size_t)b * N + u;
-    visits_here = (int)(*vp) + 1;
-    *vp = (uint16_t)min(visits_here, 0xFFFF);
+  int wpre[SY_MAX_AGENTS];
+#pragma unroll
+  for (int i = 0; i < SY_MAX_AGENTS; ++i) wpre[i] = (i <= P && act[i] >= 0) ? edge_weight(tb, N, g, pos[i], act[i]) : 0;
+  {  // MrX: legal target or stay; may not step onto a police node (yard.py:161-188)
+    const int a0 = act[0], u = pos[0];
+    int tgt = u;
+    if (a0 >= 0 && wpre[0] > 0 && wpre[0] + p.toll <= money[0]) tgt = a0;
+    bool occupied = false;
+    for (int i = 1; i <= P; ++i) occupied |= (pos[i] == tgt);
+    if (!occupied) pos[0] = tgt;
   }
-  double r64;
-  float r32;
-  if (status == ST_CAPTURE) {
-    r64 = (a == 0) ? -1.0 : 1.0;
-    r32 = (float)r64;
-  } else if (status != ST_RUNNING) {
-    r64 = (a == 0) ? 1.0 : 0.0;
-    r32 = (float)r64;
-  } else {
-    const double tt = (double)s.t[e];
-    const int x = s.pos[e * AS + 0];
-    if (a == 0) {
-      // reward_calculator.py:126-148
-      int dmin = DIST_INF;
-      long long dsum = 0;
-      bool any_inf = false;
-      for (int i = 1; i <= P; ++i) {
-        const int d = dist_of(tb, N, g, x, s.pos[e * AS + i]);
-        dmin = min(dmin, d);
-        any_inf |= (d == DIST_INF);
-        dsum += d;
-      }
-      const double inf = __longlong_as_double(0x7ff0000000000000LL);
-      const double closest = (dmin == DIST_INF) ? inf : (double)dmin;
-      const double avg = any_inf ? inf : __ddiv_rn((double)dsum, (double)P);  // np.mean: exact sum / P
-      const double x1 = __ddiv_rn(-1.0, __dadd_rn(closest, 1.0));
-      const double x2 = __ddiv_rn(-1.0, __dadd_rn(avg, 1.0));
-      const double x3 = (double)move_count(tb, N, g, x, s.money[e * AS + 0], p.toll);
-      const double x4 = __dmul_rn(0.1, tt);
-      if (MODE == SY_REWARD_FP64) {
-        const double t1 = __dmul_rn(p.w64[4], x1), t2 = __dmul_rn(p.w64[5], x2), t3 = __dmul_rn(p.w64[6], x3);
-        const double t4 = __dmul_rn(__dsub_rn(1.0, p.w64[7]), x4);
-        r64 = __dadd_rn(__dadd_rn(__dadd_rn(t1, t2), t3), t4);
-        r32 = (float)r64;
-      } else {
-        const float t1 = __fmul_rn(p.w32[4], (float)x1), t2 = __fmul_rn(p.w32[5], (float)x2);
-        const float t3 = __fmul_rn(p.w32[6], (float)x3);
-        const float t4 = __fmul_rn(__fsub_rn(1.0f, p.w32[7]), (float)x4);
-        r32 = __fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
-        r64 = (double)r32;
-      }
-    } else {
-      // reward_calculator.py:182-227
-      const int k = a - 1;
-      const double dx = exp_neg(tb, dist_of(tb, N, g, u, x));
-      double grp = 0.0, ov = 0.0, prox = 0.0;
-      for (int j = 0; j < P; ++j) {
-        if (j == k) continue;
-        const int d = dist_of(tb, N, g, u, s.pos[e * AS + 1 + j]);
-        const double ex = exp_neg(tb, d);
-        grp = __dadd_rn(grp, ex);
-        if (d <= 1)
-          ov = __dadd_rn(ov, 1.0);
-        else
-          prox = __dadd_rn(prox, ex);
-      }
-      // QUIRK reward_calculator.py:190: the mobility term uses the budget of agent index k (not k+1)
-      const double mob = (double)move_count(tb, N, g, u, s.money[e * AS + k], p.toll);
-      const double cov = __ldg(tb.coverage + min(visits_here, tb.n_cov - 1));
-      const double x4 = __dmul_rn(0.05, tt);
-      if (MODE == SY_REWARD_FP64) {
-        const double u1 = __dmul_rn(p.w64[0], dx), u2 = __dmul_rn(p.w64[1], grp), u3 = __dmul_rn(p.w64[2], mob);
-        const double u4 = __dmul_rn(__dsub_rn(1.0, p.w64[3]), x4);
-        const double u5 = __dmul_rn(p.w64[9], prox), u6 = __dmul_rn(p.w64[10], ov), u7 = __dmul_rn(p.w64[8], cov);
-        r64 = __dadd_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(u1, u2), u3), u4), u5), u6), u7);
-        r32 = (float)r64;
-      } else {
-        const float u1 = __fmul_rn(p.w32[0], (float)dx), u2 = __fmul_rn(p.w32[1], (float)grp);
-        const float u3 = __fmul_rn(p.w32[2], (float)mob);
-        const float u4 = __fmul_rn(__fsub_rn(1.0f, p.w32[3]), (float)x4);
-        const float u5 = __fmul_rn(p.w32[9], (float)prox), u6 = __fmul_rn(p.w32[10], (float)ov);
-        const float u7 = __fmul_rn(p.w32[8], (float)cov);
-        r32 = __fadd_rn(__fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1, u2), u3), u4), u5), u6), u7);
-        r64 = (double)r32;
-      }
-    }
+  bool no_money = true;
+#pragma unroll
+  for (int i = 1; i < SY_MAX_AGENTS; ++i) {  // police in order; later police see earlier moves (yard.py:192-243)
+    if (i > P) break;
+    const int ai = act[i], m = money[i], u = pos[i];
+    if (ai == -1 || m == 0) continue;  // None / DEFAULT_ACTION / broke: skipped (yard.py:210-215)
+    no_money = false;
+    if (ai < 0 || ai == u) continue;
+    const int w = wpre[i];
+    if (w == 0 || w + p.toll > m) continue;  // not a possible move -> stay
+    bool occupied = false;
+    for (int j = 1; j <= P; ++j) occupied |= (pos[j] == ai);
+    if (occupied) continue;  // may step onto MrX (capture) but not onto police (yard.py:231)
+    pos[i] = ai;
+    money[i] = m - (w + p.toll);
+    spent += w + p.toll;
   }
-  s.rew[e * AS + a] = r32;
-  s.rew64[e * AS + a] = r64;
+  bool capture = false;
+  for (int i = 1; i <= P; ++i) capture |= (pos[i] == pos[0]);
+  // reward_calculator.py:63-79; `timestep` is the pre-increment value (yard.py:345,355)
+  return capture ? ST_CAPTURE : (t > p.max_t ? ST_TIMEOUT : (no_money ? ST_NO_MONEY : ST_RUNNING));
 }
 
+struct RewardTables {  // shared-memory copies of the head of the two float64 tables (built by NumPy on the host)
+  double exp_neg[EXP_SMEM];
+  double coverage[COV_SMEM];
+};
+__device__ __forceinline__ double exp_neg_s(const Tables& tb, const RewardTables& rt, int d) {
+  return d < EXP_SMEM ? rt.exp_neg[d] : exp_neg(tb, d);
+}
+
+// reward of agent a (reward_calculator.py:26-92 endings, :94-266 shaped), float64 value (fp32 mode: the float, widened).
+// All distance lookups of the agent are issued before any is used (memory-level parallelism; the loops are fully
+// unrolled over SY_MAX_AGENTS with a break so that the values stay in registers).
 template <int MODE>
-__global__ void __launch_bounds__(THREADS) sy_step_kernel(const Params p) {
-  __shared__ TileSmem s;
-  extern __shared__ float sbel[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int N = p.N, P = p.P, A = p.A;
-  const int tile0 = blockIdx.x * TILE;
-  const int nEnv = min(TILE, p.B - tile0);
+__device__ __forceinline__ double agent_reward(const Params& p, const RewardTables& rt, const int* pos, const int* money, int g,
+                                               int t, int status, int a, int visits_here) {
   const Tables& tb = p.tb;
+  const int N = p.N, P = p.P;
+  if (status == ST_CAPTURE) return (a == 0) ? -1.0 : 1.0;
+  if (status != ST_RUNNING) return (a == 0) ? 1.0 : 0.0;
+  const double tt = (double)t;
+  const int u = pos[a];
+  int dj[SY_MAX_AGENTS];  // d(u, pos[j]), j = 0 is MrX
+#pragma unroll
+  for (int j = 0; j < SY_MAX_AGENTS; ++j) dj[j] = (j <= P) ? dist_of(tb, N, g, u, pos[j]) : 0;
+  if (a == 0) {
+    // reward_calculator.py:126-148
+    int dmin = DIST_INF;
+    long long dsum = 0;
+    bool any_inf = false;
+#pragma unroll
+    for (int i = 1; i < SY_MAX_AGENTS; ++i) {
+      if (i > P) break;
+      dmin = min(dmin, dj[i]);
+      any_inf |= (dj[i] == DIST_INF);
+      dsum += dj[i];
+    }
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double closest = (dmin == DIST_INF) ? inf : (double)dmin;
+    const double avg = any_inf ? inf : __ddiv_rn((double)dsum, (double)P);  // np.mean: exact sum / P
+    const double x1 = __ddiv_rn(-1.0, __dadd_rn(closest, 1.0));
+    const double x2 = __ddiv_rn(-1.0, __dadd_rn(avg, 1.0));
+    const double x3 = (double)move_count(tb, N, g, u, money[0], p.toll);
+    const double x4 = __dmul_rn(0.1, tt);
+    if (MODE == SY_REWARD_FP64) {
+      const double t1 = __dmul_rn(p.w64[4], x1), t2 = __dmul_rn(p.w64[5], x2), t3 = __dmul_rn(p.w64[6], x3);
+      const double t4 = __dmul_rn(__dsub_rn(1.0, p.w64[7]), x4);
+      return __dadd_rn(__dadd_rn(__dadd_rn(t1, t2), t3), t4);
+    } else {
+      const float t1 = __fmul_rn(p.w32[4], (float)x1), t2 = __fmul_rn(p.w32[5], (float)x2);
+      const float t3 = __fmul_rn(p.w32[6], (float)x3);
+      const float t4 = __fmul_rn(__fsub_rn(1.0f, p.w32[7]), (float)x4);
+      return (double)__fadd_rn(__fadd_rn(__fadd_rn(t1, t2), t3), t4);
+    }
+  }
+  // reward_calculator.py:182-227
+  const int k = a - 1;
+  // QUIRK reward_calculator.py:190: the mobility term uses the budget of agent index k (not k+1)
+  const double mob = (double)move_count(tb, N, g, u, money[k], p.toll);
+  const int vc = min(visits_here, tb.n_cov - 1);
+  const double cov = vc < COV_SMEM ? rt.coverage[vc] : __ldg(tb.coverage + vc);
+  const double dx = exp_neg_s(tb, rt, dj[0]);
+  double grp = 0.0, ov = 0.0, prox = 0.0;
+#pragma unroll
+  for (int j = 0; j < SY_MAX_AGENTS - 1; ++j) {
+    if (j >= P) break;
+    if (j == k) continue;
+    const int d = dj[1 + j];
+    const double ex = exp_neg_s(tb, rt, d);
+    grp = __dadd_rn(grp, ex);
+    if (d <= 1)
+      ov = __dadd_rn(ov, 1.0);
+    else
+      prox = __dadd_rn(prox, ex);
+  }
+  const double x4 = __dmul_rn(0.05, tt);
+  if (MODE == SY_REWARD_FP64) {
+    const double u1 = __dmul_rn(p.w64[0], dx), u2 = __dmul_rn(p.w64[1], grp), u3 = __dmul_rn(p.w64[2], mob);
+    const double u4 = __dmul_rn(__dsub_rn(1.0, p.w64[3]), x4);
+    const double u5 = __dmul_rn(p.w64[9], prox), u6 = __dmul_rn(p.w64[10], ov), u7 = __dmul_rn(p.w64[8], cov);
+    return __dadd_rn(__dsub_rn(__dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(u1, u2), u3), u4), u5), u6), u7);
+  } else {
+    const float u1 = __fmul_rn(p.w32[0], (float)dx), u2 = __fmul_rn(p.w32[1], (float)grp);
+    const float u3 = __fmul_rn(p.w32[2], (float)mob);
+    const float u4 = __fmul_rn(__fsub_rn(1.0f, p.w32[3]), (float)x4);
+    const float u5 = __fmul_rn(p.w32[9], (float)prox), u6 = __fmul_rn(p.w32[10], (float)ov);
+    const float u7 = __fmul_rn(p.w32[8], (float)cov);
+    return (double)__fadd_rn(__fsub_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(u1, u2), u3), u4), u5), u6), u7);
+  }
+}
 
-  // ---- phase 0: stage the tile (coalesced)
-  for (int i = tid; i < nEnv * A; i += THREADS) {
+// state of the warp's envs back to HBM (coalesced from the smem rows), per-env scalars lane = env, visit rows of
+// freshly reset envs cleared (yard.py:85), belief operation handed to the observe kernel
+__device__ __forceinline__ void store_state(const Params& p, const WarpTile& wt, int b0, int nEnv, int lane, int t_new, int gid,
+                                            int episode, int done, int bel_op, int revealed, bool clear_visits) {
+  const int A = p.A, N = p.N;
+  __syncwarp();
+  for (int i = lane; i < nEnv * A; i += 32) {
     const int e = i / A, a = i - e * A;
-    const size_t o = (size_t)tile0 * A + i;
+    const size_t o = (size_t)b0 * A + i;
+    const int m = wt.money[e * AS + a];
+    p.st.pos[o] = wt.pos[e * AS + a];
+    p.st.money[o] = m;
+    p.ob.agent_budget[o] = (float)m;  // yard.py:329-331
+  }
+  if (lane < nEnv) {
+    const int b = b0 + lane;
+    p.st.timestep[b] = t_new;
+    p.st.graph_id[b] = gid;
+    p.st.episode[b] = episode;
+    p.st.done[b] = (uint8_t)done;
+    p.ob.mrx_revealed[b] = revealed;
+    p.bel_flags[b] = (uint8_t)bel_op;
+  }
+  unsigned clr = __ballot_sync(FULL, clear_visits && lane < nEnv);
+  while (clr) {
+    const int e = __ffs(clr) - 1;
+    clr &= clr - 1;
+    warp_zero_bytes(reinterpret_cast<uint8_t*>(p.st.visits + (size_t)(b0 + e) * N), N * (int)sizeof(uint16_t), lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// logic kernel: one thread per env, one warp per 32 consecutive envs, no CTA-wide barriers.  All envs of a
+// 65 536-env batch are resident at once (single wave), so the dependent lookups of different envs overlap.
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p) {
+  __shared__ WarpTile wts[LOGIC_THREADS / 32];
+  __shared__ RewardTables rt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < EXP_SMEM; i += LOGIC_THREADS) rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
+  for (int i = threadIdx.x; i < COV_SMEM; i += LOGIC_THREADS) rt.coverage[i] = __ldg(p.tb.coverage + min(i, p.tb.n_cov - 1));
+  __syncthreads();  // the only CTA-wide barrier: tables staged
+  const int b0 = (blockIdx.x * (LOGIC_THREADS / 32) + warp) * 32;
+  if (b0 >= p.B) return;
+  WarpTile& wt = wts[warp];
+  const int nEnv = min(32, p.B - b0);
+  const int N = p.N, A = p.A, P = p.P;
+
+  // ---- stage the warp's AoS rows (coalesced)
+  for (int i = lane; i < nEnv * A; i += 32) {
+    const int e = i / A, a = i - e * A;
+    const size_t o = (size_t)b0 * A + i;
     const long long a64 = p.actions[o];
-    s.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
-    s.pos[e * AS + a] = p.st.pos[o];
-    s.money[e * AS + a] = p.st.money[o];
+    wt.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
+    wt.pos[e * AS + a] = p.st.pos[o];
+    wt.money[e * AS + a] = p.st.money[o];
   }
-  if (tid < TILE) {
-    const bool live = tid < nEnv;
-    const int b = tile0 + tid;
-    s.t[tid] = live ? p.st.timestep[b] : 0;
-    s.gid[tid] = live ? p.st.graph_id[b] : 0;
-    s.episode[tid] = live ? p.st.episode[b] : 0;
-    s.frozen[tid] = live ? (int)p.st.done[b] : 1;
-    s.done[tid] = s.frozen[tid];
-    s.status[tid] = ST_RUNNING;
-    s.clear_visits[tid] = 0;
-    s.bel_op[tid] = BEL_KEEP;
-    s.revealed[tid] = -1;
+  const bool live = lane < nEnv;
+  const int b = b0 + lane;
+  int t = 0, g = 0, episode = 0, frozen = 1;
+  if (live) {
+    t = p.st.timestep[b];
+    g = p.st.graph_id[b];
+    episode = p.st.episode[b];
+    frozen = p.st.done[b];
   }
-  __syncthreads();
+  __syncwarp();
+  int* pos = wt.pos + lane * AS;
+  int* money = wt.money + lane * AS;
+  int* act = wt.act + lane * AS;
 
-  // ---- phase 1a: sequential move rule, lane = env (yard.py:155-243)
-  int spent = 0;
-  if (warp == 0 && lane < nEnv && !s.frozen[lane]) {
-    const int e = lane, g = s.gid[e];
-    int* pos = s.pos + e * AS;
-    int* money = s.money + e * AS;
-    const int* act = s.act + e * AS;
-    {  // MrX: legal target or stay; may not step onto a police node (yard.py:161-188)
-      const int a0 = act[0], u = pos[0];
-      int tgt = u;
-      if (a0 >= 0) {
-        const int w = edge_weight(tb, N, g, u, a0);
-        if (w > 0 && w + p.toll <= money[0]) tgt = a0;
-      }
-      bool occupied = false;
-      for (int i = 1; i <= P; ++i) occupied |= (pos[i] == tgt);
-      if (!occupied) pos[0] = tgt;
-    }
-    bool no_money = true;
-    for (int i = 1; i <= P; ++i) {  // police in order; later police see earlier moves (yard.py:192-243)
-      const int ai = act[i], m = money[i], u = pos[i];
-      if (ai == -1 || m == 0) continue;  // None / DEFAULT_ACTION / broke: skipped (yard.py:210-215)
-      no_money = false;
-      if (ai < 0 || ai == u) continue;
-      const int w = edge_weight(tb, N, g, u, ai);
-      if (w == 0 || w + p.toll > m) continue;  // not a possible move -> stay
-      bool occupied = false;
-      for (int j = 1; j <= P; ++j) occupied |= (pos[j] == ai);
-      if (occupied) continue;  // may step onto MrX (capture) but not onto police (yard.py:231)
-      pos[i] = ai;
-      money[i] = m - (w + p.toll);
-      spent += w + p.toll;
-    }
-    bool capture = false;
-    for (int i = 1; i <= P; ++i) capture |= (pos[i] == pos[0]);
-    // reward_calculator.py:63-79; `timestep` is the pre-increment value (yard.py:345,355)
-    s.status[e] = capture ? ST_CAPTURE : (s.t[e] > p.max_t ? ST_TIMEOUT : (no_money ? ST_NO_MONEY : ST_RUNNING));
-  }
-  __syncthreads();
+  // ---- moves + ending
+  int status = ST_RUNNING, spent = 0;
+  const bool active = live && !frozen;
+  if (active) status = move_phase(p, pos, money, act, g, t, spent);
 
-  // ---- phase 1b: rewards, warp = agent, lane = env
-  for (int a = warp; a < A; a += NWARPS) {
-    if (lane < nEnv) {
-      if (s.frozen[lane]) {
-        s.rew[lane * AS + a] = 0.0f;
-        s.rew64[lane * AS + a] = 0.0;
-      } else {
-        agent_reward<MODE>(p, s, lane, tile0 + lane, a);
+  // ---- visit counts (yard.py:244-245) and rewards; reward bits go to the (now dead) action slots
+  if (live) {
+    if (active) {  // police never share a node (yard.py:231), so the P counters are distinct: load all, then store
+      uint16_t* vrow = p.st.visits + (size_t)b * N;
+      int vis[SY_MAX_AGENTS];
+#pragma unroll
+      for (int i = 1; i < SY_MAX_AGENTS; ++i) vis[i] = (i <= P) ? (int)vrow[pos[i]] + 1 : 0;
+#pragma unroll
+      for (int i = 1; i < SY_MAX_AGENTS; ++i) {
+        if (i > P) break;
+        vrow[pos[i]] = (uint16_t)min(vis[i], 0xFFFF);
+        act[i] = vis[i];  // stash for the reward below (the action slots are dead after the moves)
       }
     }
+#pragma unroll 1
+    for (int a = 0; a < A; ++a) {
+      double r64 = 0.0;
+      if (active) r64 = agent_reward<MODE>(p, rt, pos, money, g, t, status, a, a > 0 ? act[a] : 0);
+      act[a] = __float_as_int((float)r64);
+      if (p.out.reward64) p.out.reward64[(size_t)b * A + a] = r64;
+    }
+    act[AS - 1] = status | (frozen << 8);
   }
-  __syncthreads();
-
-  // ---- results of this step (coalesced), before the auto-reset rewrites the tile state
-  for (int i = tid; i < nEnv * A; i += THREADS) {
+  __syncwarp();
+  for (int i = lane; i < nEnv * A; i += 32) {  // results of this step, coalesced
     const int e = i / A, a = i - e * A;
-    const size_t o = (size_t)tile0 * A + i;
-    const int st = s.status[e];
+    const size_t o = (size_t)b0 * A + i;
+    const int sw = wt.act[e * AS + AS - 1], st = sw & 0xff;
     const bool term = (st == ST_CAPTURE) || (st == ST_NO_MONEY), trunc = (st == ST_TIMEOUT);
-    p.out.reward[o] = s.rew[e * AS + a];
-    if (p.out.reward64) p.out.reward64[o] = s.rew64[e * AS + a];
+    p.out.reward[o] = __int_as_float(wt.act[e * AS + a]);
     p.out.terminated[o] = term;
     p.out.truncated[o] = trunc;
-    p.out.done[o] = term || trunc || s.frozen[e];
+    p.out.done[o] = term || trunc || (sw >> 8);
   }
-  __syncthreads();
+  __syncwarp();
 
-  // ---- phase 1c: timestep, reveal, auto-reset, statistics; lane = env
-  if (warp == 0) {
-    int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
-    if (lane < nEnv) {
-      const int e = lane, b = tile0 + e;
-      const int st = s.status[e];
-      if (!s.frozen[e]) {
-        n_step = 1;
-        int t_new = s.t[e] + 1;  // yard.py:355
-        p.out.winner[b] = (int8_t)(st == ST_CAPTURE ? SY_WINNER_POLICE : (st == ST_RUNNING ? SY_WINNER_NONE : SY_WINNER_MRX));
-        int bel = BEL_PROPAGATE;
-        if (st != ST_RUNNING) {
-          n_ep = 1;
-          n_pol = (st == ST_CAPTURE);
-          n_mrx = (st != ST_CAPTURE);
-          n_trunc = (st == ST_TIMEOUT);
-          n_broke = (st == ST_NO_MONEY);
-          len_sum = t_new;
-          if (p.auto_reset) {  // same-step auto-reset: the observation describes the fresh episode
-            const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
-            const int ep = s.episode[e] + 1;
-            s.episode[e] = ep;
-            if (p.resample_graph) s.gid[e] = philox_graph_choice(p, env_id, (unsigned)ep);
-            philox_start_positions(p, env_id, (unsigned)ep, s.pos + e * AS);
-            s.money[e * AS] = p.mrx_money;
-            for (int i = 1; i <= P; ++i) s.money[e * AS + i] = p.agent_money;
-            t_new = 0;
-            s.clear_visits[e] = 1;
-            bel = BEL_UNIFORM;
-          } else {
-            s.done[e] = 1;
-          }
+  // ---- next-step state: timestep, reveal schedule, same-step auto-reset (Philox), statistics
+  int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
+  int t_new = t, done = frozen, bel = BEL_KEEP, revealed = -1;
+  bool clear_visits = false;
+  if (live) {
+    if (active) {
+      n_step = 1;
+      t_new = t + 1;  // yard.py:355
+      p.out.winner[b] = (int8_t)(status == ST_CAPTURE ? SY_WINNER_POLICE : (status == ST_RUNNING ? SY_WINNER_NONE : SY_WINNER_MRX));
+      bel = BEL_PROPAGATE;
+      if (status != ST_RUNNING) {
+        n_ep = 1;
+        n_pol = (status == ST_CAPTURE);
+        n_mrx = (status != ST_CAPTURE);
+        n_trunc = (status == ST_TIMEOUT);
+        n_broke = (status == ST_NO_MONEY);
+        len_sum = t_new;
+        if (p.auto_reset) {  // same-step auto-reset: the observation describes the fresh episode
+          const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
+          episode += 1;
+          if (p.resample_graph) g = philox_graph_choice(p, env_id, (unsigned)episode);
+          philox_start_positions(p, env_id, (unsigned)episode, pos, act);
+          money[0] = p.mrx_money;
+          for (int i = 1; i <= P; ++i) money[i] = p.agent_money;
+          t_new = 0;
+          clear_visits = true;
+          bel = BEL_UNIFORM;
+        } else {
+          done = 1;
         }
-        s.t[e] = t_new;
-        // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
-        const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
-        if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
-        s.bel_op[e] = bel;
-        s.revealed[e] = (p.reveal <= 0 || rev) ? s.pos[e * AS] : -1;
-      } else {
-        p.out.winner[b] = SY_WINNER_NONE;
-        const int t_cur = s.t[e];
-        const bool rev = p.reveal > 0 && t_cur > 0 && (t_cur % p.reveal) == 0;
-        s.revealed[e] = (p.reveal <= 0 || rev) ? s.pos[e * AS] : -1;
       }
+    } else {
+      p.out.winner[b] = SY_WINNER_NONE;
     }
-    if (p.out.stats) {
-      n_step = __reduce_add_sync(FULL, n_step);
-      n_ep = __reduce_add_sync(FULL, n_ep);
+    // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
+    const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
+    if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
+    revealed = (p.reveal <= 0 || rev) ? pos[0] : -1;
+  }
+  if (p.out.stats) {
+    n_step = __reduce_add_sync(FULL, n_step);
+    n_ep = __reduce_add_sync(FULL, n_ep);
+    spent = __reduce_add_sync(FULL, spent);
+    if (n_ep) {  // warp-uniform
       n_mrx = __reduce_add_sync(FULL, n_mrx);
       n_pol = __reduce_add_sync(FULL, n_pol);
       n_trunc = __reduce_add_sync(FULL, n_trunc);
       n_broke = __reduce_add_sync(FULL, n_broke);
       len_sum = __reduce_add_sync(FULL, len_sum);
-      spent = __reduce_add_sync(FULL, spent);
-      if (lane == 0) {
-        unsigned long long* st = reinterpret_cast<unsigned long long*>(p.out.stats);
-        atomicAdd(st + SY_STAT_ENV_STEPS, (unsigned long long)n_step);
-        if (n_ep) {
-          atomicAdd(st + SY_STAT_EPISODES, (unsigned long long)n_ep);
-          atomicAdd(st + SY_STAT_MRX_WINS, (unsigned long long)n_mrx);
-          atomicAdd(st + SY_STAT_POLICE_WINS, (unsigned long long)n_pol);
-          atomicAdd(st + SY_STAT_TRUNCATIONS, (unsigned long long)n_trunc);
-          atomicAdd(st + SY_STAT_OUT_OF_MONEY, (unsigned long long)n_broke);
-          atomicAdd(st + SY_STAT_SUM_EPISODE_LENGTH, (unsigned long long)len_sum);
-        }
-        if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
+    }
+    if (lane == 0) {
+      unsigned long long* st = reinterpret_cast<unsigned long long*>(p.out.stats);
+      atomicAdd(st + SY_STAT_ENV_STEPS, (unsigned long long)n_step);
+      if (n_ep) {
+        atomicAdd(st + SY_STAT_EPISODES, (unsigned long long)n_ep);
+        atomicAdd(st + SY_STAT_MRX_WINS, (unsigned long long)n_mrx);
+        atomicAdd(st + SY_STAT_POLICE_WINS, (unsigned long long)n_pol);
+        atomicAdd(st + SY_STAT_TRUNCATIONS, (unsigned long long)n_trunc);
+        atomicAdd(st + SY_STAT_OUT_OF_MONEY, (unsigned long long)n_broke);
+        atomicAdd(st + SY_STAT_SUM_EPISODE_LENGTH, (unsigned long long)len_sum);
       }
+      if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
     }
   }
-  __syncthreads();
-
-  // ---- phase 2
-  assemble_tile(p, s, sbel, tile0, nEnv);
+  store_state(p, wt, b0, nEnv, lane, t_new, g, episode, done, bel, revealed, clear_visits);
 }
 
 // ---------------------------------------------------------------------------------------------
-// reset kernel (yard.py:80-142): re-initialise the masked envs, rewrite every env's observations
+// reset kernel (yard.py:80-142): re-initialise the masked envs (same warp = 32 envs layout)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(THREADS) sy_reset_kernel(const Params p) {
-  __shared__ TileSmem s;
-  extern __shared__ float sbel[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int A = p.A, P = p.P;
+__global__ void __launch_bounds__(LOGIC_THREADS) sy_reset_kernel(const Params p) {
+  __shared__ WarpTile wts[LOGIC_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b0 = (blockIdx.x * (LOGIC_THREADS / 32) + warp) * 32;
+  if (b0 >= p.B) return;
+  WarpTile& wt = wts[warp];
+  const int nEnv = min(32, p.B - b0);
+  const int A = p.A;
+  const bool live = lane < nEnv;
+  const int b = b0 + lane;
+  const bool rst = live && (p.reset_mask == nullptr || p.reset_mask[b] != 0);
+  const unsigned rst_mask = __ballot_sync(FULL, rst);
+  for (int i = lane; i < nEnv * A; i += 32) {
+    const int e = i / A, a = i - e * A;
+    const size_t o = (size_t)b0 * A + i;
+    if ((rst_mask >> e) & 1u) {
+      wt.money[e * AS + a] = (a == 0) ? p.mrx_money : p.agent_money;  // yard.py:117-119
+      wt.pos[e * AS + a] = p.init_pos ? p.init_pos[o] : 0;
+    } else {
+      wt.money[e * AS + a] = p.st.money[o];
+      wt.pos[e * AS + a] = p.st.pos[o];
+    }
+  }
+  __syncwarp();
+  int t = 0, g = 0, episode = 0, done = 1, revealed = -1;
+  if (live) {
+    if (rst) {
+      episode = p.restart ? 0 : p.st.episode[b] + 1;
+      done = 0;
+      g = p.init_gid ? p.init_gid[b] : p.st.graph_id[b];
+      if (p.init_pos == nullptr) {
+        const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
+        if (p.resample_graph && p.init_gid == nullptr) g = philox_graph_choice(p, env_id, (unsigned)episode);
+        philox_start_positions(p, env_id, (unsigned)episode, wt.pos + lane * AS, wt.act + lane * AS);
+      }
+    } else {
+      t = p.st.timestep[b];
+      episode = p.st.episode[b];
+      done = p.st.done[b];
+      g = p.st.graph_id[b];
+    }
+    const bool rev = p.reveal > 0 && t > 0 && (t % p.reveal) == 0;
+    revealed = (p.reveal <= 0 || rev) ? wt.pos[lane * AS] : -1;
+  }
+  store_state(p, wt, b0, nEnv, lane, t, g, episode, done, rst ? BEL_UNIFORM : BEL_KEEP, revealed, rst);
+}
+
+// ---------------------------------------------------------------------------------------------
+// observe kernel: everything that is a pure function of the new state (yard.py:271-335 observation assembly
+// and the belief_map).  One CTA per 32-env tile, warp-specialised and barrier-free between the roles:
+//   writer warps: stream the dense observations.  Per env: 16-byte zero stores over the env's contiguous
+//                 action_mask [A,N] and node_features [N,A] regions, then -- while those lines are still in
+//                 L2 -- the few ones (affordable neighbours, one-hot positions).  Pure HBM write stream.
+//   belief warps: belief propagation (belief_module.py:69-111 in expectation) as a lane = env SpMM over the
+//                 tile's rows held TRANSPOSED in shared memory; latency-bound, hidden under the write stream.
+// ---------------------------------------------------------------------------------------------
+constexpr int BSTRIDE = TILE + 1;
+constexpr int BEL_JMAX = 128;  // nodes per belief warp on the fast path -> N <= BEL_WARPS * 128
+
+// warp-cooperative copy of n bytes from shared memory to global memory; src and dst have the same 16-byte phase
+__device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src, int n, int lane) {
+  const int head = min(n, (int)((16u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u));
+  if (lane < head) dst[lane] = src[lane];
+  const int nvec = (n - head) >> 4;
+  uint4* d = reinterpret_cast<uint4*>(dst + head);
+  const uint4* sv = reinterpret_cast<const uint4*>(src + head);
+#pragma unroll 2
+  for (int i = lane; i < nvec; i += 32) __stcs(d + i, sv[i]);
+  const int done = head + (nvec << 4);
+  if (lane < n - done) dst[done + lane] = src[done + lane];
+}
+
+// node_features of one env: n = N*A floats, all zero except the agents' one-hot entries at flat index fpos[a]
+// (yard.py:279-290).  Every 16-byte chunk is written exactly once: lane a assembles and stores the chunk that holds
+// agent a's one (a per-lane bitmask, filled through shared memory, tells the zero-fill loop to skip those chunks).
+__device__ __forceinline__ void warp_write_node_features(float* nf, int n, const int* fpos /*smem, A entries, -1 = none*/,
+                                                          unsigned long long* bits /*smem, 32 words, all zero*/, int A, int lane) {
+  const int head = min(n, (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(nf) & 15u)) & 15u) >> 2));
+  const int nvec = (n - head) >> 2;
+  const int tail0 = head + (nvec << 2);
+  int myc = -1;  // body chunk that holds this lane's agent
+  if (lane < A) {
+    const int f = fpos[lane] - head;
+    if (fpos[lane] >= 0 && f >= 0 && f < (nvec << 2)) {
+      myc = f >> 2;
+      atomicOr(bits + (myc & 31), 1ull << (myc >> 5));
+    }
+  }
+  __syncwarp();
+  const unsigned long long mine = bits[lane];  // bit t: chunk t * 32 + lane holds a one
+  if (lane < head || (lane >= 32 - (n - tail0))) {  // the few floats before / after the aligned body
+    const int f = lane < head ? lane : tail0 + (lane - (32 - (n - tail0)));
+    float v = 0.0f;
+    for (int a = 0; a < A; ++a) v = (fpos[a] == f) ? 1.0f : v;
+    nf[f] = v;
+  }
+  uint4* body = reinterpret_cast<uint4*>(nf + head);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  unsigned long long m = mine;
+#pragma unroll 4
+  for (int i = lane; i < nvec; i += 32, m >>= 1)
+    if (!(m & 1ull)) __stcs(body + i, z);
+  __syncwarp();
+  if (mine) bits[lane] = 0ull;
+  if (myc >= 0) {
+    uint4 v = z;
+    for (int a = 0; a < A; ++a) {
+      const int f = fpos[a] - head;
+      if (fpos[a] >= 0 && (f >> 2) == myc) {
+        const unsigned one = 0x3f800000u;
+        const int sub = f & 3;
+        v.x = sub == 0 ? one : v.x;
+        v.y = sub == 1 ? one : v.y;
+        v.z = sub == 2 ? one : v.z;
+        v.w = sub == 3 ? one : v.w;
+      }
+    }
+    __stcs(body + myc, v);
+  }
+}
+
+// writer warps: stream the dense observations of the tile.  Everything the ones depend on is staged into shared
+// memory first (one round trip for the whole tile): agents' nodes and budgets, reveal flags and -- when the tile sits
+// on one graph and its CSR fits -- the graph's row pointers / neighbours / weights.  Each env's action_mask rows are
+// assembled in a per-warp shared-memory image and copied out, node_features are assembled in registers: every byte of
+// the observations is stored exactly once (measured: byte-sized ones stored after a zero-fill cost 60% extra time).
+__device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
+  const Tables& tb = p.tb;
+  const int N = p.N, A = p.A;
+  int* s_pos = reinterpret_cast<int*>(dyn + p.wr_off);  // [TILE * A]
+  int* s_money = s_pos + TILE * A;                      // [TILE * A]
+  int* s_rev = s_money + TILE * A;                      // [TILE]
+  int* s_gid = s_rev + TILE;                            // [TILE]
+  int* s_fpos = s_gid + TILE;                           // [WR_WARPS * SY_MAX_AGENTS] flat node_features index per agent
+  unsigned long long* bits = reinterpret_cast<unsigned long long*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + w * 32;  // [WR_WARPS * 32]
+  uint8_t* s_img = reinterpret_cast<uint8_t*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + WR_WARPS * 32 * 8 + (size_t)w * p.wr_img_stride;  // mask image
+  int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);  // [N + 1]
+  uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
+  uint8_t* s_wgt = reinterpret_cast<uint8_t*>(s_col + tb.nnz_stride);
+  const int tw = w * 32 + lane;
+  const int gl = (lane < nEnv) ? p.st.graph_id[tile0 + lane] : -1;
+  const int g0 = __shfl_sync(FULL, gl, 0);
+  const bool staged = p.wr_stage_csr && __all_sync(FULL, gl == g0 || gl < 0);
+  for (int i = tw; i < nEnv * A; i += WR_WARPS * 32) {
+    s_pos[i] = p.st.pos[(size_t)tile0 * A + i];
+    s_money[i] = p.st.money[(size_t)tile0 * A + i];
+  }
+  if (tw < nEnv) {
+    s_rev[tw] = p.ob.mrx_revealed[tile0 + tw];
+    s_gid[tw] = gl;
+  }
+  if (staged) {
+    const int32_t* grp = tb.row_ptr + (size_t)g0 * (N + 1);
+    const int nnz = __ldg(grp + N);
+    for (int i = tw; i <= N; i += WR_WARPS * 32) s_rp[i] = __ldg(grp + i);
+    for (int k = tw; k < nnz; k += WR_WARPS * 32) {
+      s_col[k] = __ldg(tb.col + (size_t)g0 * tb.nnz_stride + k);
+      s_wgt[k] = __ldg(tb.wgt + (size_t)g0 * tb.nnz_stride + k);
+    }
+  }
+  for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
+  bits[lane] = 0ull;
+  named_barrier(2, WR_WARPS * 32);
+  int* fpos = s_fpos + w * SY_MAX_AGENTS;
+  const int lpa = 32 / A;
+  for (int e = w; e < nEnv; e += WR_WARPS) {
+    const int b = tile0 + e;
+    uint8_t* mask = p.ob.action_mask + (size_t)b * A * N;
+    float* nf = p.ob.node_features + (size_t)b * N * A;
+    const int phase = (int)(reinterpret_cast<uintptr_t>(mask) & 15u);
+    uint8_t* img = s_img + phase;  // same 16-byte phase as the destination
+    // ---- ones of this env into the shared-memory image (action_mask.py:65-76: adjacent and weight + toll <= budget)
+    const int ag = lane / lpa, sub = lane - ag * lpa;  // lpa lanes share one agent's neighbour list
+    if (ag < A && !(p.dbg_skip & 2)) {
+      const int u = s_pos[e * A + ag], m = s_money[e * A + ag], g = s_gid[e];
+      uint8_t* row = img + ag * N;
+      if (staged) {
+        const int r0 = s_rp[u], r1 = s_rp[u + 1];
+        for (int k = r0 + sub; k < r1; k += lpa)
+          if ((int)s_wgt[k] + p.toll <= m) row[s_col[k]] = 1;
+      } else {
+        const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1) + u;
+        const int r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
+        const uint8_t* wg = tb.wgt + (size_t)g * tb.nnz_stride;
+        for (int k = r0 + sub; k < r1; k += lpa)
+          if ((int)__ldg(wg + k) + p.toll <= m) row[__ldg(cl + k)] = 1;
+      }
+      // yard.py:279-290: one-hot positions; the MrX column stays blank while he is hidden
+      if (sub == 0) fpos[ag] = (ag > 0 || s_rev[e] >= 0) ? u * A + ag : -1;
+    }
+    __syncwarp();
+    warp_copy_bytes(mask, img, A * N, lane);
+    if (p.wr_nf_fast)
+      warp_write_node_features(nf, N * A, fpos, bits, A, lane);
+    else {  // very large N * A: zero-fill, then the ones (same warp, ordered by the __syncwarp)
+      warp_zero_bytes(reinterpret_cast<uint8_t*>(nf), N * A * (int)sizeof(float), lane);
+      __syncwarp();
+      if (lane < A && fpos[lane] >= 0) nf[fpos[lane]] = 1.0f;
+    }
+    __syncwarp();
+    for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+  }
+}
+
+// generic belief path: one warp per env, lane = node; any N, any mix of graphs.  sb: 2N floats of this warp.
+__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane) {
+  const int N = p.N;
+  const Tables& tb = p.tb;
+  float* bel = p.st.belief + (size_t)b * N;
+  if (op == BEL_UNIFORM) {
+    const float u = 1.0f / (float)N;
+    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = u;
+  } else if (op == BEL_DELTA) {
+    const int x = p.st.pos[(size_t)b * p.A];
+    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
+  } else if (op == BEL_PROPAGATE) {
+    const int g = p.st.graph_id[b];
+    const float* idg = tb.inv_deg + (size_t)g * N;
+    const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1);
+    const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
+    __syncwarp();
+    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) sb[j] = bel[j] * __ldg(idg + j);
+    __syncwarp();
+    float part = 0.0f;
+    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
+      const int r0 = __ldg(rp + j), r1 = __ldg(rp + j + 1);
+      float acc = 0.0f;
+      _Pragma("unroll 1") for (int k = r0; k < r1; ++k) acc += sb[__ldg(cl + k)];
+      if (r1 == r0) acc = bel[j];  // isolated node keeps its mass (belief_module.py:93-97)
+      sb[N + j] = acc;
+      part += acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    if (part == 0.0f) {  // belief_module.py:36-37
+      const float u = 1.0f / (float)N;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = u;
+    } else {
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = sb[N + j] / part;
+    }
+  }
+}
+
+__device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
+  const int N = p.N;
+  // every belief warp reads the same 32 flags / graph ids, so the branches below are uniform across the role
+  int op = BEL_KEEP, g = -1;
+  if (lane < nEnv) {
+    op = p.bel_flags[tile0 + lane];
+    g = p.st.graph_id[tile0 + lane];
+  }
+  const unsigned prop = __ballot_sync(FULL, op == BEL_PROPAGATE);
+  const unsigned any = __ballot_sync(FULL, op != BEL_KEEP);
+  if (!any) return;
+  const int g0 = __shfl_sync(FULL, g, prop ? __ffs(prop) - 1 : 0);
+  const bool fast = p.bel_fast && prop && __all_sync(FULL, op != BEL_PROPAGATE || g == g0);
+  if (!fast) {
+    float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * 2 * N;
+    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane);
+    return;
+  }
+  // fast path: tin[j * BSTRIDE + e] (transposed) so that lane = env: the CSR walk is warp-uniform (no divergence,
+  // neighbour entries are one broadcast LDS), every smem access is conflict-free, the normaliser is lane-local.
+  float* __restrict__ tin = reinterpret_cast<float*>(dyn);
+  float* __restrict__ tout = reinterpret_cast<float*>(dyn + p.bel_off_out);
+  float* __restrict__ part = reinterpret_cast<float*>(dyn + p.bel_off_part);
+  int4* __restrict__ spack = reinterpret_cast<int4*>(dyn + p.bel_off_pack);
+  const int32_t* rp = p.tb.row_ptr + (size_t)g0 * (N + 1);
+  const int4* gpack = p.tb.nbr_pack + (size_t)g0 * p.tb.pack_stride;
+  const int jpw = (N + BEL_WARPS - 1) / BEL_WARPS;  // warp w owns nodes [j0, j1) = CSR entries [k0, k1)
+  const int j0 = min(N, w * jpw), j1 = min(N, j0 + jpw);
+  const int k0 = __ldg(rp + j0), k1 = __ldg(rp + j1);
+  for (int e = w; e < TILE; e += BEL_WARPS) {
+    if ((prop >> e) & 1u) {
+      const float* bel = p.st.belief + (size_t)(tile0 + e) * N;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) cp_async4(tin + j * BSTRIDE + e, bel + j);
+    } else {
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) tin[j * BSTRIDE + e] = 0.0f;
+    }
+  }
+  for (int k = k0 + lane; k < k1; k += 32) cp_async16(spack + k, gpack + k);  // this warp's CSR segment
+  // isolated nodes keep their mass (belief_module.py:93-97): found while the copies are in flight
+  unsigned iso[(BEL_JMAX + 31) / 32];
+#pragma unroll
+  for (int r = 0; r < (BEL_JMAX + 31) / 32; ++r) {
+    const int j = j0 + r * 32 + lane;
+    iso[r] = __ballot_sync(FULL, j < j1 && __ldg(rp + j) == __ldg(rp + j + 1));
+  }
+  cp_async_wait_all();
+  named_barrier(1, BEL_WARPS * 32);
+  float sum = 0.0f, a = 0.0f;
+  const unsigned char* tin_lane = reinterpret_cast<const unsigned char*>(tin + lane);
+  unsigned char* tout_lane = reinterpret_cast<unsigned char*>(tout + lane);
+#pragma unroll 1
+  for (int k = k0; k < k1; k += 4) {  // 4 entries per trip: all shared-memory loads first, then the dependent FMA chain
+    int4 c[4];
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = spack[min(k + i, k1 - 1)];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float*>(tin_lane + c[i].x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (k + i < k1) {  // warp-uniform
+        a = fmaf(v[i], __int_as_float(c[i].y), a);
+        if (c[i].z >= 0) {  // last entry of its row; warp-uniform
+          *reinterpret_cast<float*>(tout_lane + c[i].z) = a;
+          sum += a;
+          a = 0.0f;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < (BEL_JMAX + 31) / 32; ++r) {
+    unsigned m = iso[r];
+    while (m) {
+      const int j = j0 + r * 32 + __ffs(m) - 1;
+      m &= m - 1;
+      const float v = tin[j * BSTRIDE + lane];
+      tout[j * BSTRIDE + lane] = v;
+      sum += v;
+    }
+  }
+  part[w * 32 + lane] = sum;
+  named_barrier(1, BEL_WARPS * 32);
+  // normalise + per-env operation, coalesced copy-out: warp per env, lane = node
+  const float unif = 1.0f / (float)N;
+  for (int e = w; e < nEnv; e += BEL_WARPS) {
+    const int ope = __shfl_sync(FULL, op, e);
+    if (ope == BEL_KEEP) continue;
+    float* bel = p.st.belief + (size_t)(tile0 + e) * N;
+    if (ope == BEL_PROPAGATE) {
+      float tot = 0.0f;
+#pragma unroll
+      for (int ww = 0; ww < BEL_WARPS; ++ww) tot += part[ww * 32 + e];
+      if (tot == 0.0f) {  // belief_module.py:29-38
+        _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+      } else {
+        const float inv = 1.0f / tot;
+        _Pragma("unroll 2") for (int j = lane; j < N; j += 32) bel[j] = tout[j * BSTRIDE + e] * inv;
+      }
+    } else if (ope == BEL_UNIFORM) {
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+    } else {
+      const int x = p.st.pos[(size_t)(tile0 + e) * p.A];
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile0 = blockIdx.x * TILE;
   const int nEnv = min(TILE, p.B - tile0);
-
-  if (tid < TILE) {
-    const bool live = tid < nEnv;
-    const int b = tile0 + tid;
-    const bool rst = live && (p.reset_mask == nullptr || p.reset_mask[b] != 0);
-    s.clear_visits[tid] = rst;
-    s.bel_op[tid] = rst ? BEL_UNIFORM : BEL_KEEP;
-    s.status[tid] = ST_RUNNING;
-    s.frozen[tid] = 0;
-    if (rst) {
-      s.t[tid] = 0;
-      s.episode[tid] = p.restart ? 0 : p.st.episode[b] + 1;
-      s.done[tid] = 0;
-      s.gid[tid] = p.init_gid ? p.init_gid[b] : p.st.graph_id[b];
-    } else {
-      s.t[tid] = live ? p.st.timestep[b] : 0;
-      s.episode[tid] = live ? p.st.episode[b] : 0;
-      s.done[tid] = live ? (int)p.st.done[b] : 1;
-      s.gid[tid] = live ? p.st.graph_id[b] : 0;
-    }
+  const int nbw = BEL_WARPS;  // without a belief map the belief warps simply exit
+  if (warp < nbw && !p.belief_on) return;
+  if (warp < nbw) {
+    if (!(p.dbg_skip & 4)) belief_role(p, dyn, tile0, nEnv, warp, lane);
+  } else if (!(p.dbg_skip & 1)) {
+    writer_role(p, dyn, tile0, nEnv, warp - nbw, lane);
   }
-  __syncthreads();
-  for (int i = tid; i < nEnv * A; i += THREADS) {
-    const int e = i / A, a = i - e * A;
-    const size_t o = (size_t)tile0 * A + i;
-    if (s.clear_visits[e]) {
-      s.money[e * AS + a] = (a == 0) ? p.mrx_money : p.agent_money;  // yard.py:117-119
-      s.pos[e * AS + a] = p.init_pos ? p.init_pos[o] : 0;
-    } else {
-      s.money[e * AS + a] = p.st.money[o];
-      s.pos[e * AS + a] = p.st.pos[o];
-    }
-  }
-  __syncthreads();
-  if (warp == 0 && lane < nEnv) {
-    const int e = lane, b = tile0 + e;
-    if (s.clear_visits[e] && p.init_pos == nullptr) {
-      const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
-      if (p.resample_graph && p.init_gid == nullptr) s.gid[e] = philox_graph_choice(p, env_id, (unsigned)s.episode[e]);
-      philox_start_positions(p, env_id, (unsigned)s.episode[e], s.pos + e * AS);
-    }
-    const int t_cur = s.t[e];
-    const bool rev = p.reveal > 0 && t_cur > 0 && (t_cur % p.reveal) == 0;
-    s.revealed[e] = (p.reveal <= 0 || rev) ? s.pos[e * AS] : -1;
-  }
-  (void)P;
-  __syncthreads();
-  assemble_tile(p, s, sbel, tile0, nEnv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -740,15 +1010,20 @@ struct SyEnv {
   void* d_wgt = nullptr;
   void* d_cnt = nullptr;
   void* d_inv_deg = nullptr;
+  void* d_pack = nullptr;
+  void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
   void* d_exp = nullptr;
   void* d_cov = nullptr;
-  size_t bel_smem = 0;
+  size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
+  int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0;
+  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, wr_nf_fast = 0;
+  size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
 
 namespace {
 
 void free_graph_tables(SyEnv* e) {
-  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg}) {
+  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack}) {
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
   }
@@ -784,19 +1059,29 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
     p.w32[i] = (float)c.reward_weights[i];
   }
   p.tb = env->tb;
+  {
+    static const int dbg = [] { const char* v = getenv("SY_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
+    p.dbg_skip = dbg;
+  }
+  p.bel_flags = (uint8_t*)env->d_bel_flags;
+  p.bel_fast = env->bel_fast;
+  p.bel_off_out = env->bel_off_out;
+  p.bel_off_part = env->bel_off_part;
+  p.bel_off_pack = env->bel_off_pack;
+  p.wr_off = env->wr_off;
+  p.wr_off_csr = env->wr_off_csr;
+  p.wr_img_stride = env->wr_img_stride;
+  p.wr_stage_csr = env->wr_stage_csr;
+  p.wr_nf_fast = env->wr_nf_fast;
   p.st = *st;
   if (ob) p.ob = *ob;
   if (out) p.out = *out;
   return SY_OK;
 }
 
-bool aligned16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0; }
-
 int check_obs(const SyObs* ob) {
   if (!ob || !ob->action_mask || !ob->node_features || !ob->agent_budget || !ob->mrx_revealed)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyObs has NULL members");
-  if (!aligned16(ob->action_mask) || !aligned16(ob->node_features))
-    return fail(SY_ERR_INVALID_ARGUMENT, "action_mask / node_features must be 16-byte aligned");
   return SY_OK;
 }
 
@@ -828,19 +1113,9 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
   SyEnv* e = new SyEnv();
   e->cfg = *c;
   e->A = c->num_police + 1;
-  e->bel_smem = c->belief ? (size_t)NWARPS * 2 * c->num_nodes * sizeof(float) : 0;
-  if (e->bel_smem > 160 * 1024) {
+  if (cudaMalloc(&e->d_bel_flags, (size_t)c->num_envs) != cudaSuccess) {
     delete e;
-    return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes too large for the belief kernel's shared memory");
-  }
-  if (e->bel_smem > 32 * 1024) {
-    cudaError_t err = cudaFuncSetAttribute(sy_step_kernel<SY_REWARD_FP64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bel_smem);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(sy_step_kernel<SY_REWARD_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bel_smem);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(sy_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->bel_smem);
-    if (err != cudaSuccess) {
-      delete e;
-      return fail(SY_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(err));
-    }
+    return fail(SY_ERR_CUDA, "cudaMalloc of the per-env flag buffer failed");
   }
   *out_env = e;
   return SY_OK;
@@ -852,6 +1127,7 @@ void sy_destroy(SyEnv* e) {
   free_graph_tables(e);
   if (e->d_exp) cudaFree(e->d_exp);
   if (e->d_cov) cudaFree(e->d_cov);
+  if (e->d_bel_flags) cudaFree(e->d_bel_flags);
   delete e;
 }
 
@@ -889,6 +1165,8 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   // validate + narrow on the host (setup path)
   std::vector<uint16_t> col16((size_t)G * nnz_stride, 0);
   std::vector<uint8_t> w8((size_t)G * nnz_stride, 0);
+  const int pack_stride = nnz_stride;
+  std::vector<int4> pack((size_t)G * pack_stride, make_int4(0, 0, -1, 0));
   int wcap = 1;
   for (int g = 0; g < G; ++g) {
     const int32_t* rp = row_ptr + (size_t)g * (N + 1);
@@ -903,6 +1181,11 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
         if (wt < 1 || wt > 255) return fail(SY_ERR_INVALID_ARGUMENT, "graph %d: edge weight %d outside 1..255", g, wt);
         col16[(size_t)g * nnz_stride + k] = (uint16_t)v;
         w8[(size_t)g * nnz_stride + k] = (uint8_t)wt;
+        const float inv_deg_v = 1.0f / (float)(rp[v + 1] - rp[v]);  // v has at least the edge back to u
+        int bits;
+        std::memcpy(&bits, &inv_deg_v, sizeof(bits));
+        pack[(size_t)g * pack_stride + k] = make_int4(v * BSTRIDE * (int)sizeof(float), bits,
+                                                       k == rp[u + 1] - 1 ? u * BSTRIDE * (int)sizeof(float) : -1, 0);
         if (wt > wcap) wcap = wt;
       }
     }
@@ -920,6 +1203,8 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   CUDA_TRY(cudaMalloc(&e->d_wgt, (size_t)G * nnz_stride));
   CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1)));
   CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_pack, pack.size() * sizeof(int4)));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pack, pack.data(), pack.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_row_ptr, row_ptr, (size_t)G * (N + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_col, col16.data(), col16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_wgt, w8.data(), w8.size(), cudaMemcpyHostToDevice, s));
@@ -947,6 +1232,42 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   e->tb.wgt = (const uint8_t*)e->d_wgt;
   e->tb.cnt = (const uint8_t*)e->d_cnt;
   e->tb.inv_deg = (const float*)e->d_inv_deg;
+  e->tb.nbr_pack = (const int4*)e->d_pack;
+  e->tb.pack_stride = pack_stride;
+  // dynamic shared memory of the observe kernel's belief warps (generic: BEL_WARPS x 2N floats; fast path: two
+  // transposed tiles [N][BSTRIDE] + per-warp partial sums)
+  e->bel_smem = 0;
+  e->bel_fast = 0;
+  if (e->cfg.belief) {
+    const size_t generic = (size_t)BEL_WARPS * 2 * N * sizeof(float);
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_out = up16((size_t)N * BSTRIDE * sizeof(float));
+    const size_t off_part = up16(2 * off_out);
+    const size_t off_pack = up16(off_part + (size_t)BEL_WARPS * 32 * sizeof(float));
+    const size_t fast = off_pack + (size_t)pack_stride * sizeof(int4);
+    if (fast <= 110 * 1024 && N <= BEL_WARPS * BEL_JMAX) {
+      e->bel_fast = 1;  // N <= ~400 (2 CTAs per SM); N <= ~250 keeps 3 CTAs per SM
+      e->bel_off_out = (int)off_out;
+      e->bel_off_part = (int)off_part;
+      e->bel_off_pack = (int)off_pack;
+    }
+    e->bel_smem = e->bel_fast && fast > generic ? fast : generic;
+    if (e->bel_smem > 180 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes too large for the belief kernel's shared memory");
+  }
+  {  // writer staging area: pos, money [TILE, A], revealed, graph id [TILE], per-warp flat one-hot indices and
+     // action_mask images, then (optionally) the graph's CSR
+    const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
+    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + WR_WARPS * SY_MAX_AGENTS) * sizeof(int) + WR_WARPS * 32 * 8 + WR_WARPS * img_stride;
+    const size_t csr = (size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3 + 16;
+    e->wr_off = (int)((e->bel_smem + 15) & ~(size_t)15);
+    e->wr_img_stride = (int)img_stride;
+    e->wr_off_csr = (int)(((size_t)e->wr_off + base + 15) & ~(size_t)15);
+    e->wr_stage_csr = (csr <= 32 * 1024 && (size_t)e->wr_off_csr + csr <= 200 * 1024) ? 1 : 0;
+    e->wr_nf_fast = ((size_t)N * e->A <= 8000) ? 1 : 0;  // chunk bitmask of warp_write_node_features is 64 bits
+    e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
+    if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
+    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
+  }
   e->tb.G = G;
   e->tb.Ns = Ns;
   e->tb.nnz_stride = nnz_stride;
@@ -980,8 +1301,11 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
   p.init_gid = init_gid;
   p.restart = restart;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
-  sy_reset_kernel<<<grid, THREADS, e->bel_smem, (cudaStream_t)stream>>>(p);
+  cudaStream_t s = (cudaStream_t)stream;
+  sy_reset_kernel<<<(unsigned)((p.B + LOGIC_THREADS - 1) / LOGIC_THREADS), LOGIC_THREADS, 0, s>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  sy_observe_kernel<<<(unsigned)((p.B + TILE - 1) / TILE), THREADS, e->obs_smem, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
@@ -997,12 +1321,16 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   if ((rc = check_obs(ob))) return rc;
   p.actions = reinterpret_cast<const long long*>(actions);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
+  const unsigned grid = (unsigned)((p.B + LOGIC_THREADS - 1) / LOGIC_THREADS);
   cudaStream_t s = (cudaStream_t)stream;
-  if (e->cfg.reward_mode == SY_REWARD_FP64)
-    sy_step_kernel<SY_REWARD_FP64><<<grid, THREADS, e->bel_smem, s>>>(p);
+  if (p.dbg_skip & 32) {
+  } else if (e->cfg.reward_mode == SY_REWARD_FP64)
+    sy_logic_kernel<SY_REWARD_FP64><<<grid, LOGIC_THREADS, 0, s>>>(p);
   else
-    sy_step_kernel<SY_REWARD_FP32><<<grid, THREADS, e->bel_smem, s>>>(p);
+    sy_logic_kernel<SY_REWARD_FP32><<<grid, LOGIC_THREADS, 0, s>>>(p);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  if (!(p.dbg_skip & 16)) sy_observe_kernel<<<(unsigned)((p.B + TILE - 1) / TILE), THREADS, e->obs_smem, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;

@@ -1,0 +1,20 @@
+#!/usr/bin/env python
+"""Key raw metrics of an ncu report. usage: python tools/ncu_summary.py report.ncu-rep"""
+import csv, io, subprocess, sys
+txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(txt)))
+hdr, units = rows[0], rows[1]
+want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'launch__occupancy_limit_warps', 'launch__waves_per_multiprocessor', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum', 'smsp__inst_executed.sum', 'launch__shared_mem_per_block_static', 'launch__shared_mem_per_block_dynamic',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'lts__t_sector_hit_rate.pct', 'smsp__warps_eligible.avg.per_cycle_active',
+        'sm__cycles_active.avg', 'sm__cycles_elapsed.max', 'lts__t_sectors_op_write.sum', 'lts__t_sectors_op_read.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'sm__cycles_active.max', 'sm__cycles_active.min', 'lts__t_sectors_srcunit_tex_op_write.sum', 'dram__sectors_write.sum']
+for w in want:
+    if w in hdr:
+        i = hdr.index(w)
+        print(f"{w:70s} {units[i]:14s} {[r[i] for r in rows[2:]]}")
