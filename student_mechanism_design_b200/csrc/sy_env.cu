@@ -12,10 +12,10 @@
 //
 // Two launches per step (measured on B200: a fused per-tile kernel ran its phases in lockstep over the whole
 // chip -- every phase added its full latency and HBM idled during the game logic):
-//   sy_logic_kernel    thread per env (warp = 32 envs, agents in a conflict-free smem row), no CTA barrier; all
-//                      65 536 envs of a batch are resident in one wave so their dependent table lookups overlap.
-//                      Moves -> ending -> visit counts + rewards (fp64 / no-FMA fp32) -> timestep, reveal schedule,
-//                      same-step auto-reset (Philox) -> coalesced state / result write-back, statistics.
+//   sy_logic_kernel    CTA of 4 warps per 32-env tile, lane = env, agents in a conflict-free smem row; the whole batch is
+//                      resident in one wave.  Warp 0: order-dependent moves -> ending; all warps: visit counts + rewards
+//                      (warp = agent; fp64 / no-FMA fp32); warp 0: timestep, reveal schedule, same-step auto-reset
+//                      (Philox), statistics; coalesced state / result write-back.
 //   sy_observe_kernel  CTA per 32-env tile, warp-specialised, no barrier between the roles: writer warps stream the
 //                      dense observations (16-byte zero stores + the few ones while the lines sit in L2); belief
 //                      warps run the belief propagation as a lane = env SpMM over a transposed smem tile (LDGSTS).
@@ -61,7 +61,7 @@ constexpr int WR_WARPS = 8;    // ... warps 8..15 stream the dense observations
 constexpr int THREADS = (BEL_WARPS + WR_WARPS) * 32;
 constexpr int EXP_SMEM = 128;  // logic kernel: exp(-d) entries staged in shared memory
 constexpr int COV_SMEM = 256;  // logic kernel: coverage entries staged in shared memory
-constexpr int LOGIC_THREADS = 128;  // logic / reset kernels: 4 warps x 32 envs, no CTA barrier
+constexpr int LOGIC_THREADS = 128;  // logic kernel: 4 warps per 32-env tile; reset kernel: 4 warps x 32 envs
 constexpr int AS = SY_MAX_AGENTS + 1;  // odd smem row stride -> conflict-free lane = env access
 constexpr unsigned FULL = 0xffffffffu;
 enum { DIST_INF = 0xFFFF };
@@ -78,8 +78,9 @@ struct Tables {
   const uint8_t* wgt;    // [G, nnz_stride]
   const uint8_t* cnt;    // [G, N, wcap+1] #neighbours with weight <= c
   const float* inv_deg;  // [G, N]
-  const int4* nbr_pack;  // [G, pack_stride] per CSR entry {byte offset of the nbr's tile row, bits of 1/deg(nbr), byte offset of the
-                         //  output row on the row's last entry else -1, 0}
+  const int2* nbr_pack;  // [G, pack_stride] belief fast path: per neighbour {byte offset of its tile row, bits of 1/deg(nbr)};
+                         //  every node's list is padded to a multiple of 4 entries with {0, 0.0f}
+  const int32_t* pack_ptr;  // [G, N+1] start of each node's list in nbr_pack (entries)
   const double* exp_neg; // [n_exp]
   const double* coverage;  // [n_cov]
   int n_exp, n_cov, G, Ns, nnz_stride, wcap, pack_stride;
@@ -97,7 +98,7 @@ struct Params {
   SyObs ob;
   SyOut out;
   const long long* actions;
-  int bel_fast, bel_off_out, bel_off_part, bel_off_pack;  // belief fast path: dynamic smem layout (bytes)
+  int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr, wr_nf_fast;  // writer warps: smem staging layout (bytes) and path flags
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
@@ -158,9 +159,6 @@ __device__ __forceinline__ int philox_graph_choice(const Params& p, unsigned env
 __device__ __forceinline__ int edge_weight(const Tables& tb, int N, int g, int u, int v) {
   return __ldg(tb.W + ((size_t)g * N + u) * tb.Ns + v);
 }
-__device__ __forceinline__ int dist_of(const Tables& tb, int N, int g, int u, int v) {
-  return __ldg(tb.D + ((size_t)g * N + u) * N + v);
-}
 // len(_get_possible_moves(pos, .)[0]) for a budget (yard.py:420-472), with the toll extension
 __device__ __forceinline__ int move_count(const Tables& tb, int N, int g, int u, int money, int toll) {
   int c = money - toll;
@@ -204,19 +202,20 @@ __device__ __forceinline__ void warp_zero_bytes(uint8_t* ptr, int n, int lane) {
 // logic kernel pieces.  lane = env; the env's agents live in a shared-memory row (stride AS, conflict-free)
 // ---------------------------------------------------------------------------------------------
 struct WarpTile {
-  int act[32 * AS];    // normalised actions; reused as reward bits / Philox scratch; slot [AS-1] = status word
+  int act[32 * AS];    // normalised actions, then visit counts / reward bits; reset kernel: Philox scratch
   int pos[32 * AS];
   int money[32 * AS];
 };
 
 // the order-dependent move rule (yard.py:155-243) and the ending (reward_calculator.py:63-79).  An agent's own node
 // does not change before its own move, so all A edge-weight lookups are issued up front (one round trip).
+template <int MAXA>
 __device__ __forceinline__ int move_phase(const Params& p, int* pos, int* money, const int* act, int g, int t, int& spent) {
   const Tables& tb = p.tb;
   const int N = p.N, P = p.P;
-  int wpre[SY_MAX_AGENTS];
+  int wpre[MAXA];
 #pragma unroll
-  for (int i = 0; i < SY_MAX_AGENTS; ++i) wpre[i] = (i <= P && act[i] >= 0) ? edge_weight(tb, N, g, pos[i], act[i]) : 0;
+  for (int i = 0; i < MAXA; ++i) wpre[i] = (i <= P && act[i] >= 0) ? edge_weight(tb, N, g, pos[i], act[i]) : 0;
   {  // MrX: legal target or stay; may not step onto a police node (yard.py:161-188)
     const int a0 = act[0], u = pos[0];
     int tgt = u;
@@ -227,7 +226,7 @@ __device__ __forceinline__ int move_phase(const Params& p, int* pos, int* money,
   }
   bool no_money = true;
 #pragma unroll
-  for (int i = 1; i < SY_MAX_AGENTS; ++i) {  // police in order; later police see earlier moves (yard.py:192-243)
+  for (int i = 1; i < MAXA; ++i) {  // police in order; later police see earlier moves (yard.py:192-243)
     if (i > P) break;
     const int ai = act[i], m = money[i], u = pos[i];
     if (ai == -1 || m == 0) continue;  // None / DEFAULT_ACTION / broke: skipped (yard.py:210-215)
@@ -259,7 +258,7 @@ __device__ __forceinline__ double exp_neg_s(const Tables& tb, const RewardTables
 // reward of agent a (reward_calculator.py:26-92 endings, :94-266 shaped), float64 value (fp32 mode: the float, widened).
 // All distance lookups of the agent are issued before any is used (memory-level parallelism; the loops are fully
 // unrolled over SY_MAX_AGENTS with a break so that the values stay in registers).
-template <int MODE>
+template <int MODE, int MAXA>
 __device__ __forceinline__ double agent_reward(const Params& p, const RewardTables& rt, const int* pos, const int* money, int g,
                                                int t, int status, int a, int visits_here) {
   const Tables& tb = p.tb;
@@ -268,16 +267,17 @@ __device__ __forceinline__ double agent_reward(const Params& p, const RewardTabl
   if (status != ST_RUNNING) return (a == 0) ? 1.0 : 0.0;
   const double tt = (double)t;
   const int u = pos[a];
-  int dj[SY_MAX_AGENTS];  // d(u, pos[j]), j = 0 is MrX
+  int dj[MAXA];  // d(u, pos[j]), j = 0 is MrX
+  const uint16_t* drow = tb.D + ((size_t)g * N + u) * N;
 #pragma unroll
-  for (int j = 0; j < SY_MAX_AGENTS; ++j) dj[j] = (j <= P) ? dist_of(tb, N, g, u, pos[j]) : 0;
+  for (int j = 0; j < MAXA; ++j) dj[j] = (j <= P) ? (int)__ldg(drow + pos[j]) : 0;
   if (a == 0) {
     // reward_calculator.py:126-148
     int dmin = DIST_INF;
     long long dsum = 0;
     bool any_inf = false;
 #pragma unroll
-    for (int i = 1; i < SY_MAX_AGENTS; ++i) {
+    for (int i = 1; i < MAXA; ++i) {
       if (i > P) break;
       dmin = min(dmin, dj[i]);
       any_inf |= (dj[i] == DIST_INF);
@@ -310,7 +310,7 @@ __device__ __forceinline__ double agent_reward(const Params& p, const RewardTabl
   const double dx = exp_neg_s(tb, rt, dj[0]);
   double grp = 0.0, ov = 0.0, prox = 0.0;
 #pragma unroll
-  for (int j = 0; j < SY_MAX_AGENTS - 1; ++j) {
+  for (int j = 0; j < MAXA - 1; ++j) {
     if (j >= P) break;
     if (j == k) continue;
     const int d = dj[1 + j];
@@ -369,25 +369,35 @@ __device__ __forceinline__ void store_state(const Params& p, const WarpTile& wt,
 }
 
 // ---------------------------------------------------------------------------------------------
-// logic kernel: one thread per env, one warp per 32 consecutive envs, no CTA-wide barriers.  All envs of a
-// 65 536-env batch are resident at once (single wave), so the dependent lookups of different envs overlap.
+// logic kernel: one CTA of 4 warps per 32-env tile, lane = env.  A warp executes a few thousand dependent
+// instructions per tile, so the work is spread over the warps wherever the rule allows: warp 0 runs the
+// order-dependent moves, all four warps the per-agent rewards (warp = agent), warp 0 the next-step state (Philox
+// auto-reset) while warps 1..3 write the results; loads that do not depend on each other are issued together.
+// MAXA (4 / 8 / 16 >= A) bounds the fully unrolled per-agent loops so that their values stay in registers.
 // ---------------------------------------------------------------------------------------------
-template <int MODE>
+struct LogicSmem {
+  WarpTile wt;
+  RewardTables rt;
+  int scratch[32 * AS];
+  int reset_pos[32 * AS];  // start nodes of the next episode, drawn speculatively
+  int reset_gid[32];
+  int t[32], gid[32], episode[32], frozen[32], status[32];
+  int t_new[32], done[32], bel[32], revealed[32], clear[32];
+};
+
+template <int MODE, int MAXA>
 __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p) {
-  __shared__ WarpTile wts[LOGIC_THREADS / 32];
-  __shared__ RewardTables rt;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < EXP_SMEM; i += LOGIC_THREADS) rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
-  for (int i = threadIdx.x; i < COV_SMEM; i += LOGIC_THREADS) rt.coverage[i] = __ldg(p.tb.coverage + min(i, p.tb.n_cov - 1));
-  __syncthreads();  // the only CTA-wide barrier: tables staged
-  const int b0 = (blockIdx.x * (LOGIC_THREADS / 32) + warp) * 32;
-  if (b0 >= p.B) return;
-  WarpTile& wt = wts[warp];
+  __shared__ LogicSmem sm;
+  WarpTile& wt = sm.wt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b0 = blockIdx.x * 32;
   const int nEnv = min(32, p.B - b0);
   const int N = p.N, A = p.A, P = p.P;
 
-  // ---- stage the warp's AoS rows (coalesced)
-  for (int i = lane; i < nEnv * A; i += 32) {
+  // ---- P0: stage the tile (coalesced) and the head of the two float64 tables
+  for (int i = tid; i < EXP_SMEM; i += LOGIC_THREADS) sm.rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
+  for (int i = tid; i < COV_SMEM; i += LOGIC_THREADS) sm.rt.coverage[i] = __ldg(p.tb.coverage + min(i, p.tb.n_cov - 1));
+  for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = i / A, a = i - e * A;
     const size_t o = (size_t)b0 * A + i;
     const long long a64 = p.actions[o];
@@ -395,126 +405,172 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
     wt.pos[e * AS + a] = p.st.pos[o];
     wt.money[e * AS + a] = p.st.money[o];
   }
+  if (tid < 32) {
+    const bool live = tid < nEnv;
+    const int b = b0 + tid;
+    sm.t[tid] = live ? p.st.timestep[b] : 0;
+    sm.gid[tid] = live ? p.st.graph_id[b] : 0;
+    sm.episode[tid] = live ? p.st.episode[b] : 0;
+    sm.frozen[tid] = live ? (int)p.st.done[b] : 1;
+    sm.status[tid] = ST_RUNNING;
+  }
+  __syncthreads();
   const bool live = lane < nEnv;
   const int b = b0 + lane;
-  int t = 0, g = 0, episode = 0, frozen = 1;
-  if (live) {
-    t = p.st.timestep[b];
-    g = p.st.graph_id[b];
-    episode = p.st.episode[b];
-    frozen = p.st.done[b];
-  }
-  __syncwarp();
+  const int t = sm.t[lane], g = sm.gid[lane], frozen = sm.frozen[lane];
+  const bool active = live && !frozen;
   int* pos = wt.pos + lane * AS;
   int* money = wt.money + lane * AS;
   int* act = wt.act + lane * AS;
 
-  // ---- moves + ending
-  int status = ST_RUNNING, spent = 0;
-  const bool active = live && !frozen;
-  if (active) status = move_phase(p, pos, money, act, g, t, spent);
+  // ---- P1: moves + ending, warp 0  ||  warp 1: the start nodes (and graph) a same-step auto-reset WOULD draw --
+  // Philox(seed; env, episode + 1) does not depend on the outcome, so it is computed off the critical path
+  int spent = 0;
+  if (warp == 0) {
+    if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent);
+  } else if (warp == 1 && p.auto_reset && active) {
+    const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
+    const unsigned ep = (unsigned)(sm.episode[lane] + 1);
+    sm.reset_gid[lane] = p.resample_graph ? philox_graph_choice(p, env_id, ep) : g;
+    philox_start_positions(p, env_id, ep, sm.reset_pos + lane * AS, sm.scratch + lane * AS);
+  }
+  __syncthreads();
 
-  // ---- visit counts (yard.py:244-245) and rewards; reward bits go to the (now dead) action slots
+  // ---- P2: visit counts (yard.py:244-245) and rewards, warp = agent; reward bits go to the (now dead) action slots
+  const int status = sm.status[lane];
   if (live) {
-    if (active) {  // police never share a node (yard.py:231), so the P counters are distinct: load all, then store
-      uint16_t* vrow = p.st.visits + (size_t)b * N;
-      int vis[SY_MAX_AGENTS];
-#pragma unroll
-      for (int i = 1; i < SY_MAX_AGENTS; ++i) vis[i] = (i <= P) ? (int)vrow[pos[i]] + 1 : 0;
-#pragma unroll
-      for (int i = 1; i < SY_MAX_AGENTS; ++i) {
-        if (i > P) break;
-        vrow[pos[i]] = (uint16_t)min(vis[i], 0xFFFF);
-        act[i] = vis[i];  // stash for the reward below (the action slots are dead after the moves)
-      }
-    }
 #pragma unroll 1
-    for (int a = 0; a < A; ++a) {
+    for (int a = warp; a < A; a += LOGIC_THREADS / 32) {
       double r64 = 0.0;
-      if (active) r64 = agent_reward<MODE>(p, rt, pos, money, g, t, status, a, a > 0 ? act[a] : 0);
+      if (active) {
+        int visits_here = 0;
+        if (a > 0) {  // police never share a node (yard.py:231): the P counters of an env are distinct addresses
+          uint16_t* vp = p.st.visits + (size_t)b * N + pos[a];
+          visits_here = (int)(*vp) + 1;
+          *vp = (uint16_t)min(visits_here, 0xFFFF);
+        }
+        r64 = agent_reward<MODE, MAXA>(p, sm.rt, pos, money, g, t, status, a, visits_here);
+      }
       act[a] = __float_as_int((float)r64);
       if (p.out.reward64) p.out.reward64[(size_t)b * A + a] = r64;
     }
-    act[AS - 1] = status | (frozen << 8);
   }
-  __syncwarp();
-  for (int i = lane; i < nEnv * A; i += 32) {  // results of this step, coalesced
+  __syncthreads();
+
+  // ---- P3: warps 1..3 write the results (coalesced)  ||  warp 0 computes the next-step state
+  if (warp > 0) {
+    for (int i = tid - 32; i < nEnv * A; i += LOGIC_THREADS - 32) {
+      const int e = i / A, a = i - e * A;
+      const size_t o = (size_t)b0 * A + i;
+      const int st = sm.status[e];
+      const bool term = (st == ST_CAPTURE) || (st == ST_NO_MONEY), trunc = (st == ST_TIMEOUT);
+      p.out.reward[o] = __int_as_float(wt.act[e * AS + a]);
+      p.out.terminated[o] = term;
+      p.out.truncated[o] = trunc;
+      p.out.done[o] = term || trunc || sm.frozen[e];
+    }
+  } else {
+    // timestep, reveal schedule, same-step auto-reset (Philox), statistics
+    int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
+    int t_new = t, done = frozen, bel = BEL_KEEP, revealed = -1, episode = sm.episode[lane], gnew = g;
+    bool clear_visits = false;
+    if (live) {
+      if (active) {
+        n_step = 1;
+        t_new = t + 1;  // yard.py:355
+        p.out.winner[b] = (int8_t)(status == ST_CAPTURE ? SY_WINNER_POLICE : (status == ST_RUNNING ? SY_WINNER_NONE : SY_WINNER_MRX));
+        bel = BEL_PROPAGATE;
+        if (status != ST_RUNNING) {
+          n_ep = 1;
+          n_pol = (status == ST_CAPTURE);
+          n_mrx = (status != ST_CAPTURE);
+          n_trunc = (status == ST_TIMEOUT);
+          n_broke = (status == ST_NO_MONEY);
+          len_sum = t_new;
+          if (p.auto_reset) {  // same-step auto-reset: the observation describes the fresh episode
+            episode += 1;
+            gnew = sm.reset_gid[lane];
+            money[0] = p.mrx_money;
+            pos[0] = sm.reset_pos[lane * AS];
+            for (int i = 1; i <= P; ++i) {
+              money[i] = p.agent_money;
+              pos[i] = sm.reset_pos[lane * AS + i];
+            }
+            t_new = 0;
+            clear_visits = true;
+            bel = BEL_UNIFORM;
+          } else {
+            done = 1;
+          }
+        }
+      } else {
+        p.out.winner[b] = SY_WINNER_NONE;
+      }
+      // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
+      const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
+      if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
+      revealed = (p.reveal <= 0 || rev) ? pos[0] : -1;
+    }
+    sm.t_new[lane] = t_new;
+    sm.gid[lane] = gnew;
+    sm.episode[lane] = episode;
+    sm.done[lane] = done;
+    sm.bel[lane] = bel;
+    sm.revealed[lane] = revealed;
+    sm.clear[lane] = clear_visits;
+    if (p.out.stats) {
+      n_step = __reduce_add_sync(FULL, n_step);
+      n_ep = __reduce_add_sync(FULL, n_ep);
+      spent = __reduce_add_sync(FULL, spent);
+      if (n_ep) {  // warp-uniform
+        n_mrx = __reduce_add_sync(FULL, n_mrx);
+        n_pol = __reduce_add_sync(FULL, n_pol);
+        n_trunc = __reduce_add_sync(FULL, n_trunc);
+        n_broke = __reduce_add_sync(FULL, n_broke);
+        len_sum = __reduce_add_sync(FULL, len_sum);
+      }
+      if (lane == 0) {
+        unsigned long long* st = reinterpret_cast<unsigned long long*>(p.out.stats);
+        atomicAdd(st + SY_STAT_ENV_STEPS, (unsigned long long)n_step);
+        if (n_ep) {
+          atomicAdd(st + SY_STAT_EPISODES, (unsigned long long)n_ep);
+          atomicAdd(st + SY_STAT_MRX_WINS, (unsigned long long)n_mrx);
+          atomicAdd(st + SY_STAT_POLICE_WINS, (unsigned long long)n_pol);
+          atomicAdd(st + SY_STAT_TRUNCATIONS, (unsigned long long)n_trunc);
+          atomicAdd(st + SY_STAT_OUT_OF_MONEY, (unsigned long long)n_broke);
+          atomicAdd(st + SY_STAT_SUM_EPISODE_LENGTH, (unsigned long long)len_sum);
+        }
+        if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85)
+  for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = i / A, a = i - e * A;
     const size_t o = (size_t)b0 * A + i;
-    const int sw = wt.act[e * AS + AS - 1], st = sw & 0xff;
-    const bool term = (st == ST_CAPTURE) || (st == ST_NO_MONEY), trunc = (st == ST_TIMEOUT);
-    p.out.reward[o] = __int_as_float(wt.act[e * AS + a]);
-    p.out.terminated[o] = term;
-    p.out.truncated[o] = trunc;
-    p.out.done[o] = term || trunc || (sw >> 8);
+    const int m = wt.money[e * AS + a];
+    p.st.pos[o] = wt.pos[e * AS + a];
+    p.st.money[o] = m;
+    p.ob.agent_budget[o] = (float)m;  // yard.py:329-331
   }
-  __syncwarp();
-
-  // ---- next-step state: timestep, reveal schedule, same-step auto-reset (Philox), statistics
-  int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
-  int t_new = t, done = frozen, bel = BEL_KEEP, revealed = -1;
-  bool clear_visits = false;
-  if (live) {
-    if (active) {
-      n_step = 1;
-      t_new = t + 1;  // yard.py:355
-      p.out.winner[b] = (int8_t)(status == ST_CAPTURE ? SY_WINNER_POLICE : (status == ST_RUNNING ? SY_WINNER_NONE : SY_WINNER_MRX));
-      bel = BEL_PROPAGATE;
-      if (status != ST_RUNNING) {
-        n_ep = 1;
-        n_pol = (status == ST_CAPTURE);
-        n_mrx = (status != ST_CAPTURE);
-        n_trunc = (status == ST_TIMEOUT);
-        n_broke = (status == ST_NO_MONEY);
-        len_sum = t_new;
-        if (p.auto_reset) {  // same-step auto-reset: the observation describes the fresh episode
-          const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
-          episode += 1;
-          if (p.resample_graph) g = philox_graph_choice(p, env_id, (unsigned)episode);
-          philox_start_positions(p, env_id, (unsigned)episode, pos, act);
-          money[0] = p.mrx_money;
-          for (int i = 1; i <= P; ++i) money[i] = p.agent_money;
-          t_new = 0;
-          clear_visits = true;
-          bel = BEL_UNIFORM;
-        } else {
-          done = 1;
-        }
-      }
-    } else {
-      p.out.winner[b] = SY_WINNER_NONE;
-    }
-    // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
-    const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
-    if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
-    revealed = (p.reveal <= 0 || rev) ? pos[0] : -1;
+  if (tid < nEnv) {
+    const int bb = b0 + tid;
+    p.st.timestep[bb] = sm.t_new[tid];
+    p.st.graph_id[bb] = sm.gid[tid];
+    p.st.episode[bb] = sm.episode[tid];
+    p.st.done[bb] = (uint8_t)sm.done[tid];
+    p.ob.mrx_revealed[bb] = sm.revealed[tid];
+    p.bel_flags[bb] = (uint8_t)sm.bel[tid];
   }
-  if (p.out.stats) {
-    n_step = __reduce_add_sync(FULL, n_step);
-    n_ep = __reduce_add_sync(FULL, n_ep);
-    spent = __reduce_add_sync(FULL, spent);
-    if (n_ep) {  // warp-uniform
-      n_mrx = __reduce_add_sync(FULL, n_mrx);
-      n_pol = __reduce_add_sync(FULL, n_pol);
-      n_trunc = __reduce_add_sync(FULL, n_trunc);
-      n_broke = __reduce_add_sync(FULL, n_broke);
-      len_sum = __reduce_add_sync(FULL, len_sum);
-    }
-    if (lane == 0) {
-      unsigned long long* st = reinterpret_cast<unsigned long long*>(p.out.stats);
-      atomicAdd(st + SY_STAT_ENV_STEPS, (unsigned long long)n_step);
-      if (n_ep) {
-        atomicAdd(st + SY_STAT_EPISODES, (unsigned long long)n_ep);
-        atomicAdd(st + SY_STAT_MRX_WINS, (unsigned long long)n_mrx);
-        atomicAdd(st + SY_STAT_POLICE_WINS, (unsigned long long)n_pol);
-        atomicAdd(st + SY_STAT_TRUNCATIONS, (unsigned long long)n_trunc);
-        atomicAdd(st + SY_STAT_OUT_OF_MONEY, (unsigned long long)n_broke);
-        atomicAdd(st + SY_STAT_SUM_EPISODE_LENGTH, (unsigned long long)len_sum);
-      }
-      if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
-    }
+  unsigned clr = __ballot_sync(FULL, live && sm.clear[lane]);
+  for (int n = 0; clr; ++n) {
+    const int e = __ffs(clr) - 1;
+    clr &= clr - 1;
+    if ((n & (LOGIC_THREADS / 32 - 1)) == warp)
+      warp_zero_bytes(reinterpret_cast<uint8_t*>(p.st.visits + (size_t)(b0 + e) * N), N * (int)sizeof(uint16_t), lane);
   }
-  store_state(p, wt, b0, nEnv, lane, t_new, g, episode, done, bel, revealed, clear_visits);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -788,12 +844,13 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   float* __restrict__ tin = reinterpret_cast<float*>(dyn);
   float* __restrict__ tout = reinterpret_cast<float*>(dyn + p.bel_off_out);
   float* __restrict__ part = reinterpret_cast<float*>(dyn + p.bel_off_part);
-  int4* __restrict__ spack = reinterpret_cast<int4*>(dyn + p.bel_off_pack);
-  const int32_t* rp = p.tb.row_ptr + (size_t)g0 * (N + 1);
-  const int4* gpack = p.tb.nbr_pack + (size_t)g0 * p.tb.pack_stride;
-  const int jpw = (N + BEL_WARPS - 1) / BEL_WARPS;  // warp w owns nodes [j0, j1) = CSR entries [k0, k1)
+  int2* __restrict__ spack = reinterpret_cast<int2*>(dyn + p.bel_off_pack);
+  int* __restrict__ sptr = reinterpret_cast<int*>(dyn + p.bel_off_ptr);
+  const int32_t* gptr = p.tb.pack_ptr + (size_t)g0 * (N + 1);
+  const int2* gpack = p.tb.nbr_pack + (size_t)g0 * p.tb.pack_stride;
+  const int jpw = (N + BEL_WARPS - 1) / BEL_WARPS;  // warp w owns nodes [j0, j1) = list entries [q0, q1)
   const int j0 = min(N, w * jpw), j1 = min(N, j0 + jpw);
-  const int k0 = __ldg(rp + j0), k1 = __ldg(rp + j1);
+  const int q0 = __ldg(gptr + j0), q1 = __ldg(gptr + j1);
   for (int e = w; e < TILE; e += BEL_WARPS) {
     if ((prop >> e) & 1u) {
       const float* bel = p.st.belief + (size_t)(tile0 + e) * N;
@@ -802,38 +859,43 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) tin[j * BSTRIDE + e] = 0.0f;
     }
   }
-  for (int k = k0 + lane; k < k1; k += 32) cp_async16(spack + k, gpack + k);  // this warp's CSR segment
-  // isolated nodes keep their mass (belief_module.py:93-97): found while the copies are in flight
+  for (int k = q0 + 2 * lane; k < q1; k += 64) cp_async16(spack + k, gpack + k);  // this warp's lists (2 entries / copy)
+  // list bounds of this warp's nodes; isolated nodes keep their mass (belief_module.py:93-97)
   unsigned iso[(BEL_JMAX + 31) / 32];
 #pragma unroll
   for (int r = 0; r < (BEL_JMAX + 31) / 32; ++r) {
     const int j = j0 + r * 32 + lane;
-    iso[r] = __ballot_sync(FULL, j < j1 && __ldg(rp + j) == __ldg(rp + j + 1));
+    int qa = 0, qb = 1;
+    if (j < j1) {
+      qa = __ldg(gptr + j);
+      qb = __ldg(gptr + j + 1);
+      sptr[j + 1] = qb;
+    }
+    iso[r] = __ballot_sync(FULL, qa == qb);
   }
   cp_async_wait_all();
   named_barrier(1, BEL_WARPS * 32);
-  float sum = 0.0f, a = 0.0f;
+  float sum = 0.0f;
   const unsigned char* tin_lane = reinterpret_cast<const unsigned char*>(tin + lane);
-  unsigned char* tout_lane = reinterpret_cast<unsigned char*>(tout + lane);
+  float* tout_row = tout + j0 * BSTRIDE + lane;
+  const int4* pp = reinterpret_cast<const int4*>(spack + q0);
+  int qa = q0;
 #pragma unroll 1
-  for (int k = k0; k < k1; k += 4) {  // 4 entries per trip: all shared-memory loads first, then the dependent FMA chain
-    int4 c[4];
-    float v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = spack[min(k + i, k1 - 1)];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float*>(tin_lane + c[i].x);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (k + i < k1) {  // warp-uniform
-        a = fmaf(v[i], __int_as_float(c[i].y), a);
-        if (c[i].z >= 0) {  // last entry of its row; warp-uniform
-          *reinterpret_cast<float*>(tout_lane + c[i].z) = a;
-          sum += a;
-          a = 0.0f;
-        }
-      }
+  for (int j = j0; j < j1; ++j, tout_row += BSTRIDE) {
+    const int qb = sptr[j + 1];
+    float a = 0.0f;
+#pragma unroll 1
+    for (; qa < qb; qa += 4, pp += 2) {  // 4 neighbours per trip (lists are padded); warp-uniform
+      const int4 e0 = pp[0], e1 = pp[1];
+      const float v0 = *reinterpret_cast<const float*>(tin_lane + e0.x), v1 = *reinterpret_cast<const float*>(tin_lane + e0.z);
+      const float v2 = *reinterpret_cast<const float*>(tin_lane + e1.x), v3 = *reinterpret_cast<const float*>(tin_lane + e1.z);
+      a = fmaf(v0, __int_as_float(e0.y), a);
+      a = fmaf(v1, __int_as_float(e0.w), a);
+      a = fmaf(v2, __int_as_float(e1.y), a);
+      a = fmaf(v3, __int_as_float(e1.w), a);
     }
+    *tout_row = a;
+    sum += a;
   }
 #pragma unroll
   for (int r = 0; r < (BEL_JMAX + 31) / 32; ++r) {
@@ -1011,11 +1073,12 @@ struct SyEnv {
   void* d_cnt = nullptr;
   void* d_inv_deg = nullptr;
   void* d_pack = nullptr;
+  void* d_pack_ptr = nullptr;
   void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
   void* d_exp = nullptr;
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
-  int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0;
+  int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
   int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, wr_nf_fast = 0;
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
@@ -1023,7 +1086,7 @@ struct SyEnv {
 namespace {
 
 void free_graph_tables(SyEnv* e) {
-  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack}) {
+  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack, &e->d_pack_ptr}) {
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
   }
@@ -1068,6 +1131,7 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.bel_off_out = env->bel_off_out;
   p.bel_off_part = env->bel_off_part;
   p.bel_off_pack = env->bel_off_pack;
+  p.bel_off_ptr = env->bel_off_ptr;
   p.wr_off = env->wr_off;
   p.wr_off_csr = env->wr_off_csr;
   p.wr_img_stride = env->wr_img_stride;
@@ -1165,8 +1229,9 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   // validate + narrow on the host (setup path)
   std::vector<uint16_t> col16((size_t)G * nnz_stride, 0);
   std::vector<uint8_t> w8((size_t)G * nnz_stride, 0);
-  const int pack_stride = nnz_stride;
-  std::vector<int4> pack((size_t)G * pack_stride, make_int4(0, 0, -1, 0));
+  const int pack_stride = ((nnz_stride + 3 * N + 3) & ~3) + 4;  // every list padded to a multiple of 4 entries
+  std::vector<int2> pack((size_t)G * pack_stride, make_int2(0, 0));
+  std::vector<int32_t> pack_ptr((size_t)G * (N + 1), 0);
   int wcap = 1;
   for (int g = 0; g < G; ++g) {
     const int32_t* rp = row_ptr + (size_t)g * (N + 1);
@@ -1174,6 +1239,7 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
     for (int u = 0; u < N; ++u) {
       if (rp[u + 1] < rp[u] || rp[u + 1] > nnz_stride) return fail(SY_ERR_INVALID_ARGUMENT, "graph %d: bad row_ptr at node %d", g, u);
       if (rp[u + 1] - rp[u] > 255) return fail(SY_ERR_INVALID_ARGUMENT, "graph %d: node %d has more than 255 neighbours", g, u);
+      pack_ptr[(size_t)g * (N + 1) + u + 1] = pack_ptr[(size_t)g * (N + 1) + u] + ((rp[u + 1] - rp[u] + 3) & ~3);
       for (int k = rp[u]; k < rp[u + 1]; ++k) {
         const int v = col[(size_t)g * nnz_stride + k], wt = w[(size_t)g * nnz_stride + k];
         if (v < 0 || v >= N || v == u) return fail(SY_ERR_INVALID_ARGUMENT, "graph %d: bad neighbour %d of node %d", g, v, u);
@@ -1184,8 +1250,7 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
         const float inv_deg_v = 1.0f / (float)(rp[v + 1] - rp[v]);  // v has at least the edge back to u
         int bits;
         std::memcpy(&bits, &inv_deg_v, sizeof(bits));
-        pack[(size_t)g * pack_stride + k] = make_int4(v * BSTRIDE * (int)sizeof(float), bits,
-                                                       k == rp[u + 1] - 1 ? u * BSTRIDE * (int)sizeof(float) : -1, 0);
+        pack[(size_t)g * pack_stride + pack_ptr[(size_t)g * (N + 1) + u] + (k - rp[u])] = make_int2(v * BSTRIDE * (int)sizeof(float), bits);
         if (wt > wcap) wcap = wt;
       }
     }
@@ -1203,8 +1268,10 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   CUDA_TRY(cudaMalloc(&e->d_wgt, (size_t)G * nnz_stride));
   CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1)));
   CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&e->d_pack, pack.size() * sizeof(int4)));
-  CUDA_TRY(cudaMemcpyAsync(e->d_pack, pack.data(), pack.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMalloc(&e->d_pack, pack.size() * sizeof(int2)));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pack, pack.data(), pack.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMalloc(&e->d_pack_ptr, pack_ptr.size() * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpyAsync(e->d_pack_ptr, pack_ptr.data(), pack_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_row_ptr, row_ptr, (size_t)G * (N + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_col, col16.data(), col16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_wgt, w8.data(), w8.size(), cudaMemcpyHostToDevice, s));
@@ -1232,7 +1299,8 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   e->tb.wgt = (const uint8_t*)e->d_wgt;
   e->tb.cnt = (const uint8_t*)e->d_cnt;
   e->tb.inv_deg = (const float*)e->d_inv_deg;
-  e->tb.nbr_pack = (const int4*)e->d_pack;
+  e->tb.nbr_pack = (const int2*)e->d_pack;
+  e->tb.pack_ptr = (const int32_t*)e->d_pack_ptr;
   e->tb.pack_stride = pack_stride;
   // dynamic shared memory of the observe kernel's belief warps (generic: BEL_WARPS x 2N floats; fast path: two
   // transposed tiles [N][BSTRIDE] + per-warp partial sums)
@@ -1244,12 +1312,14 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
     const size_t off_out = up16((size_t)N * BSTRIDE * sizeof(float));
     const size_t off_part = up16(2 * off_out);
     const size_t off_pack = up16(off_part + (size_t)BEL_WARPS * 32 * sizeof(float));
-    const size_t fast = off_pack + (size_t)pack_stride * sizeof(int4);
+    const size_t off_ptr = up16(off_pack + (size_t)pack_stride * sizeof(int2));
+    const size_t fast = off_ptr + (size_t)(N + 2) * sizeof(int);
     if (fast <= 110 * 1024 && N <= BEL_WARPS * BEL_JMAX) {
       e->bel_fast = 1;  // N <= ~400 (2 CTAs per SM); N <= ~250 keeps 3 CTAs per SM
       e->bel_off_out = (int)off_out;
       e->bel_off_part = (int)off_part;
       e->bel_off_pack = (int)off_pack;
+      e->bel_off_ptr = (int)off_ptr;
     }
     e->bel_smem = e->bel_fast && fast > generic ? fast : generic;
     if (e->bel_smem > 180 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes too large for the belief kernel's shared memory");
@@ -1321,13 +1391,20 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   if ((rc = check_obs(ob))) return rc;
   p.actions = reinterpret_cast<const long long*>(actions);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  const unsigned grid = (unsigned)((p.B + LOGIC_THREADS - 1) / LOGIC_THREADS);
+  const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
   cudaStream_t s = (cudaStream_t)stream;
+  const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
   if (p.dbg_skip & 32) {
-  } else if (e->cfg.reward_mode == SY_REWARD_FP64)
-    sy_logic_kernel<SY_REWARD_FP64><<<grid, LOGIC_THREADS, 0, s>>>(p);
-  else
-    sy_logic_kernel<SY_REWARD_FP32><<<grid, LOGIC_THREADS, 0, s>>>(p);
+  } else if (p.A <= 4) {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
+  } else if (p.A <= 8) {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, s>>>(p);
+  } else {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, s>>>(p);
+  }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   if (!(p.dbg_skip & 16)) sy_observe_kernel<<<(unsigned)((p.B + TILE - 1) / TILE), THREADS, e->obs_smem, s>>>(p);
