@@ -382,13 +382,11 @@ class BatchedScotlandYardEnv:
         all-reduce (NCCL over NVLink on a GPU box)."""
         if self.stats_vec is None:
             raise _cabi.SyError("collect_stats=False")
-        v = self.stats_vec
         if reduce_group is not None:
-            import torch.distributed as dist
+            from .sharding import allreduce_stats
 
-            v = v.clone()
-            dist.all_reduce(v, op=dist.ReduceOp.SUM, group=None if reduce_group is True else reduce_group)
-        h = v.cpu().tolist()
+            return allreduce_stats(self.stats_vec, None if reduce_group is True else reduce_group)
+        h = self.stats_vec.cpu().tolist()
         return {k: int(h[i]) for i, k in enumerate(_cabi.STAT_NAMES)}
 
     def reset_stats(self):

@@ -430,3 +430,76 @@ def test_step_host_equals_step(torch_cuda, tables):
         assert np.array_equal(a.belief_map.cpu().numpy(), b.belief_map.cpu().numpy())
     a.close()
     b.close()
+
+
+def test_compat_env_replays_reference_traces(torch_cuda, golden_traces, tables):
+    """The single-episode view with the reference's call shape (dicts keyed by agent name, numpy observations with
+    the reference's dtypes) replays recorded reference episodes bit for bit (yard.py:80-269,319-332)."""
+    pkg = _pkg()
+    gt = golden_traces
+    names = [str(x) for x in gt["names"]]
+    total = 0
+    for n in names[::8]:
+        t = _trace(gt, n)
+        seed, N, E, P, money = [int(x) for x in t["config"]]
+        weights = dict(zip(so.REWARD_WEIGHT_NAMES, t["weights"].tolist()))
+        g = pkg.GraphSpec(N, t["edge_links"], t["edges"])
+        env = pkg.CustomEnvironment(P, money, weights, None, 0, N, E, None, graph=g, reward_tables=tables)
+        obs, infos = env.reset(graph=g, start_positions=t["start"])
+        agents = ["MrX"] + [f"Police{i}" for i in range(P)]
+        assert list(obs) == agents and env.agents == agents and env.action_space("MrX").n == N
+        assert np.array_equal(np.stack([obs[a]["action_mask"] for a in agents]), t["obs0_mask"])
+        o = obs["Police0"]
+        assert o["adjacency_matrix"].dtype == np.float64 and o["adjacency_matrix"].shape == (N, N)
+        assert o["node_features"].dtype == np.float64 and o["node_features"].shape == (N, P + 1)
+        assert o["edge_index"].shape == (2, len(t["edges"])) and o["edge_index"].dtype == np.int32
+        assert o["agent_budget"].dtype == np.float32 and o["agent_budget"].shape == (1,)
+        assert o["action_mask"].dtype == bool and o["agent_position"] == int(t["start"][1])
+        for s, act in enumerate(t["actions"]):
+            obs, rew, term, trunc, infos = env.step({a: int(act[i]) for i, a in enumerate(agents)})
+            assert [env.MrX_pos[0]] + env.police_positions == t["pos"][s].tolist(), (n, s)
+            assert env.agents_money == t["money"][s].tolist(), (n, s)
+            assert np.asarray([rew[a] for a in agents]).tobytes() == t["reward"][s].tobytes(), (n, s)
+            assert all(term[a] == bool(t["terminated"][s]) and trunc[a] == bool(t["truncated"][s]) for a in agents)
+            assert {None: 0, "MrX": 1, "Police": 2}[env.current_winner] == int(t["winner"][s])
+            want_mask = np.unpackbits(t["masks"][s], axis=-1)[..., :N].astype(bool)
+            assert np.array_equal(np.stack([obs[a]["action_mask"] for a in agents]), want_mask), (n, s)
+            for i in range(P + 1):
+                assert env.get_possible_moves(i).tolist() == np.nonzero(want_mask[i])[0].tolist()
+            total += 1
+        assert env.agents == [] or not (t["terminated"][-1] or t["truncated"][-1])
+        env.close()
+    assert total > 60
+
+
+def test_torchrl_adapter_on_device(torch_cuda, tables):
+    """The torchrl EnvBase adapter over a real device env (stand-in base classes; torchrl is not installed):
+    zero-copy keys, `_reset` masks, per-agent action entries."""
+    torch = torch_cuda
+    import fake_torchrl
+    from student_mechanism_design_b200 import torchrl_env
+
+    pkg = _pkg()
+    c = dict(N=20, E=34, P=2, money=8, G=2, B=40, kw=dict(belief=True, reveal_interval=2), mode="fp64")
+    env, ob = _make_pair(pkg, c, tables, auto_reset=False)
+    tenv = torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict)(env)
+    td = tenv.reset()
+    assert td.get(("agents", "observation", "action_mask")).data_ptr() == env.action_mask.data_ptr()
+    assert np.array_equal(td.get(("MrX", "observation", "agent_position"))[:, 0].cpu().numpy(), ob.pos()[:, 0])
+    for s in range(15):
+        acts = ob.sample_actions(s)
+        tin = fake_torchrl.TensorDict({}, batch_size=[c["B"]])
+        for i, name in enumerate(env.possible_agents):
+            tin.set((name, "action"), torch.from_numpy(acts[:, i:i + 1]).cuda())
+        out = tenv.step(tin)
+        want = ob.step(acts)
+        assert out.get(("agents", "reward")).squeeze(-1).cpu().numpy().tobytes() == want["reward"].astype(np.float32).tobytes()
+        assert np.array_equal(out.get("terminated")[:, 0].cpu().numpy(), want["terminated"])
+        assert np.array_equal(out.get(("Police1", "observation", "action_mask"))[:, 0].cpu().numpy(), ob.masks()[:, 2])
+    done = np.asarray(ob.done)
+    if done.any():
+        m = torch.from_numpy(done).cuda().reshape(-1, 1)
+        td = tenv.reset(fake_torchrl.TensorDict({"_reset": m}, batch_size=[c["B"]]))
+        assert not env.done[torch.from_numpy(done).cuda()].any()
+        assert bool((env.timestep[torch.from_numpy(done).cuda()] == 0).all())
+    env.close()
