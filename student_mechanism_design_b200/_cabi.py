@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsy_env.so")
+# SY_LIB_PATH: profiling experiments only (kernel variants built side by side); the product loads the in-tree library
+LIB_PATH = os.environ.get("SY_LIB_PATH") or os.path.join(_HERE, "libsy_env.so")
 
 SY_ABI_VERSION = 1
 SY_NUM_REWARD_WEIGHTS = 11

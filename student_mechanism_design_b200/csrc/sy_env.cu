@@ -59,9 +59,15 @@ constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = 
 constexpr int BEL_WARPS = 8;   // observe kernel: warps 0..7 propagate the belief ...
 constexpr int WR_WARPS = 8;    // ... warps 8..15 stream the dense observations
 constexpr int THREADS = (BEL_WARPS + WR_WARPS) * 32;
-constexpr int EXP_SMEM = 128;  // logic kernel: exp(-d) entries staged in shared memory
-constexpr int COV_SMEM = 256;  // logic kernel: coverage entries staged in shared memory
-constexpr int LOGIC_THREADS = 128;  // logic kernel: 4 warps per 32-env tile; reset kernel: 4 warps x 32 envs
+constexpr int EXP_SMEM = 96;   // logic kernel: exp(-d) entries staged in shared memory (larger d: global table)
+constexpr int COV_SMEM = 64;   // logic kernel: coverage entries staged in shared memory
+constexpr int HS = 18;         // row stride (halfwords) of the u16 smem rows: 9 words, conflict-free for lane = env
+typedef unsigned short u16;
+#ifndef SY_LOGIC_WARPS
+#define SY_LOGIC_WARPS 4
+#endif
+constexpr int LOGIC_WARPS = SY_LOGIC_WARPS;  // logic kernel: warps per 32-env tile; reset kernel: warps x 32 envs
+constexpr int LOGIC_THREADS = LOGIC_WARPS * 32;
 constexpr int AS = SY_MAX_AGENTS + 1;  // odd smem row stride -> conflict-free lane = env access
 constexpr unsigned FULL = 0xffffffffu;
 enum { DIST_INF = 0xFFFF };
@@ -130,21 +136,22 @@ __device__ __forceinline__ unsigned word_of(const uint4& r, int i) {
 }
 
 // A distinct uniform nodes (distribution of np.random.choice(N, A, replace=False), yard.py:112-116)
-__device__ void philox_start_positions(const Params& p, unsigned env, unsigned episode, int* out, int* chosen /*A ints of scratch*/) {
+template <typename T>
+__device__ void philox_start_positions(const Params& p, unsigned env, unsigned episode, T* out, T* chosen /*A entries of scratch*/) {
   uint4 r = make_uint4(0, 0, 0, 0);
   const uint2 key = make_uint2(p.seed_lo, p.seed_hi);
   for (int a = 0; a < p.A; ++a) {
     if ((a & 3) == 0) r = philox4x32(make_uint4(env, episode, RNG_RESET_POS, (unsigned)(a >> 2)), key);
     int x = (int)__umulhi(word_of(r, a & 3), (unsigned)(p.N - a));
     for (int i = 0; i < a; ++i)
-      if (x >= chosen[i]) ++x;
+      if (x >= (int)chosen[i]) ++x;
     int j = a;
-    while (j > 0 && chosen[j - 1] > x) {
+    while (j > 0 && (int)chosen[j - 1] > x) {
       chosen[j] = chosen[j - 1];
       --j;
     }
-    chosen[j] = x;
-    out[a] = x;
+    chosen[j] = (T)x;
+    out[a] = (T)x;
   }
 }
 
@@ -207,42 +214,61 @@ struct WarpTile {
   int money[32 * AS];
 };
 
-// the order-dependent move rule (yard.py:155-243) and the ending (reward_calculator.py:63-79).  An agent's own node
-// does not change before its own move, so all A edge-weight lookups are issued up front (one round trip).
-template <int MAXA>
-__device__ __forceinline__ int move_phase(const Params& p, int* pos, int* money, const int* act, int g, int t, int& spent) {
+// the order-dependent move rule (yard.py:155-243) and the ending (reward_calculator.py:63-79).  The env's agents are
+// pulled into registers (loops fully unrolled over MAXA with predicates, so indexing is static and the rule runs on
+// register compares instead of a chain of dependent shared-memory loads); an agent's own node does not change before
+// its own move, so all A edge-weight lookups are issued up front (one round trip).
+template <int MAXA, typename PosT>
+__device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money, const int* act, int g, int t, int& spent) {
   const Tables& tb = p.tb;
   const int N = p.N, P = p.P;
-  int wpre[MAXA];
+  int rp[MAXA], rm[MAXA], ra[MAXA], wpre[MAXA];
 #pragma unroll
-  for (int i = 0; i < MAXA; ++i) wpre[i] = (i <= P && act[i] >= 0) ? edge_weight(tb, N, g, pos[i], act[i]) : 0;
+  for (int i = 0; i < MAXA; ++i) {
+    const bool valid = i <= P;
+    rp[i] = valid ? (int)pos[i] : -2 - i;  // unused slots: distinct negative values that never match a node
+    rm[i] = valid ? money[i] : 0;
+    ra[i] = valid ? act[i] : -1;
+  }
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) wpre[i] = (i <= P && ra[i] >= 0) ? edge_weight(tb, N, g, rp[i], ra[i]) : 0;
   {  // MrX: legal target or stay; may not step onto a police node (yard.py:161-188)
-    const int a0 = act[0], u = pos[0];
-    int tgt = u;
-    if (a0 >= 0 && wpre[0] > 0 && wpre[0] + p.toll <= money[0]) tgt = a0;
+    int tgt = rp[0];
+    if (ra[0] >= 0 && wpre[0] > 0 && wpre[0] + p.toll <= rm[0]) tgt = ra[0];
     bool occupied = false;
-    for (int i = 1; i <= P; ++i) occupied |= (pos[i] == tgt);
-    if (!occupied) pos[0] = tgt;
+#pragma unroll
+    for (int i = 1; i < MAXA; ++i) occupied |= (rp[i] == tgt);
+    if (!occupied) rp[0] = tgt;
   }
   bool no_money = true;
 #pragma unroll
   for (int i = 1; i < MAXA; ++i) {  // police in order; later police see earlier moves (yard.py:192-243)
-    if (i > P) break;
-    const int ai = act[i], m = money[i], u = pos[i];
-    if (ai == -1 || m == 0) continue;  // None / DEFAULT_ACTION / broke: skipped (yard.py:210-215)
-    no_money = false;
-    if (ai < 0 || ai == u) continue;
-    const int w = wpre[i];
-    if (w == 0 || w + p.toll > m) continue;  // not a possible move -> stay
-    bool occupied = false;
-    for (int j = 1; j <= P; ++j) occupied |= (pos[j] == ai);
-    if (occupied) continue;  // may step onto MrX (capture) but not onto police (yard.py:231)
-    pos[i] = ai;
-    money[i] = m - (w + p.toll);
-    spent += w + p.toll;
+    if (i <= P) {
+      const int ai = ra[i], m = rm[i], w = wpre[i];
+      const bool skipped = (ai == -1 || m == 0);  // None / DEFAULT_ACTION / broke: skipped (yard.py:210-215)
+      no_money &= skipped;
+      // a possible move: adjacent and affordable; otherwise the police stays (yard.py:223-229)
+      const bool can = !skipped && ai >= 0 && ai != rp[i] && w != 0 && w + p.toll <= m;
+      bool occupied = false;  // may step onto MrX (capture) but not onto police (yard.py:231)
+#pragma unroll
+      for (int j = 1; j < MAXA; ++j) occupied |= (rp[j] == ai);
+      if (can && !occupied) {
+        rp[i] = ai;
+        rm[i] = m - (w + p.toll);
+        spent += w + p.toll;
+      }
+    }
   }
   bool capture = false;
-  for (int i = 1; i <= P; ++i) capture |= (pos[i] == pos[0]);
+#pragma unroll
+  for (int i = 1; i < MAXA; ++i) capture |= (rp[i] == rp[0]);
+#pragma unroll
+  for (int i = 0; i < MAXA; ++i) {
+    if (i <= P) {
+      pos[i] = (PosT)rp[i];
+      money[i] = rm[i];
+    }
+  }
   // reward_calculator.py:63-79; `timestep` is the pre-increment value (yard.py:345,355)
   return capture ? ST_CAPTURE : (t > p.max_t ? ST_TIMEOUT : (no_money ? ST_NO_MONEY : ST_RUNNING));
 }
@@ -255,22 +281,22 @@ __device__ __forceinline__ double exp_neg_s(const Tables& tb, const RewardTables
   return d < EXP_SMEM ? rt.exp_neg[d] : exp_neg(tb, d);
 }
 
-// reward of agent a (reward_calculator.py:26-92 endings, :94-266 shaped), float64 value (fp32 mode: the float, widened).
-// All distance lookups of the agent are issued before any is used (memory-level parallelism; the loops are fully
-// unrolled over SY_MAX_AGENTS with a break so that the values stay in registers).
+// what an agent's reward needs from the graph tables
+template <int MAXA>
+struct RewardInputs {
+  int dj[MAXA];  // d(u, pos[j]), j = 0 is MrX
+  int mob;       // len(possible moves) with the budget the reference uses (see the quirk in the kernel)
+};
+
+// reward of agent a (reward_calculator.py:26-92 endings, :94-266 shaped), float64 value (fp32 mode: the float, widened)
 template <int MODE, int MAXA>
-__device__ __forceinline__ double agent_reward(const Params& p, const RewardTables& rt, const int* pos, const int* money, int g,
-                                               int t, int status, int a, int visits_here) {
+__device__ __forceinline__ double agent_reward(const Params& p, const RewardTables& rt, const RewardInputs<MAXA>& in, int t, int status,
+                                               int a, int visits_here) {
   const Tables& tb = p.tb;
-  const int N = p.N, P = p.P;
+  const int P = p.P;
   if (status == ST_CAPTURE) return (a == 0) ? -1.0 : 1.0;
   if (status != ST_RUNNING) return (a == 0) ? 1.0 : 0.0;
   const double tt = (double)t;
-  const int u = pos[a];
-  int dj[MAXA];  // d(u, pos[j]), j = 0 is MrX
-  const uint16_t* drow = tb.D + ((size_t)g * N + u) * N;
-#pragma unroll
-  for (int j = 0; j < MAXA; ++j) dj[j] = (j <= P) ? (int)__ldg(drow + pos[j]) : 0;
   if (a == 0) {
     // reward_calculator.py:126-148
     int dmin = DIST_INF;
@@ -278,17 +304,18 @@ __device__ __forceinline__ double agent_reward(const Params& p, const RewardTabl
     bool any_inf = false;
 #pragma unroll
     for (int i = 1; i < MAXA; ++i) {
-      if (i > P) break;
-      dmin = min(dmin, dj[i]);
-      any_inf |= (dj[i] == DIST_INF);
-      dsum += dj[i];
+      if (i <= P) {
+        dmin = min(dmin, in.dj[i]);
+        any_inf |= (in.dj[i] == DIST_INF);
+        dsum += in.dj[i];
+      }
     }
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double closest = (dmin == DIST_INF) ? inf : (double)dmin;
     const double avg = any_inf ? inf : __ddiv_rn((double)dsum, (double)P);  // np.mean: exact sum / P
     const double x1 = __ddiv_rn(-1.0, __dadd_rn(closest, 1.0));
     const double x2 = __ddiv_rn(-1.0, __dadd_rn(avg, 1.0));
-    const double x3 = (double)move_count(tb, N, g, u, money[0], p.toll);
+    const double x3 = (double)in.mob;
     const double x4 = __dmul_rn(0.1, tt);
     if (MODE == SY_REWARD_FP64) {
       const double t1 = __dmul_rn(p.w64[4], x1), t2 = __dmul_rn(p.w64[5], x2), t3 = __dmul_rn(p.w64[6], x3);
@@ -303,23 +330,22 @@ __device__ __forceinline__ double agent_reward(const Params& p, const RewardTabl
   }
   // reward_calculator.py:182-227
   const int k = a - 1;
-  // QUIRK reward_calculator.py:190: the mobility term uses the budget of agent index k (not k+1)
-  const double mob = (double)move_count(tb, N, g, u, money[k], p.toll);
+  const double mob = (double)in.mob;
   const int vc = min(visits_here, tb.n_cov - 1);
   const double cov = vc < COV_SMEM ? rt.coverage[vc] : __ldg(tb.coverage + vc);
-  const double dx = exp_neg_s(tb, rt, dj[0]);
+  const double dx = exp_neg_s(tb, rt, in.dj[0]);
   double grp = 0.0, ov = 0.0, prox = 0.0;
 #pragma unroll
   for (int j = 0; j < MAXA - 1; ++j) {
-    if (j >= P) break;
-    if (j == k) continue;
-    const int d = dj[1 + j];
-    const double ex = exp_neg_s(tb, rt, d);
-    grp = __dadd_rn(grp, ex);
-    if (d <= 1)
-      ov = __dadd_rn(ov, 1.0);
-    else
-      prox = __dadd_rn(prox, ex);
+    if (j < P && j != k) {
+      const int d = in.dj[1 + j];
+      const double ex = exp_neg_s(tb, rt, d);
+      grp = __dadd_rn(grp, ex);
+      if (d <= 1)
+        ov = __dadd_rn(ov, 1.0);
+      else
+        prox = __dadd_rn(prox, ex);
+    }
   }
   const double x4 = __dmul_rn(0.05, tt);
   if (MODE == SY_REWARD_FP64) {
@@ -375,24 +401,51 @@ __device__ __forceinline__ void store_state(const Params& p, const WarpTile& wt,
 // auto-reset) while warps 1..3 write the results; loads that do not depend on each other are issued together.
 // MAXA (4 / 8 / 16 >= A) bounds the fully unrolled per-agent loops so that their values stay in registers.
 // ---------------------------------------------------------------------------------------------
+#ifdef SY_PHASE_CLOCKS
+__device__ unsigned long long g_phase_clk[8];
+#define PHASE_MARK(k) do { if (tid == 0) { const long long _c = clock64(); atomicAdd(&g_phase_clk[k], (unsigned long long)(_c - _t0)); _t0 = _c; } } while (0)
+#else
+#define PHASE_MARK(k) do { } while (0)
+#endif
+
+constexpr int CNT_SMEM = 5120;  // bytes of the move-count table staged in shared memory (N * (wcap + 1) <= this)
+template <int MAXA>
 struct LogicSmem {
-  WarpTile wt;
+  static constexpr int DS = MAXA * MAXA + 2;  // row stride (halfwords) of the pair-distance matrices: odd word count
+  static constexpr int NPAIR = MAXA * (MAXA - 1) / 2;
+  u16 pos[32 * HS];        // agents' nodes (post-move after P1, next-episode nodes after a same-step auto-reset)
+  u16 scratch[32 * HS];    // Philox scratch
+  u16 reset_pos[32 * HS];  // start nodes of the next episode, drawn speculatively
+  u16 vis[32 * HS];        // visit counter at every police's node (before this step's increment)
+  u16 dmat[32 * DS];       // all-pairs distances between the env's agents
+  u16 pair_ij[NPAIR];      // pair index -> (i << 8) | j, i < j
+  int act[32 * AS];        // normalised actions
+  int money[32 * AS];
   RewardTables rt;
-  int scratch[32 * AS];
-  int reset_pos[32 * AS];  // start nodes of the next episode, drawn speculatively
+  uint8_t cnt[CNT_SMEM];   // move-count table of the tile's graph (when it fits and the tile sits on one graph)
   int reset_gid[32];
   int t[32], gid[32], episode[32], frozen[32], status[32];
   int t_new[32], done[32], bel[32], revealed[32], clear[32];
+  int cnt_staged;
 };
 
+#ifndef SY_LOGIC_MIN_CTAS
+#define SY_LOGIC_MIN_CTAS (LOGIC_WARPS == 2 ? 14 : 9)
+#endif
+#ifndef SY_VISIT_PREFETCH
+#define SY_VISIT_PREFETCH 1
+#endif
 template <int MODE, int MAXA>
-__global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p) {
-  __shared__ LogicSmem sm;
-  WarpTile& wt = sm.wt;
+__global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_kernel(const Params p) {
+  __shared__ LogicSmem<MAXA> sm;
+  constexpr int DS = LogicSmem<MAXA>::DS;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b0 = blockIdx.x * 32;
   const int nEnv = min(32, p.B - b0);
   const int N = p.N, A = p.A, P = p.P;
+#ifdef SY_PHASE_CLOCKS
+  long long _t0 = clock64();
+#endif
 
   // ---- P0: stage the tile (coalesced) and the head of the two float64 tables
   for (int i = tid; i < EXP_SMEM; i += LOGIC_THREADS) sm.rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
@@ -401,9 +454,10 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
     const int e = i / A, a = i - e * A;
     const size_t o = (size_t)b0 * A + i;
     const long long a64 = p.actions[o];
-    wt.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
-    wt.pos[e * AS + a] = p.st.pos[o];
-    wt.money[e * AS + a] = p.st.money[o];
+    const int ps = p.st.pos[o];
+    sm.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
+    sm.pos[e * HS + a] = (u16)ps;
+    sm.money[e * AS + a] = p.st.money[o];
   }
   if (tid < 32) {
     const bool live = tid < nEnv;
@@ -414,17 +468,39 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
     sm.frozen[tid] = live ? (int)p.st.done[b] : 1;
     sm.status[tid] = ST_RUNNING;
   }
+  for (int q = tid; q < A * (A - 1) / 2; q += LOGIC_THREADS) {  // pair index -> (i, j), i < j
+    int i = 0, rem = q;
+    while (rem >= A - 1 - i) {
+      rem -= A - 1 - i;
+      ++i;
+    }
+    sm.pair_ij[q] = (u16)((i << 8) | (i + 1 + rem));
+  }
+  {  // move-count table of the tile's graph (1 KB at c3): staged when every env of the tile sits on that graph
+    const int g_first = p.st.graph_id[b0];
+    const int gl = (lane < nEnv) ? p.st.graph_id[b0 + lane] : g_first;
+    const int bytes = N * (p.tb.wcap + 1);
+    const bool ok = bytes <= CNT_SMEM && __all_sync(FULL, gl == g_first);
+    if (tid == 0) sm.cnt_staged = ok;
+    if (ok)
+      for (int i = tid; i < bytes; i += LOGIC_THREADS) sm.cnt[i] = __ldg(p.tb.cnt + (size_t)g_first * bytes + i);
+  }
   __syncthreads();
+  PHASE_MARK(0);
   const bool live = lane < nEnv;
   const int b = b0 + lane;
   const int t = sm.t[lane], g = sm.gid[lane], frozen = sm.frozen[lane];
   const bool active = live && !frozen;
-  int* pos = wt.pos + lane * AS;
-  int* money = wt.money + lane * AS;
-  int* act = wt.act + lane * AS;
+  u16* pos = sm.pos + lane * HS;
+  int* money = sm.money + lane * AS;
+  const int* act = sm.act + lane * AS;
 
-  // ---- P1: moves + ending, warp 0  ||  warp 1: the start nodes (and graph) a same-step auto-reset WOULD draw --
-  // Philox(seed; env, episode + 1) does not depend on the outcome, so it is computed off the critical path
+  // ---- P1, four warps in parallel:
+  //   warp 0    the order-dependent moves + ending
+  //   warp 1    the start nodes (and graph) a same-step auto-reset WOULD draw: Philox(seed; env, episode + 1) does not
+  //             depend on the outcome, so it is computed off the critical path
+  //   warps 2,3 visit counters at both nodes each police can end on (its node or its action target): the HBM
+  //             round trip of the read-modify-write overlaps the moves
   int spent = 0;
   if (warp == 0) {
     if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent);
@@ -432,45 +508,102 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
     const unsigned ep = (unsigned)(sm.episode[lane] + 1);
     sm.reset_gid[lane] = p.resample_graph ? philox_graph_choice(p, env_id, ep) : g;
-    philox_start_positions(p, env_id, ep, sm.reset_pos + lane * AS, sm.scratch + lane * AS);
+    philox_start_positions(p, env_id, ep, sm.reset_pos + lane * HS, sm.scratch + lane * HS);
   }
   __syncthreads();
+  PHASE_MARK(1);
 
-  // ---- P2: visit counts (yard.py:244-245) and rewards, warp = agent; reward bits go to the (now dead) action slots
+  // ---- P2a: every table lookup of the rewards, once: the A(A-1)/2 distinct distances between the env's agents (the
+  // reference asks Pathfinder for each of them 2-4 times, reward_calculator.py:126-227) and the visit counters at the
+  // police nodes, spread over the warps and all issued before any is consumed.  Divergent 2-byte gathers are the
+  // scarce resource of this kernel (one L1 wavefront per lane), so each is loaded exactly once.
   const int status = sm.status[lane];
+  const bool shaped = active && status == ST_RUNNING;
+  {
+    constexpr int NPQ = (LogicSmem<MAXA>::NPAIR + LOGIC_WARPS - 1) / LOGIC_WARPS;
+    constexpr int NVQ = (MAXA + LOGIC_WARPS - 1) / LOGIC_WARPS;
+    const int npairs = A * (A - 1) / 2;
+    const uint16_t* Dg = p.tb.D + (size_t)g * N * N;
+    const uint16_t* vrow = p.st.visits + (size_t)b * N;
+    int dq[NPQ], vq[NVQ];
+#pragma unroll
+    for (int k = 0; k < NPQ; ++k) {
+      const int q = warp + k * LOGIC_WARPS;
+      dq[k] = 0;
+      if (shaped && q < npairs) {
+        const int ij = sm.pair_ij[q];
+        dq[k] = __ldg(Dg + (size_t)pos[ij >> 8] * N + pos[ij & 0xff]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NVQ; ++k) {
+      const int i = 1 + warp + k * LOGIC_WARPS;
+      vq[k] = (active && i <= P) ? (int)vrow[pos[i]] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < NPQ; ++k) {
+      const int q = warp + k * LOGIC_WARPS;
+      if (shaped && q < npairs) {
+        const int ij = sm.pair_ij[q], i = ij >> 8, j = ij & 0xff;
+        sm.dmat[lane * DS + i * MAXA + j] = (u16)dq[k];
+        sm.dmat[lane * DS + j * MAXA + i] = (u16)dq[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NVQ; ++k) {
+      const int i = 1 + warp + k * LOGIC_WARPS;
+      if (active && i <= P) sm.vis[lane * HS + i] = (u16)vq[k];
+    }
+  }
+  if (warp == 0) PHASE_MARK(1);
+  __syncthreads();
+  PHASE_MARK(2);
+
+  // ---- P2b: visit counts (yard.py:244-245) and rewards, warp = agent (agents warp, warp + LOGIC_WARPS, ...)
   if (live) {
 #pragma unroll 1
-    for (int a = warp; a < A; a += LOGIC_THREADS / 32) {
+    for (int a = warp; a < A; a += LOGIC_WARPS) {
       double r64 = 0.0;
       if (active) {
         int visits_here = 0;
+        const int u = pos[a];
         if (a > 0) {  // police never share a node (yard.py:231): the P counters of an env are distinct addresses
-          uint16_t* vp = p.st.visits + (size_t)b * N + pos[a];
-          visits_here = (int)(*vp) + 1;
-          *vp = (uint16_t)min(visits_here, 0xFFFF);
+          visits_here = (int)sm.vis[lane * HS + a] + 1;
+          p.st.visits[(size_t)b * N + u] = (uint16_t)min(visits_here, 0xFFFF);
         }
-        r64 = agent_reward<MODE, MAXA>(p, sm.rt, pos, money, g, t, status, a, visits_here);
+        RewardInputs<MAXA> in;
+        in.mob = 0;
+        if (status == ST_RUNNING) {
+#pragma unroll
+          for (int j = 0; j < MAXA; ++j) in.dj[j] = (j <= P && j != a) ? (int)sm.dmat[lane * DS + a * MAXA + j] : 0;
+          // QUIRK reward_calculator.py:190: the police mobility term uses the budget of agent index a-1 (not a)
+          const int mny = money[a == 0 ? 0 : a - 1];
+          const int c = min(mny - p.toll, p.tb.wcap);
+          if (c > 0) in.mob = sm.cnt_staged ? (int)sm.cnt[u * (p.tb.wcap + 1) + c] : move_count(p.tb, N, g, u, mny, p.toll);
+        }
+        r64 = agent_reward<MODE, MAXA>(p, sm.rt, in, t, status, a, visits_here);
       }
-      act[a] = __float_as_int((float)r64);
+      p.out.reward[(size_t)b * A + a] = (float)r64;
       if (p.out.reward64) p.out.reward64[(size_t)b * A + a] = r64;
     }
   }
+  if (warp == 0) PHASE_MARK(3);
   __syncthreads();
+  PHASE_MARK(4);
 
-  // ---- P3: warps 1..3 write the results (coalesced)  ||  warp 0 computes the next-step state
+  // ---- P3: warps 1..3 write the flags (coalesced)  ||  warp 0 computes the next-step state
   if (warp > 0) {
     for (int i = tid - 32; i < nEnv * A; i += LOGIC_THREADS - 32) {
-      const int e = i / A, a = i - e * A;
+      const int e = i / A;
       const size_t o = (size_t)b0 * A + i;
       const int st = sm.status[e];
       const bool term = (st == ST_CAPTURE) || (st == ST_NO_MONEY), trunc = (st == ST_TIMEOUT);
-      p.out.reward[o] = __int_as_float(wt.act[e * AS + a]);
       p.out.terminated[o] = term;
       p.out.truncated[o] = trunc;
       p.out.done[o] = term || trunc || sm.frozen[e];
     }
   } else {
-    // timestep, reveal schedule, same-step auto-reset (Philox), statistics
+    // timestep, reveal schedule, same-step auto-reset, statistics
     int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
     int t_new = t, done = frozen, bel = BEL_KEEP, revealed = -1, episode = sm.episode[lane], gnew = g;
     bool clear_visits = false;
@@ -491,10 +624,10 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
             episode += 1;
             gnew = sm.reset_gid[lane];
             money[0] = p.mrx_money;
-            pos[0] = sm.reset_pos[lane * AS];
+            pos[0] = sm.reset_pos[lane * HS];
             for (int i = 1; i <= P; ++i) {
               money[i] = p.agent_money;
-              pos[i] = sm.reset_pos[lane * AS + i];
+              pos[i] = sm.reset_pos[lane * HS + i];
             }
             t_new = 0;
             clear_visits = true;
@@ -509,7 +642,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
       // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
       const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
       if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
-      revealed = (p.reveal <= 0 || rev) ? pos[0] : -1;
+      revealed = (p.reveal <= 0 || rev) ? (int)pos[0] : -1;
     }
     sm.t_new[lane] = t_new;
     sm.gid[lane] = gnew;
@@ -543,15 +676,17 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
         if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
       }
     }
+    PHASE_MARK(5);
   }
   __syncthreads();
+  PHASE_MARK(6);
 
   // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85)
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = i / A, a = i - e * A;
     const size_t o = (size_t)b0 * A + i;
-    const int m = wt.money[e * AS + a];
-    p.st.pos[o] = wt.pos[e * AS + a];
+    const int m = sm.money[e * AS + a];
+    p.st.pos[o] = (int)sm.pos[e * HS + a];
     p.st.money[o] = m;
     p.ob.agent_budget[o] = (float)m;  // yard.py:329-331
   }
@@ -568,9 +703,10 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_logic_kernel(const Params p)
   for (int n = 0; clr; ++n) {
     const int e = __ffs(clr) - 1;
     clr &= clr - 1;
-    if ((n & (LOGIC_THREADS / 32 - 1)) == warp)
+    if (n % LOGIC_WARPS == warp)
       warp_zero_bytes(reinterpret_cast<uint8_t*>(p.st.visits + (size_t)(b0 + e) * N), N * (int)sizeof(uint16_t), lane);
   }
+  PHASE_MARK(7);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1153,6 +1289,17 @@ int check_obs(const SyObs* ob) {
 
 extern "C" {
 
+#ifdef SY_PHASE_CLOCKS
+int sy_debug_phase_clocks(unsigned long long* out8, int reset) {  // profiling builds only, not declared in sy_env.h
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_phase_clk, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 int sy_abi_version(void) { return SY_ABI_VERSION; }
 const char* sy_last_error(void) { return g_err.c_str(); }
 int64_t sy_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -1165,7 +1312,7 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
   if (c->num_police < 1 || c->num_police + 1 > SY_MAX_AGENTS)
     return fail(SY_ERR_INVALID_ARGUMENT, "num_police must be in [1, %d]", SY_MAX_AGENTS - 1);
   if (c->num_nodes < c->num_police + 1 || c->num_nodes > 65534)
-    return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes must be in [num_police + 1, 65534]");
+    return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes must be in [num_police + 1, 65534]");  // nodes are staged as u16
   if (c->agent_money < 0 || c->mrx_money < 0 || c->toll < 0 || c->reveal_interval < 0 || c->max_timestep < 0)
     return fail(SY_ERR_INVALID_ARGUMENT, "negative money / toll / reveal_interval / max_timestep");
   if (c->reward_mode != SY_REWARD_FP64 && c->reward_mode != SY_REWARD_FP32)
@@ -1391,9 +1538,11 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   if ((rc = check_obs(ob))) return rc;
   p.actions = reinterpret_cast<const long long*>(actions);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
-  const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
   cudaStream_t s = (cudaStream_t)stream;
   const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
+  const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
+  // (measured: issuing the step in chunks on two streams, or a persistent observe grid, does not overlap the two
+  //  kernels on this part -- the block scheduler drains the older grid first -- so the step is two plain launches)
   if (p.dbg_skip & 32) {
   } else if (p.A <= 4) {
     if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
@@ -1407,7 +1556,7 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  if (!(p.dbg_skip & 16)) sy_observe_kernel<<<(unsigned)((p.B + TILE - 1) / TILE), THREADS, e->obs_smem, s>>>(p);
+  if (!(p.dbg_skip & 16)) sy_observe_kernel<<<grid, THREADS, e->obs_smem, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
