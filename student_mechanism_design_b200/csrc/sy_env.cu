@@ -918,41 +918,53 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   }
 }
 
-// generic belief path: one warp per env, lane = node; any N, any mix of graphs.  sb: 2N floats of this warp.
+// generic belief path: one warp per env, lane = node; any N, any mix of graphs.  sb: N floats of this warp.
+// The env's row is copied to shared memory (LDGSTS), every lane then gathers its nodes' padded neighbour lists
+// {node, 1/deg} straight from the (L1-resident) pool tables.  The normaliser is the sum of the INPUT row: the
+// propagation conserves mass exactly (sum_j sum_{i in nbr(j)} b_i/deg_i = sum_i b_i on an undirected graph, isolated
+// nodes keep theirs), so it equals the reference's sum of the output up to fp32 rounding and needs no second buffer.
 __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane) {
   const int N = p.N;
   const Tables& tb = p.tb;
   float* bel = p.st.belief + (size_t)b * N;
+  const float unif = 1.0f / (float)N;
   if (op == BEL_UNIFORM) {
-    const float u = 1.0f / (float)N;
-    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = u;
+    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
   } else if (op == BEL_DELTA) {
     const int x = p.st.pos[(size_t)b * p.A];
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
   } else if (op == BEL_PROPAGATE) {
     const int g = p.st.graph_id[b];
-    const float* idg = tb.inv_deg + (size_t)g * N;
-    const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1);
-    const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
+    const int32_t* gptr = tb.pack_ptr + (size_t)g * (N + 1);
+    const int2* gpack = tb.nbr_pack + (size_t)g * tb.pack_stride;
     __syncwarp();
-    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) sb[j] = bel[j] * __ldg(idg + j);
+    for (int j = lane; j < N; j += 32) cp_async4(sb + j, bel + j);
+    cp_async_wait_all();
     __syncwarp();
-    float part = 0.0f;
-    _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
-      const int r0 = __ldg(rp + j), r1 = __ldg(rp + j + 1);
-      float acc = 0.0f;
-      _Pragma("unroll 1") for (int k = r0; k < r1; ++k) acc += sb[__ldg(cl + k)];
-      if (r1 == r0) acc = bel[j];  // isolated node keeps its mass (belief_module.py:93-97)
-      sb[N + j] = acc;
-      part += acc;
-    }
+    float tot = 0.0f;
+    for (int j = lane; j < N; j += 32) tot += sb[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-    if (part == 0.0f) {  // belief_module.py:36-37
-      const float u = 1.0f / (float)N;
-      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = u;
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+    if (tot == 0.0f) {  // belief_module.py:36-37
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
-      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = sb[N + j] / part;
+      const float inv = 1.0f / tot;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
+        const int qa = __ldg(gptr + j), qb = __ldg(gptr + j + 1);
+        float acc = 0.0f;
+        _Pragma("unroll 1") for (int q = qa; q < qb; q += 4) {  // lists are padded to multiples of 4 with {0, 0.0f}
+          const int4 e0 = __ldg(reinterpret_cast<const int4*>(gpack + q)), e1 = __ldg(reinterpret_cast<const int4*>(gpack + q + 2));
+          // entries hold the byte offset of the neighbour's row in the fast path's transposed tile: node * BSTRIDE * 4
+          const float v0 = sb[(unsigned)e0.x / (BSTRIDE * 4u)], v1 = sb[(unsigned)e0.z / (BSTRIDE * 4u)];
+          const float v2 = sb[(unsigned)e1.x / (BSTRIDE * 4u)], v3 = sb[(unsigned)e1.z / (BSTRIDE * 4u)];
+          acc = fmaf(v0, __int_as_float(e0.y), acc);
+          acc = fmaf(v1, __int_as_float(e0.w), acc);
+          acc = fmaf(v2, __int_as_float(e1.y), acc);
+          acc = fmaf(v3, __int_as_float(e1.w), acc);
+        }
+        if (qa == qb) acc = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
+        bel[j] = acc * inv;
+      }
     }
   }
 }
@@ -971,7 +983,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   const int g0 = __shfl_sync(FULL, g, prop ? __ffs(prop) - 1 : 0);
   const bool fast = p.bel_fast && prop && __all_sync(FULL, op != BEL_PROPAGATE || g == g0);
   if (!fast) {
-    float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * 2 * N;
+    float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * N;
     for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane);
     return;
   }
@@ -1449,12 +1461,12 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   e->tb.nbr_pack = (const int2*)e->d_pack;
   e->tb.pack_ptr = (const int32_t*)e->d_pack_ptr;
   e->tb.pack_stride = pack_stride;
-  // dynamic shared memory of the observe kernel's belief warps (generic: BEL_WARPS x 2N floats; fast path: two
+  // dynamic shared memory of the observe kernel's belief warps (generic: BEL_WARPS x N floats; fast path: two
   // transposed tiles [N][BSTRIDE] + per-warp partial sums)
   e->bel_smem = 0;
   e->bel_fast = 0;
   if (e->cfg.belief) {
-    const size_t generic = (size_t)BEL_WARPS * 2 * N * sizeof(float);
+    const size_t generic = (size_t)BEL_WARPS * N * sizeof(float);
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_out = up16((size_t)N * BSTRIDE * sizeof(float));
     const size_t off_part = up16(2 * off_out);

@@ -503,3 +503,39 @@ def test_torchrl_adapter_on_device(torch_cuda, tables):
         assert not env.done[torch.from_numpy(done).cuda()].any()
         assert bool((env.timestep[torch.from_numpy(done).cuda()] == 0).all())
     env.close()
+
+
+def test_large_graph_generic_paths_vs_c_oracle(torch_cuda, tables):
+    """BASELINE config 4 shape (N=1000, 6 police): too large for the transposed-tile belief path, so the generic
+    warp-per-env belief, the staged-CSR writers and the u16 tables are exercised; checked against the C oracle."""
+    import sy_oracle_c as oc
+
+    pkg = _pkg()
+    N, E, P, B = 1000, 2000, 6, 70
+    pool = pkg.generate_graph_pool(2, N, E, seed=11)
+    kw = dict(tolls=1, belief=True, reveal_interval=5)
+    env = pkg.BatchedScotlandYardEnv(B, P, 20, graphs=pool, seed=3, auto_reset=True, keep_reward64=True,
+                                     reward_tables=tables, resample_graph=True, max_timestep=9, **kw)
+    cfg = so.OracleConfig(num_police=P, agent_money=20, toll=1, belief=True, reveal_interval=5, max_timestep=9,
+                          exp_table=tables[0], cov_table=tables[1])
+    ob = oc.CBatch(cfg, pool, B, seed=3, auto_reset=True, resample_graph=True)
+    env.reset()
+    W, D = env.graph_tables(1)
+    assert np.array_equal(D.astype(np.int32), ob._D[1]) and np.array_equal(W.astype(np.int32), ob._W[1])
+    for s in range(14):
+        acts = env.sample_actions(step_counter=s)
+        assert np.array_equal(acts.cpu().numpy(), ob.sample_actions(s)), s
+        env.step(acts)
+        want = ob.step(acts.cpu().numpy())
+        assert env.reward64.cpu().numpy().tobytes() == want["reward"].tobytes(), s
+        assert np.array_equal(env.terminated[:, 0].cpu().numpy(), want["terminated"])
+        assert np.array_equal(env.truncated[:, 0].cpu().numpy(), want["truncated"])
+        assert np.array_equal(env.pos.cpu().numpy(), ob.pos()) and np.array_equal(env.money.cpu().numpy(), ob.money())
+        assert np.array_equal(env.graph_id.cpu().numpy(), np.asarray(ob.graph_id, dtype=np.int32))
+        assert np.array_equal(env.visits.cpu().numpy(), ob.visits())
+        assert np.array_equal(env.action_mask.cpu().numpy(), ob.masks())
+        assert np.array_equal(env.node_features.cpu().numpy(), ob.node_features())
+        assert np.array_equal(env.mrx_revealed.cpu().numpy(), ob.revealed())
+        assert np.abs(env.belief_map.cpu().numpy().astype(np.float64) - ob.belief()).max() <= BELIEF_TOL
+    assert env.stats()["truncations"] > 0
+    env.close()
