@@ -94,6 +94,7 @@ struct Tables {
 
 struct Params {
   int B, N, P, A;
+  int inv_A;  // ceil(2^16 / A): (i * inv_A) >> 16 == i / A for i < 2^12
   int agent_money, mrx_money, max_t, reveal, toll, belief_on, auto_reset, resample_graph, reward_mode;
   unsigned long long env_offset;
   unsigned seed_lo, seed_hi;
@@ -370,7 +371,7 @@ __device__ __forceinline__ void store_state(const Params& p, const WarpTile& wt,
   const int A = p.A, N = p.N;
   __syncwarp();
   for (int i = lane; i < nEnv * A; i += 32) {
-    const int e = i / A, a = i - e * A;
+    const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
     const int m = wt.money[e * AS + a];
     p.st.pos[o] = wt.pos[e * AS + a];
@@ -435,12 +436,11 @@ struct LogicSmem {
 #ifndef SY_VISIT_PREFETCH
 #define SY_VISIT_PREFETCH 1
 #endif
-template <int MODE, int MAXA>
-__global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_kernel(const Params p) {
-  __shared__ LogicSmem<MAXA> sm;
+// one 32-env tile by LOGIC_THREADS threads (tid = 0 .. LOGIC_THREADS-1); BAR is the named barrier they share
+template <int MODE, int MAXA, int BAR>
+__device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm, int b0, int tid) {
   constexpr int DS = LogicSmem<MAXA>::DS;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b0 = blockIdx.x * 32;
+  const int lane = tid & 31, warp = tid >> 5;
   const int nEnv = min(32, p.B - b0);
   const int N = p.N, A = p.A, P = p.P;
 #ifdef SY_PHASE_CLOCKS
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
   for (int i = tid; i < EXP_SMEM; i += LOGIC_THREADS) sm.rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
   for (int i = tid; i < COV_SMEM; i += LOGIC_THREADS) sm.rt.coverage[i] = __ldg(p.tb.coverage + min(i, p.tb.n_cov - 1));
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
-    const int e = i / A, a = i - e * A;
+    const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
     const long long a64 = p.actions[o];
     const int ps = p.st.pos[o];
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
     if (ok)
       for (int i = tid; i < bytes; i += LOGIC_THREADS) sm.cnt[i] = __ldg(p.tb.cnt + (size_t)g_first * bytes + i);
   }
-  __syncthreads();
+  named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(0);
   const bool live = lane < nEnv;
   const int b = b0 + lane;
@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
     sm.reset_gid[lane] = p.resample_graph ? philox_graph_choice(p, env_id, ep) : g;
     philox_start_positions(p, env_id, ep, sm.reset_pos + lane * HS, sm.scratch + lane * HS);
   }
-  __syncthreads();
+  named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(1);
 
   // ---- P2a: every table lookup of the rewards, once: the A(A-1)/2 distinct distances between the env's agents (the
@@ -556,13 +556,13 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
     }
   }
   if (warp == 0) PHASE_MARK(1);
-  __syncthreads();
+  named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(2);
 
   // ---- P2b: visit counts (yard.py:244-245) and rewards, warp = agent (agents warp, warp + LOGIC_WARPS, ...)
   if (live) {
 #pragma unroll 1
-    for (int a = warp; a < A; a += LOGIC_WARPS) {
+    for (int a = (warp + LOGIC_WARPS - 1) % LOGIC_WARPS; a < A; a += LOGIC_WARPS) {  // warp 0 (moves, next state) gets the fewest
       double r64 = 0.0;
       if (active) {
         int visits_here = 0;
@@ -588,13 +588,13 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
     }
   }
   if (warp == 0) PHASE_MARK(3);
-  __syncthreads();
+  named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(4);
 
   // ---- P3: warps 1..3 write the flags (coalesced)  ||  warp 0 computes the next-step state
   if (warp > 0) {
     for (int i = tid - 32; i < nEnv * A; i += LOGIC_THREADS - 32) {
-      const int e = i / A;
+      const int e = (i * p.inv_A) >> 16;
       const size_t o = (size_t)b0 * A + i;
       const int st = sm.status[e];
       const bool term = (st == ST_CAPTURE) || (st == ST_NO_MONEY), trunc = (st == ST_TIMEOUT);
@@ -678,12 +678,12 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
     }
     PHASE_MARK(5);
   }
-  __syncthreads();
+  named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(6);
 
   // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85)
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
-    const int e = i / A, a = i - e * A;
+    const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
     const int m = sm.money[e * AS + a];
     p.st.pos[o] = (int)sm.pos[e * HS + a];
@@ -709,6 +709,12 @@ __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_ker
   PHASE_MARK(7);
 }
 
+template <int MODE, int MAXA>
+__global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_kernel(const Params p) {
+  __shared__ LogicSmem<MAXA> sm;
+  logic_tile<MODE, MAXA, 3>(p, sm, blockIdx.x * 32, threadIdx.x);
+}
+
 // ---------------------------------------------------------------------------------------------
 // reset kernel (yard.py:80-142): re-initialise the masked envs (same warp = 32 envs layout)
 // ---------------------------------------------------------------------------------------------
@@ -725,7 +731,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_reset_kernel(const Params p)
   const bool rst = live && (p.reset_mask == nullptr || p.reset_mask[b] != 0);
   const unsigned rst_mask = __ballot_sync(FULL, rst);
   for (int i = lane; i < nEnv * A; i += 32) {
-    const int e = i / A, a = i - e * A;
+    const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
     if ((rst_mask >> e) & 1u) {
       wt.money[e * AS + a] = (a == 0) ? p.mrx_money : p.agent_money;  // yard.py:117-119
@@ -1253,6 +1259,7 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.N = c.num_nodes;
   p.P = c.num_police;
   p.A = env->A;
+  p.inv_A = (65536 + env->A - 1) / env->A;
   p.agent_money = c.agent_money;
   p.mrx_money = c.mrx_money;
   p.max_t = c.max_timestep;
@@ -1553,8 +1560,10 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   cudaStream_t s = (cudaStream_t)stream;
   const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
   const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
-  // (measured: issuing the step in chunks on two streams, or a persistent observe grid, does not overlap the two
-  //  kernels on this part -- the block scheduler drains the older grid first -- so the step is two plain launches)
+  // Two plain launches.  Measured alternatives that did NOT pay on B200: issuing the step in chunks on two streams or a
+  // persistent observe grid (the block scheduler drains the older grid first: no overlap), and one persistent kernel
+  // whose logic warps run one tile ahead of the observe warps (the logic's loads and shared-memory accesses queue
+  // behind the writers' store stream in the SM's in-order LSU: the times added up, 159 vs 136 us).
   if (p.dbg_skip & 32) {
   } else if (p.A <= 4) {
     if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
