@@ -955,21 +955,52 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
       const float inv = 1.0f / tot;
-      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
-        const int qa = __ldg(gptr + j), qb = __ldg(gptr + j + 1);
-        float acc = 0.0f;
-        _Pragma("unroll 1") for (int q = qa; q < qb; q += 4) {  // lists are padded to multiples of 4 with {0, 0.0f}
-          const int4 e0 = __ldg(reinterpret_cast<const int4*>(gpack + q)), e1 = __ldg(reinterpret_cast<const int4*>(gpack + q + 2));
-          // entries hold the byte offset of the neighbour's row in the fast path's transposed tile: node * BSTRIDE * 4
-          const float v0 = sb[(unsigned)e0.x / (BSTRIDE * 4u)], v1 = sb[(unsigned)e0.z / (BSTRIDE * 4u)];
-          const float v2 = sb[(unsigned)e1.x / (BSTRIDE * 4u)], v3 = sb[(unsigned)e1.z / (BSTRIDE * 4u)];
-          acc = fmaf(v0, __int_as_float(e0.y), acc);
-          acc = fmaf(v1, __int_as_float(e0.w), acc);
-          acc = fmaf(v2, __int_as_float(e1.y), acc);
-          acc = fmaf(v3, __int_as_float(e1.w), acc);
+      constexpr int U = 4;  // nodes per lane in flight: their list bounds, then their first blocks, are loaded together
+      _Pragma("unroll 1") for (int j0 = lane; j0 < N; j0 += 32 * U) {
+        int qa[U], qb[U];
+        int4 e0[U], e1[U];
+        float acc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 32 * u;
+          qa[u] = qb[u] = 0;
+          if (j < N) {
+            qa[u] = __ldg(gptr + j);
+            qb[u] = __ldg(gptr + j + 1);
+          }
         }
-        if (qa == qb) acc = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
-        bel[j] = acc * inv;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          e0[u] = e1[u] = make_int4(0, 0, 0, 0);
+          if (qa[u] < qb[u]) {  // lists are padded to multiples of 4 with {0, 0.0f}
+            e0[u] = __ldg(reinterpret_cast<const int4*>(gpack + qa[u]));
+            e1[u] = __ldg(reinterpret_cast<const int4*>(gpack + qa[u] + 2));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          // entries hold the byte offset of the neighbour's row in the fast path's transposed tile: node * BSTRIDE * 4
+          float a = sb[(unsigned)e0[u].x / (BSTRIDE * 4u)] * __int_as_float(e0[u].y);
+          a = fmaf(sb[(unsigned)e0[u].z / (BSTRIDE * 4u)], __int_as_float(e0[u].w), a);
+          a = fmaf(sb[(unsigned)e1[u].x / (BSTRIDE * 4u)], __int_as_float(e1[u].y), a);
+          a = fmaf(sb[(unsigned)e1[u].z / (BSTRIDE * 4u)], __int_as_float(e1[u].w), a);
+          acc[u] = a;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 32 * u;
+          _Pragma("unroll 1") for (int q = qa[u] + 4; q < qb[u]; q += 4) {  // nodes with more than 4 neighbours
+            const int4 f0 = __ldg(reinterpret_cast<const int4*>(gpack + q)), f1 = __ldg(reinterpret_cast<const int4*>(gpack + q + 2));
+            acc[u] = fmaf(sb[(unsigned)f0.x / (BSTRIDE * 4u)], __int_as_float(f0.y), acc[u]);
+            acc[u] = fmaf(sb[(unsigned)f0.z / (BSTRIDE * 4u)], __int_as_float(f0.w), acc[u]);
+            acc[u] = fmaf(sb[(unsigned)f1.x / (BSTRIDE * 4u)], __int_as_float(f1.y), acc[u]);
+            acc[u] = fmaf(sb[(unsigned)f1.z / (BSTRIDE * 4u)], __int_as_float(f1.w), acc[u]);
+          }
+          if (j < N) {
+            if (qa[u] == qb[u]) acc[u] = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
+            bel[j] = acc[u] * inv;
+          }
+        }
       }
     }
   }
