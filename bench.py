@@ -243,25 +243,40 @@ def run_cuda_arm(args, wl):
         env.step(actions)
         counter += 1
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
     sampler.active = True
     launches0 = lib.sy_launch_count()
     ev0.record()
-    for k in range(K):
-        env.sample_actions(out=actions, step_counter=counter)
-        kev[k][0].record()
-        env.step(actions)
-        kev[k][1].record()
-        counter += 1
+    if args.python_loop:
+        for k in range(K):
+            env.sample_actions(out=actions, step_counter=counter)
+            env.step(actions)
+            counter += 1
+    else:  # the K steps are issued by one C-ABI call (sy_rollout_random): no Python between steps
+        env.rollout_random(K, actions=actions, step_counter=counter)
+        counter += K
     stats_total = env.stats(reduce_group=True if dist is not None else None)  # the one collective (NCCL)
     ev1.record()
     barrier()
     sampler.active = False
     launches = lib.sy_launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
     value = world * B * K / (ms_total * 1e-3)
+
+    # ---- duration of the sy_step call alone (its two kernels), CUDA events around every call, for the roofline
+    Kk = min(K, 300)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    barrier()
+    sampler.active = True
+    for k in range(Kk):
+        env.sample_actions(out=actions, step_counter=counter)
+        kev[k][0].record()
+        env.step(actions)
+        kev[k][1].record()
+        counter += 1
+    barrier()
+    sampler.active = False
+    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
 
     # ---- end to end through the host-buffer API
     Ke = max(3, min(K, args.e2e_steps))
@@ -304,7 +319,7 @@ def run_cuda_arm(args, wl):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
-                       "envs_per_gpu": B, "global_envs": world * B, "policy": "on-device Philox random valid",
+                       "envs_per_gpu": B, "global_envs": world * B, "policy": "on-device Philox random valid", "loop": "python" if args.python_loop else "sy_rollout_random (C)",
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -333,6 +348,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--python-loop", action="store_true", help="issue every step from Python instead of sy_rollout_random")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     wl = dict(WORKLOADS[args.workload], name=args.workload)

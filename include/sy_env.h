@@ -180,6 +180,13 @@ int sy_step_host(SyEnv* env, const int64_t* actions_host, int64_t* actions_dev, 
 int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, int64_t* actions,
                       sy_stream_t stream);
 
+/* `num_steps` steps of the random-valid policy rollout the reference's trainers start from (gnn_trainer.py:201-250 with
+ * RandomAgent, src/agent/random_agent.py:7): per step sy_sample_actions(step_counter0 + k) into `actions` (device,
+ * int64 [B, A]) followed by sy_step, issued back to back from C on `stream` (no host work per step beyond the launches;
+ * capturable in a CUDA graph).  Buffers hold the state / observation / result of the last step afterwards. */
+int sy_rollout_random(SyEnv* env, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* state,
+                      const SyObs* obs, const SyOut* out, sy_stream_t stream);
+
 /* replaces compute_action_mask (action_mask.py:30-83) for Q queries on dense float64 inputs
  * (device pointers): adj [N,N]; weights [N,N] or NULL (adjacency as unit costs, :99-113);
  * toll_matrix [N,N] or NULL (then toll_scalar is used everywhere, :86-96); cur [Q]; budget [Q];

@@ -1645,6 +1645,17 @@ int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_
   return SY_OK;
 }
 
+int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,
+                      const SyOut* out, sy_stream_t stream) {
+  if (!e || !actions || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions or negative num_steps");
+  for (int32_t k = 0; k < num_steps; ++k) {
+    int rc = sy_sample_actions(e, st, step_counter0 + (uint32_t)k, actions, stream);
+    if (rc) return rc;
+    if ((rc = sy_step(e, actions, st, ob, out, stream))) return rc;
+  }
+  return SY_OK;
+}
+
 int sy_action_mask_dense(int32_t Q, int32_t N, const double* adj, const double* w, const double* toll_m, double toll_s,
                          const int32_t* cur, const double* budget, uint8_t* out, sy_stream_t stream) {
   if (Q < 0 || N <= 0 || !adj || !cur || !budget || !out) return fail(SY_ERR_INVALID_ARGUMENT, "bad dense mask arguments");

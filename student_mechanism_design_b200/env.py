@@ -251,6 +251,24 @@ class BatchedScotlandYardEnv:
                                                     out.data_ptr(), self._stream()))
         return out
 
+    def rollout_random(self, num_steps: int, actions: Optional[torch.Tensor] = None,
+                       step_counter: Optional[int] = None) -> torch.Tensor:
+        """`num_steps` steps of the on-device random-valid policy (the RandomAgent baseline of the reference,
+        src/agent/random_agent.py:7), issued from C without returning to Python between steps.  Returns the
+        actions of the last step; state / observations / results describe the last step."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        if actions is None:
+            actions = torch.empty(self.num_envs, self.num_agents, dtype=torch.int64, device=self.device)
+        if step_counter is None:
+            step_counter = self._sample_counter
+            self._sample_counter += int(num_steps)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_rollout_random(self._handle, int(num_steps), int(step_counter) & 0xFFFFFFFF,
+                                                    actions.data_ptr(), C.byref(self._state), C.byref(self._obs),
+                                                    C.byref(self._out), self._stream()))
+        return actions
+
     # ------------------------------------------------------------------ host-buffer API (the reference's call shape)
     def _host_buffers(self):
         if getattr(self, "_host", None) is None:

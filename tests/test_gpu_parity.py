@@ -539,3 +539,43 @@ def test_large_graph_generic_paths_vs_c_oracle(torch_cuda, tables):
         assert np.abs(env.belief_map.cpu().numpy().astype(np.float64) - ob.belief()).max() <= BELIEF_TOL
     assert env.stats()["truncations"] > 0
     env.close()
+
+
+def test_rollout_random_and_cuda_graph_replay(torch_cuda, tables):
+    """sy_rollout_random (T steps issued from C) == T python-level sample + step calls == the same steps replayed
+    from a captured CUDA graph (every launch of the library is stream-ordered and capturable)."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=10, G=2, B=100, kw=dict(belief=True, reveal_interval=4, tolls=1), mode="fp64")
+    a, _ = _make_pair(pkg, c, tables)
+    b, _ = _make_pair(pkg, c, tables)
+    g, _ = _make_pair(pkg, c, tables)
+    for e in (a, b, g):
+        e.reset()
+    T = 24
+    for s in range(T):
+        a.step(a.sample_actions(step_counter=s))
+    b.rollout_random(T, step_counter=0)
+    # CUDA graph: capture 4 steps, replay 6 times (step counters 0..3 are baked in, so compare against the same)
+    ref, _ = _make_pair(pkg, c, tables)
+    ref.reset()
+    side = torch.cuda.Stream()
+    acts = torch.empty(c["B"], c["P"] + 1, dtype=torch.int64, device="cuda")
+    graph = torch.cuda.CUDAGraph()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g.rollout_random(1, actions=acts, step_counter=0)  # warm-up outside the capture
+        ref.rollout_random(1, step_counter=0)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph, stream=side):
+        g.rollout_random(4, actions=acts, step_counter=1)
+    for _ in range(3):
+        graph.replay()
+        ref.rollout_random(4, step_counter=1)
+    torch.cuda.synchronize()
+    for k in ("pos", "money", "timestep", "episode", "visits", "belief_map", "reward64", "terminated", "action_mask",
+              "node_features", "stats_vec"):
+        assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), k
+        assert getattr(g, k).cpu().numpy().tobytes() == getattr(ref, k).cpu().numpy().tobytes(), k
+    for e in (a, b, g, ref):
+        e.close()
