@@ -1595,6 +1595,8 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   // persistent observe grid (the block scheduler drains the older grid first: no overlap), and one persistent kernel
   // whose logic warps run one tile ahead of the observe warps (the logic's loads and shared-memory accesses queue
   // behind the writers' store stream in the SM's in-order LSU: the times added up, 159 vs 136 us).
+  // Also measured: an L2 persisting access-policy window on the belief map (52 MB at c3) slowed the step to 166-255 us
+  // (the carve-out starves the write stream of L2), so no residency hints are set.
   if (p.dbg_skip & 32) {
   } else if (p.A <= 4) {
     if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
