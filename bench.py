@@ -280,15 +280,17 @@ def run_cuda_arm(args, wl):
 
     # ---- end to end through the host-buffer API
     Ke = max(3, min(K, args.e2e_steps))
+    wire = torch.int64 if args.e2e_int64 else torch.int32  # host actions travel as int32 unless asked otherwise
+    wb = 8 if args.e2e_int64 else 4
     for _ in range(3):
-        env.step_host(env.sample_actions_host(step_counter=counter))
+        env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire))
         counter += 1
     barrier()
     sampler.active = True
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(Ke):
-        host_actions = env.sample_actions_host(step_counter=counter)  # the "policy" hands over HOST actions
+        host_actions = env.sample_actions_host(step_counter=counter, dtype=wire)  # the "policy" hands over HOST actions
         res = env.step_host(host_actions)  # H2D actions, kernel, D2H reward/flags, synchronised
         counter += 1
     ev1.record()
@@ -297,8 +299,8 @@ def run_cuda_arm(args, wl):
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
     assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
     e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": env.host_h2d_bytes_per_step, "d2h_bytes_per_step": env.host_d2h_bytes_per_step,
-           "steps": Ke, "note": "actions int64[B,A] from pinned host memory in; reward f32 + terminated/truncated/done "
+           "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb),
+           "steps": Ke, "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 + terminated/truncated/done "
            "u8 [B,A] + winner out to pinned host memory; observations stay on the device for the GPU policy; the D2H "
            "count includes the random policy's actions coming back to the host"}
 
@@ -348,6 +350,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype) instead of int32")
     ap.add_argument("--python-loop", action="store_true", help="issue every step from Python instead of sy_rollout_random")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -175,6 +175,15 @@ typedef struct SyHostOut {
 int sy_step_host(SyEnv* env, const int64_t* actions_host, int64_t* actions_dev, const SyState* state,
                  const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
 
+/* int32 wire format of the same three calls: a host-side caller moves half the bytes over PCIe (node ids fit 16 bits).
+ * Semantics are identical: -1 = DEFAULT_ACTION / None, anything that is not an affordable neighbour means `stay`. */
+int sy_step_i32(SyEnv* env, const int32_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
+                sy_stream_t stream);
+int sy_step_host_i32(SyEnv* env, const int32_t* actions_host, int32_t* actions_dev, const SyState* state,
+                     const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
+int sy_sample_actions_i32(SyEnv* env, const SyState* state, uint32_t step_counter, int32_t* actions,
+                          sy_stream_t stream);
+
 /* uniform random valid action per agent (Philox(seed; env, step_counter, agent)); -1 when the
  * agent has no affordable move (gnn_trainer.py:227-229).  The `random policy` of the benchmarks. */
 int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, int64_t* actions,

@@ -56,8 +56,17 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = env)
-constexpr int BEL_WARPS = 8;   // observe kernel: warps 0..7 propagate the belief ...
-constexpr int WR_WARPS = 8;    // ... warps 8..15 stream the dense observations
+#ifndef SY_BEL_WARPS
+#define SY_BEL_WARPS 8
+#endif
+#ifndef SY_WR_WARPS
+#define SY_WR_WARPS 8
+#endif
+#ifndef SY_STORE_HINT
+#define SY_STORE_HINT 0
+#endif
+constexpr int BEL_WARPS = SY_BEL_WARPS;  // observe kernel: the first warps propagate the belief ...
+constexpr int WR_WARPS = SY_WR_WARPS;    // ... the others stream the dense observations
 constexpr int THREADS = (BEL_WARPS + WR_WARPS) * 32;
 constexpr int EXP_SMEM = 96;   // logic kernel: exp(-d) entries staged in shared memory (larger d: global table)
 constexpr int COV_SMEM = 64;   // logic kernel: coverage entries staged in shared memory
@@ -104,7 +113,8 @@ struct Params {
   SyState st;
   SyObs ob;
   SyOut out;
-  const long long* actions;
+  const long long* actions;  // int64 [B, A] ...
+  const int* actions32;      // ... or int32 [B, A] (narrow wire format of the host-buffer path), exactly one is set
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr, wr_nf_fast;  // writer warps: smem staging layout (bytes) and path flags
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
@@ -181,6 +191,18 @@ __device__ __forceinline__ double exp_neg(const Tables& tb, int d) {
 // ---------------------------------------------------------------------------------------------
 // small device helpers
 // ---------------------------------------------------------------------------------------------
+// streaming 16-byte store of the observation arrays (written once per step, read by the policy much later)
+__device__ __forceinline__ void store_obs16(uint4* ptr, uint4 v) {
+#if SY_STORE_HINT == 0
+  __stcs(ptr, v);
+#elif SY_STORE_HINT == 1
+  *ptr = v;
+#elif SY_STORE_HINT == 2
+  __stcg(ptr, v);
+#else
+  __stwt(ptr, v);
+#endif
+}
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {  // LDGSTS: global -> shared, no staging register
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem));
@@ -453,7 +475,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
-    const long long a64 = p.actions[o];
+    const long long a64 = p.actions ? p.actions[o] : (long long)p.actions32[o];
     const int ps = p.st.pos[o];
     sm.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
     sm.pos[e * HS + a] = (u16)ps;
@@ -785,7 +807,7 @@ __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src
   uint4* d = reinterpret_cast<uint4*>(dst + head);
   const uint4* sv = reinterpret_cast<const uint4*>(src + head);
 #pragma unroll 2
-  for (int i = lane; i < nvec; i += 32) __stcs(d + i, sv[i]);
+  for (int i = lane; i < nvec; i += 32) store_obs16(d + i, sv[i]);
   const int done = head + (nvec << 4);
   if (lane < n - done) dst[done + lane] = src[done + lane];
 }
@@ -819,7 +841,7 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
   unsigned long long m = mine;
 #pragma unroll 4
   for (int i = lane; i < nvec; i += 32, m >>= 1)
-    if (!(m & 1ull)) __stcs(body + i, z);
+    if (!(m & 1ull)) store_obs16(body + i, z);
   __syncwarp();
   if (mine) bits[lane] = 0ull;
   if (myc >= 0) {
@@ -835,7 +857,7 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
         v.w = sub == 3 ? one : v.w;
       }
     }
-    __stcs(body + myc, v);
+    store_obs16(body + myc, v);
   }
 }
 
@@ -1137,7 +1159,8 @@ __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
 // ---------------------------------------------------------------------------------------------
 // random valid policy: thread per (env, agent)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, unsigned step_counter, long long* actions) {
+template <typename ActT>
+__global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, unsigned step_counter, ActT* actions) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)p.B * p.A) return;
   const int b = (int)(i / p.A), a = (int)(i - (size_t)b * p.A);
@@ -1163,7 +1186,7 @@ __global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, 
       }
     }
   }
-  actions[i] = act;
+  actions[i] = (ActT)act;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1578,8 +1601,12 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
   return SY_OK;
 }
 
-int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
-  if (!e || !actions) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
+}  // extern "C"
+
+namespace {
+int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
+              sy_stream_t stream) {
+  if (!e || (!actions && !actions32)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   if (!out || !out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
   Params p;
@@ -1587,6 +1614,7 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   if (rc) return rc;
   if ((rc = check_obs(ob))) return rc;
   p.actions = reinterpret_cast<const long long*>(actions);
+  p.actions32 = actions32;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
@@ -1616,15 +1644,8 @@ int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob
   return SY_OK;
 }
 
-int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, const SyState* st, const SyObs* ob,
-                 const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
-  if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
-  CUDA_TRY(cudaSetDevice(e->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
+int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaStream_t s) {
   const size_t n = (size_t)e->cfg.num_envs * e->A;
-  CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  const int rc = sy_step(e, actions_dev, st, ob, out, stream);
-  if (rc) return rc;
   if (ho->reward) CUDA_TRY(cudaMemcpyAsync(ho->reward, out->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (ho->terminated) CUDA_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, n, cudaMemcpyDeviceToHost, s));
   if (ho->truncated) CUDA_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, n, cudaMemcpyDeviceToHost, s));
@@ -1634,17 +1655,61 @@ int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, co
   return SY_OK;
 }
 
-int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_t* actions, sy_stream_t stream) {
+template <typename ActT>
+int sample_impl(SyEnv* e, const SyState* st, uint32_t step_counter, ActT* actions, sy_stream_t stream) {
   if (!e || !actions) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   Params p;
   int rc = fill_params(e, st, nullptr, nullptr, p);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const size_t n = (size_t)p.B * p.A;
-  sy_sample_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, step_counter, reinterpret_cast<long long*>(actions));
+  sy_sample_actions_kernel<ActT><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, step_counter, actions);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
+  return step_impl(e, actions, nullptr, st, ob, out, stream);
+}
+
+int sy_step_i32(SyEnv* e, const int32_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
+  return step_impl(e, nullptr, actions, st, ob, out, stream);
+}
+
+int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, const SyState* st, const SyObs* ob,
+                 const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
+  if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)e->cfg.num_envs * e->A;
+  CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+  const int rc = step_impl(e, actions_dev, nullptr, st, ob, out, stream);
+  if (rc) return rc;
+  return copy_results_and_sync(e, out, ho, s);
+}
+
+int sy_step_host_i32(SyEnv* e, const int32_t* actions_host, int32_t* actions_dev, const SyState* st, const SyObs* ob,
+                     const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
+  if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)e->cfg.num_envs * e->A;
+  CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  const int rc = step_impl(e, nullptr, actions_dev, st, ob, out, stream);
+  if (rc) return rc;
+  return copy_results_and_sync(e, out, ho, s);
+}
+
+int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_t* actions, sy_stream_t stream) {
+  return sample_impl<long long>(e, st, step_counter, reinterpret_cast<long long*>(actions), stream);
+}
+
+int sy_sample_actions_i32(SyEnv* e, const SyState* st, uint32_t step_counter, int32_t* actions, sy_stream_t stream) {
+  return sample_impl<int>(e, st, step_counter, actions, stream);
 }
 
 int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,

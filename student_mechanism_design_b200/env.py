@@ -229,12 +229,13 @@ class BatchedScotlandYardEnv:
         if not self._is_reset:
             raise _cabi.SyError("step() before reset()")
         a = actions
-        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == torch.int64 and a.is_contiguous()
-                and tuple(a.shape) == (self.num_envs, self.num_agents)):
+        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype in (torch.int64, torch.int32)
+                and a.is_contiguous() and tuple(a.shape) == (self.num_envs, self.num_agents)):
             a = self._dev(actions, torch.int64, (self.num_envs, self.num_agents))
+        fn = self._lib.sy_step if a.dtype == torch.int64 else self._lib.sy_step_i32  # int32: narrow wire format
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.sy_step(self._handle, a.data_ptr(), C.byref(self._state), C.byref(self._obs),
-                                          C.byref(self._out), self._stream()))
+            _cabi.check(fn(self._handle, a.data_ptr(), C.byref(self._state), C.byref(self._obs), C.byref(self._out),
+                           self._stream()))
         self._last_actions = a
         info = {"winner": self.winner, "done": self.done_flags}
         return self.observation(), self.reward, self.terminated, self.truncated, info
@@ -246,9 +247,9 @@ class BatchedScotlandYardEnv:
         if step_counter is None:
             step_counter = self._sample_counter
             self._sample_counter += 1
+        fn = self._lib.sy_sample_actions if out.dtype == torch.int64 else self._lib.sy_sample_actions_i32
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.sy_sample_actions(self._handle, C.byref(self._state), int(step_counter) & 0xFFFFFFFF,
-                                                    out.data_ptr(), self._stream()))
+            _cabi.check(fn(self._handle, C.byref(self._state), int(step_counter) & 0xFFFFFFFF, out.data_ptr(), self._stream()))
         return out
 
     def rollout_random(self, num_steps: int, actions: Optional[torch.Tensor] = None,
@@ -276,21 +277,21 @@ class BatchedScotlandYardEnv:
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, pin_memory=True)  # noqa: E731
             self._host = dict(reward=pin(B, A, dtype=torch.float32), terminated=pin(B, A, dtype=torch.bool),
                               truncated=pin(B, A, dtype=torch.bool), done=pin(B, A, dtype=torch.bool),
-                              winner=pin(B, dtype=torch.int8), actions=pin(B, A, dtype=torch.int64))
+                              winner=pin(B, dtype=torch.int8), actions=pin(B, A, dtype=torch.int64),
+                              actions32=pin(B, A, dtype=torch.int32))
             self._actions_dev = torch.empty(B, A, dtype=torch.int64, device=self.device)
+            self._actions_dev32 = torch.empty(B, A, dtype=torch.int32, device=self.device)
             self._host_out = _cabi.SyHostOut(*[self._host[k].data_ptr() for k in
                                                ("reward", "terminated", "truncated", "done", "winner")])
         return self._host
 
-    @property
-    def host_h2d_bytes_per_step(self) -> int:
-        return self.num_envs * self.num_agents * 8
+    def host_h2d_bytes_per_step(self, action_bytes: int = 8) -> int:
+        return self.num_envs * self.num_agents * action_bytes
 
-    @property
-    def host_d2h_bytes_per_step(self) -> int:
+    def host_d2h_bytes_per_step(self, action_bytes: int = 8) -> int:
         """step_host results (+ the sampled actions when sample_actions_host feeds it)"""
         B, A = self.num_envs, self.num_agents
-        return B * A * (4 + 3) + B + B * A * 8
+        return B * A * (4 + 3) + B + B * A * action_bytes
 
     def step_host(self, actions) -> Dict[str, torch.Tensor]:
         """`step` with HOST buffers on both sides, as the reference's env is called (python ints in,
@@ -301,24 +302,26 @@ class BatchedScotlandYardEnv:
             raise _cabi.SyError("step() before reset()")
         host = self._host_buffers()
         a = torch.as_tensor(actions)
-        if a.is_cuda or a.dtype != torch.int64 or not a.is_contiguous() or \
+        if a.is_cuda or a.dtype not in (torch.int64, torch.int32) or not a.is_contiguous() or \
                 tuple(a.shape) != (self.num_envs, self.num_agents):
             a = torch.as_tensor(np.asarray(a.cpu() if a.is_cuda else a), dtype=torch.int64).contiguous()
             if tuple(a.shape) != (self.num_envs, self.num_agents):
                 raise ValueError(f"expected shape {(self.num_envs, self.num_agents)}, got {tuple(a.shape)}")
+        narrow = a.dtype == torch.int32  # int32 host actions travel as int32 (half the PCIe bytes)
+        fn, stage = (self._lib.sy_step_host_i32, self._actions_dev32) if narrow else (self._lib.sy_step_host, self._actions_dev)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.sy_step_host(self._handle, a.data_ptr(), self._actions_dev.data_ptr(),
-                                               C.byref(self._state), C.byref(self._obs), C.byref(self._out),
-                                               C.byref(self._host_out), self._stream()))
+            _cabi.check(fn(self._handle, a.data_ptr(), stage.data_ptr(), C.byref(self._state), C.byref(self._obs),
+                           C.byref(self._out), C.byref(self._host_out), self._stream()))
         return {k: host[k] for k in ("reward", "terminated", "truncated", "done", "winner")}
 
-    def sample_actions_host(self, step_counter: Optional[int] = None) -> torch.Tensor:
+    def sample_actions_host(self, step_counter: Optional[int] = None, dtype=torch.int64) -> torch.Tensor:
         """random valid actions delivered in pinned HOST memory (stands in for a host-side policy)"""
         host = self._host_buffers()
-        dev_actions = self.sample_actions(out=self._actions_dev, step_counter=step_counter)
-        host["actions"].copy_(dev_actions, non_blocking=True)
+        key, stage = ("actions", self._actions_dev) if dtype == torch.int64 else ("actions32", self._actions_dev32)
+        dev_actions = self.sample_actions(out=stage, step_counter=step_counter)
+        host[key].copy_(dev_actions, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        return host["actions"]
+        return host[key]
 
     # ------------------------------------------------------------------ observations
     def _static_tensors(self):

@@ -579,3 +579,34 @@ def test_rollout_random_and_cuda_graph_replay(torch_cuda, tables):
         assert getattr(g, k).cpu().numpy().tobytes() == getattr(ref, k).cpu().numpy().tobytes(), k
     for e in (a, b, g, ref):
         e.close()
+
+
+def test_int32_wire_format_equals_int64(torch_cuda, tables):
+    """sy_step_i32 / sy_step_host_i32 / sy_sample_actions_i32: the narrow action format gives identical results."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=10, G=2, B=70, kw=dict(belief=True, reveal_interval=4), mode="fp64")
+    a, _ = _make_pair(pkg, c, tables)
+    b, _ = _make_pair(pkg, c, tables)
+    h, _ = _make_pair(pkg, c, tables)
+    for e in (a, b, h):
+        e.reset()
+    a32 = torch.empty(c["B"], c["P"] + 1, dtype=torch.int32, device="cuda")
+    for s in range(15):
+        acts = a.sample_actions(step_counter=s)
+        b.sample_actions(out=a32, step_counter=s)
+        assert torch.equal(acts.to(torch.int32), a32)
+        junk = acts.clone()
+        junk[::7] = 10_000 + s  # out of range in both formats
+        a.step(junk)
+        b.step(junk.to(torch.int32))
+        hacts = h.sample_actions_host(step_counter=s, dtype=torch.int32).clone()
+        assert hacts.dtype == torch.int32
+        hacts[::7] = 10_000 + s
+        res = h.step_host(hacts)
+        for k in ("pos", "money", "reward64", "terminated", "action_mask", "belief_map"):
+            assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), (k, s)
+            assert getattr(a, k).cpu().numpy().tobytes() == getattr(h, k).cpu().numpy().tobytes(), (k, s)
+        assert res["reward"].numpy().tobytes() == a.reward.cpu().numpy().tobytes()
+    for e in (a, b, h):
+        e.close()
