@@ -1644,13 +1644,26 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   return SY_OK;
 }
 
+// D2H of the step results.  Members that are adjacent in both device and host memory (the host mirror allocates each
+// side as one block) are merged into a single copy: one PCIe transaction instead of five.
 int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaStream_t s) {
   const size_t n = (size_t)e->cfg.num_envs * e->A;
-  if (ho->reward) CUDA_TRY(cudaMemcpyAsync(ho->reward, out->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (ho->terminated) CUDA_TRY(cudaMemcpyAsync(ho->terminated, out->terminated, n, cudaMemcpyDeviceToHost, s));
-  if (ho->truncated) CUDA_TRY(cudaMemcpyAsync(ho->truncated, out->truncated, n, cudaMemcpyDeviceToHost, s));
-  if (ho->done) CUDA_TRY(cudaMemcpyAsync(ho->done, out->done, n, cudaMemcpyDeviceToHost, s));
-  if (ho->winner) CUDA_TRY(cudaMemcpyAsync(ho->winner, out->winner, (size_t)e->cfg.num_envs, cudaMemcpyDeviceToHost, s));
+  struct Seg { char* dst; const char* src; size_t bytes; };
+  Seg segs[5];
+  int m = 0;
+  auto add = [&](void* dst, const void* src, size_t bytes) {
+    if (!dst) return;
+    if (m > 0 && segs[m - 1].dst + segs[m - 1].bytes == (char*)dst && segs[m - 1].src + segs[m - 1].bytes == (const char*)src)
+      segs[m - 1].bytes += bytes;
+    else
+      segs[m++] = Seg{(char*)dst, (const char*)src, bytes};
+  };
+  add(ho->reward, out->reward, n * sizeof(float));
+  add(ho->terminated, out->terminated, n);
+  add(ho->truncated, out->truncated, n);
+  add(ho->done, out->done, n);
+  add(ho->winner, out->winner, (size_t)e->cfg.num_envs);
+  for (int i = 0; i < m; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   return SY_OK;
 }

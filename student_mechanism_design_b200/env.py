@@ -149,12 +149,11 @@ class BatchedScotlandYardEnv:
             self.node_features = z(B, N, A, dtype=torch.float32)
             self.agent_budget = z(B, A, dtype=torch.float32)
             self.mrx_revealed = z(B, dtype=torch.int32)
-            self.reward = z(B, A, dtype=torch.float32)
+            # step results live in ONE block (reward | terminated | truncated | done | winner) so that the host-buffer
+            # path moves them with a single D2H copy
+            self._result_block = z(self._result_bytes(), dtype=torch.uint8)
+            (self.reward, self.terminated, self.truncated, self.done_flags, self.winner) = self._result_views(self._result_block)
             self.reward64 = z(B, A, dtype=torch.float64) if keep_reward64 else None
-            self.terminated = z(B, A, dtype=torch.bool)
-            self.truncated = z(B, A, dtype=torch.bool)
-            self.done_flags = z(B, A, dtype=torch.bool)
-            self.winner = z(B, dtype=torch.int8)
             self.stats_vec = z(_cabi.SY_NUM_STATS, dtype=torch.int64) if collect_stats else None
         self._state = _cabi.SyState(_ptr(self.pos), _ptr(self.money), _ptr(self.timestep), _ptr(self.graph_id),
                                     _ptr(self.episode), _ptr(self.done), _ptr(self.visits), _ptr(self.belief_map))
@@ -167,6 +166,18 @@ class BatchedScotlandYardEnv:
         self._is_reset = False
 
     # ------------------------------------------------------------------ plumbing
+    def _result_bytes(self) -> int:
+        n = self.num_envs * self.num_agents
+        return 4 * n + 3 * n + self.num_envs
+
+    def _result_views(self, block: torch.Tensor):
+        B, A = self.num_envs, self.num_agents
+        n = B * A
+        reward = block[: 4 * n].view(torch.float32).view(B, A)
+        flags = [block[4 * n + k * n: 4 * n + (k + 1) * n].view(torch.bool).view(B, A) for k in range(3)]
+        winner = block[7 * n: 7 * n + B].view(torch.int8)
+        return reward, flags[0], flags[1], flags[2], winner
+
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
@@ -275,10 +286,10 @@ class BatchedScotlandYardEnv:
         if getattr(self, "_host", None) is None:
             B, A = self.num_envs, self.num_agents
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, pin_memory=True)  # noqa: E731
-            self._host = dict(reward=pin(B, A, dtype=torch.float32), terminated=pin(B, A, dtype=torch.bool),
-                              truncated=pin(B, A, dtype=torch.bool), done=pin(B, A, dtype=torch.bool),
-                              winner=pin(B, dtype=torch.int8), actions=pin(B, A, dtype=torch.int64),
-                              actions32=pin(B, A, dtype=torch.int32))
+            self._host_block = pin(self._result_bytes(), dtype=torch.uint8)  # same layout as the device result block
+            r, te, tr, dn, wn = self._result_views(self._host_block)
+            self._host = dict(reward=r, terminated=te, truncated=tr, done=dn, winner=wn,
+                              actions=pin(B, A, dtype=torch.int64), actions32=pin(B, A, dtype=torch.int32))
             self._actions_dev = torch.empty(B, A, dtype=torch.int64, device=self.device)
             self._actions_dev32 = torch.empty(B, A, dtype=torch.int32, device=self.device)
             self._host_out = _cabi.SyHostOut(*[self._host[k].data_ptr() for k in
