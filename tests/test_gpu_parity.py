@@ -610,3 +610,67 @@ def test_int32_wire_format_equals_int64(torch_cuda, tables):
         assert res["reward"].numpy().tobytes() == a.reward.cpu().numpy().tobytes()
     for e in (a, b, h):
         e.close()
+
+
+def _custom_pair(pkg, tables, graph_spec, P, money, B, mode="fp64", **kw):
+    env = pkg.BatchedScotlandYardEnv(B, P, money, graphs=[graph_spec], seed=23, auto_reset=True, reward_mode=mode,
+                                     keep_reward64=True, reward_tables=tables, max_timestep=kw.pop("max_timestep", 250), **kw)
+    ocfg = so.OracleConfig(num_police=P, agent_money=money, reward_mode=mode, reveal_interval=kw.get("reveal_interval", 0),
+                           toll=kw.get("tolls", 0), belief=kw.get("belief", False), max_timestep=env.config.max_timestep,
+                           exp_table=tables[0], cov_table=tables[1])
+    ob = so.OracleBatch.from_seed(ocfg, [so.Graph(graph_spec.num_nodes, graph_spec.edge_links, graph_spec.edges)], B, seed=23,
+                                  auto_reset=True)
+    return env, ob
+
+
+@pytest.mark.parametrize("mode", ["fp64", "fp32"])
+def test_disconnected_graph_with_isolated_nodes(torch_cuda, tables, mode):
+    """Graphs the reference generator never produces but its code handles: unreachable pairs give distance inf
+    (pathfinding.py:133-137) -> -1/(inf+1) = -0.0, exp(-inf) = 0, mean(inf) = inf; isolated nodes have no moves and
+    keep their belief mass (belief_module.py:93-97)."""
+    pkg = _pkg()
+    # two components {0..4}, {5..8}, isolated nodes 9, 10
+    links = [[0, 1], [1, 2], [2, 3], [3, 4], [0, 4], [5, 6], [6, 7], [7, 8], [5, 8]]
+    g = pkg.GraphSpec(11, links, [1, 2, 3, 4, 2, 1, 1, 3, 2])
+    c = dict(kw=dict(belief=True, reveal_interval=3, tolls=1), mode=mode)
+    env, ob = _custom_pair(pkg, tables, g, P=3, money=9, B=96, mode=mode, belief=True, reveal_interval=3, tolls=1)
+    env.reset()
+    _compare_state(env, ob, c, "reset")
+    saw_inf = False
+    for s in range(40):
+        acts = env.sample_actions(step_counter=s)
+        a_h = acts.cpu().numpy()
+        assert np.array_equal(a_h, ob.sample_actions(s)), s
+        env.step(acts)
+        want = ob.step(a_h)
+        _compare_out(env, want, c, s)
+        _compare_state(env, ob, c, s)
+        D = ob.graphs[0].apsp()
+        pos = ob.pos()
+        saw_inf |= bool((D[pos[:, 0], pos[:, 1]] >= so.INF_U16).any())
+    assert saw_inf, "the test never exercised an unreachable pair"
+    env.close()
+
+
+def test_crowded_and_broke_edge_cases(torch_cuda, tables):
+    """N == A (every node occupied: nobody can ever move onto a free node except by capture rules), police that start
+    broke (money 0 -> all skipped -> out-of-money ending at the first step, reward_calculator.py:75-79), toll larger
+    than any budget, single police."""
+    pkg = _pkg()
+    ring = pkg.GraphSpec(5, [[0, 1], [1, 2], [2, 3], [3, 4], [0, 4]], [1, 2, 1, 3, 2])
+    for P, money, kw in [(4, 6, {}), (2, 0, {}), (3, 5, dict(tolls=9)), (1, 4, dict(belief=True))]:
+        c = dict(kw=kw, mode="fp64")
+        env, ob = _custom_pair(pkg, tables, ring, P=P, money=money, B=64, **dict(kw))
+        env.reset()
+        for s in range(25):
+            acts = env.sample_actions(step_counter=s)
+            a_h = acts.cpu().numpy()
+            assert np.array_equal(a_h, ob.sample_actions(s)), (P, money, s)
+            env.step(acts)
+            want = ob.step(a_h)
+            _compare_out(env, want, c, (P, money, s))
+            _compare_state(env, ob, c, (P, money, s))
+        st = env.stats()
+        if money == 0 or kw.get("tolls", 0) > money:
+            assert st["out_of_money"] == st["episodes"] == 64 * 25  # every step ends an episode
+        env.close()
