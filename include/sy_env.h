@@ -47,7 +47,7 @@ enum {
 enum { SY_REWARD_FP64 = 0, SY_REWARD_FP32 = 1 };
 enum { SY_WINNER_NONE = 0, SY_WINNER_MRX = 1, SY_WINNER_POLICE = 2 };
 
-/* indices into the int64 statistics vector (SyOut.stats); summed over ranks by the host */
+/* indices into the int64 statistics vector (see sy_stats); summed over ranks by the host */
 enum {
   SY_STAT_ENV_STEPS = 0,
   SY_STAT_EPISODES = 1,
@@ -56,7 +56,13 @@ enum {
   SY_STAT_TRUNCATIONS = 4, /* timestep > max_timestep, reward_calculator.py:68-74 */
   SY_STAT_OUT_OF_MONEY = 5, /* reward_calculator.py:75-79 */
   SY_STAT_SUM_EPISODE_LENGTH = 6,
-  SY_STAT_SUM_BUDGET_SPENT = 7
+  SY_STAT_SUM_BUDGET_SPENT = 7, /* over all steps (edge weight + toll of every police move) */
+  /* the aggregates of src/eval/metrics.py:AggregatedMetrics (MetricsTracker.get_aggregated_metrics, :168-232) */
+  SY_STAT_SUM_SQ_EPISODE_LENGTH = 8,
+  SY_STAT_SUM_LENGTH_POLICE_WINS = 9, /* -> mean_time_to_catch */
+  SY_STAT_SUM_LENGTH_MRX_WINS = 10,   /* -> mean_survival_time */
+  SY_STAT_SUM_EPISODE_BUDGET_SPENT = 11, /* budget spent inside FINISHED episodes -> mean_budget_spent / efficiency */
+  SY_STAT_POLICE_MOVES = 12              /* over all steps; x toll = tolls paid */
 };
 
 typedef void* sy_stream_t;
@@ -114,7 +120,7 @@ typedef struct SyOut {
   uint8_t* truncated;  /* [B, A] */
   uint8_t* done;       /* [B, A] terminated | truncated */
   int8_t* winner;      /* [B]   SY_WINNER_* (env.current_winner, yard.py:250) */
-  int64_t* stats;      /* [SY_NUM_STATS] device accumulators or NULL */
+  int64_t* stats;      /* non-NULL: collect episode statistics (accumulated inside the library; read with sy_stats) */
 } SyOut;
 
 int sy_abi_version(void);
@@ -188,6 +194,12 @@ int sy_sample_actions_i32(SyEnv* env, const SyState* state, uint32_t step_counte
  * agent has no affordable move (gnn_trainer.py:227-229).  The `random policy` of the benchmarks. */
 int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, int64_t* actions,
                       sy_stream_t stream);
+
+/* Add the statistics accumulated since the last call to `stats` (device, int64 [SY_NUM_STATS], caller-owned and
+ * cumulative) and clear the library's internal accumulators.  Asynchronous on `stream`.  Statistics are collected by
+ * sy_step only while SyOut.stats is non-NULL (they are kept in per-tile-group lines inside the library so that the
+ * step kernel's atomics do not serialise on one cache line). */
+int sy_stats(SyEnv* env, int64_t* stats, sy_stream_t stream);
 
 /* `num_steps` steps of the random-valid policy rollout the reference's trainers start from (gnn_trainer.py:201-250 with
  * RandomAgent, src/agent/random_agent.py:7): per step sy_sample_actions(step_counter0 + k) into `actions` (device,

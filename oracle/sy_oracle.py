@@ -382,6 +382,7 @@ class OracleEnv:
         self.t = 0
         self.visits = np.zeros(self.N, dtype=np.int64)  # node_visit_counts, yard.py:85
         self.winner = WINNER_NONE
+        self.moves = getattr(self, "moves", 0)  # police moves over the env's lifetime (not reset)
         self.belief = belief_uniform(self.N) if self.cfg.belief else None
         self.revealed = -1 if self.cfg.reveal_interval > 0 else self.pos[0]
 
@@ -424,6 +425,7 @@ class OracleEnv:
             if tgt not in pos[1:] and tgt != pos[i]:
                 money[i] -= int(self.W[pos[i], tgt]) + self.cfg.toll
                 pos[i] = tgt
+                self.moves += 1
         for i in range(1, A):  # yard.py:244-245
             self.visits[pos[i]] += 1
         rewards, terminated, truncated, winner = self._rewards_terminations(no_money)
@@ -597,6 +599,7 @@ class OracleBatch:
         self.envs = [OracleEnv(cfg, graphs[g], sp) for g, sp in zip(self.graph_id, start_positions)]
         self.episode = [0] * len(self.envs)
         self.done = [False] * len(self.envs)
+        self.finished = []
 
     @classmethod
     def from_seed(cls, cfg, graphs, num_envs, seed=0, env_offset=0, auto_reset=True, resample_graph=False):
@@ -627,6 +630,8 @@ class OracleBatch:
             out["reward"][b] = r
             out["terminated"][b], out["truncated"][b], out["winner"][b] = te, tr, win
             if te or tr:
+                # (episode length, winner, budget spent) of the finished episode: what metrics.py:EpisodeMetrics records
+                self.finished.append((env.t, int(win), self.cfg.num_police * self.cfg.agent_money - sum(env.money[1:])))
                 if self.auto_reset:
                     self.episode[b] += 1
                     e = self.env_offset + b

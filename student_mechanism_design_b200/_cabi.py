@@ -16,7 +16,8 @@ SY_NUM_STATS = 16
 SY_REWARD_FP64, SY_REWARD_FP32 = 0, 1
 STAT_NAMES = [
     "env_steps", "episodes", "mrx_wins", "police_wins", "truncations", "out_of_money",
-    "sum_episode_length", "sum_budget_spent",
+    "sum_episode_length", "sum_budget_spent", "sum_sq_episode_length", "sum_length_police_wins",
+    "sum_length_mrx_wins", "sum_episode_budget_spent", "police_moves",
 ]
 
 
@@ -67,6 +68,7 @@ SIGNATURES = {
                                    C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),
     "sy_sample_actions_i32": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_sample_actions": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sy_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "sy_rollout_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                     C.POINTER(SyOut), C.c_void_p]),
     "sy_action_mask_dense": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

@@ -55,6 +55,7 @@ int fail(int code, const char* fmt, ...) {
       return fail(SY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+constexpr int STAT_REPLICAS = 64;  // statistics accumulator lines (128 B each) the tiles are spread over
 constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = env)
 #ifndef SY_BEL_WARPS
 #define SY_BEL_WARPS 8
@@ -118,6 +119,7 @@ struct Params {
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr, wr_nf_fast;  // writer warps: smem staging layout (bytes) and path flags
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
+  unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
   // reset-only inputs
   const uint8_t* reset_mask;
@@ -242,7 +244,7 @@ struct WarpTile {
 // register compares instead of a chain of dependent shared-memory loads); an agent's own node does not change before
 // its own move, so all A edge-weight lookups are issued up front (one round trip).
 template <int MAXA, typename PosT>
-__device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money, const int* act, int g, int t, int& spent) {
+__device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money, const int* act, int g, int t, int& spent, int& moves) {
   const Tables& tb = p.tb;
   const int N = p.N, P = p.P;
   int rp[MAXA], rm[MAXA], ra[MAXA], wpre[MAXA];
@@ -279,6 +281,7 @@ __device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money
         rp[i] = ai;
         rm[i] = m - (w + p.toll);
         spent += w + p.toll;
+        moves += 1;
       }
     }
   }
@@ -431,7 +434,8 @@ __device__ unsigned long long g_phase_clk[8];
 #define PHASE_MARK(k) do { } while (0)
 #endif
 
-constexpr int CNT_SMEM = 5120;  // bytes of the move-count table staged in shared memory (N * (wcap + 1) <= this)
+constexpr int CNT_SMEM = 2048;  // bytes of the move-count table staged in shared memory (N * (wcap + 1) <= this); the
+                                // tile smem is kept small: 9 CTAs per SM must leave room for an L1 that holds the graph tables
 template <int MAXA>
 struct LogicSmem {
   static constexpr int DS = MAXA * MAXA + 2;  // row stride (halfwords) of the pair-distance matrices: odd word count
@@ -449,6 +453,7 @@ struct LogicSmem {
   int reset_gid[32];
   int t[32], gid[32], episode[32], frozen[32], status[32];
   int t_new[32], done[32], bel[32], revealed[32], clear[32];
+  int ep_spent[32], spent[32], moves[32];  // statistics inputs handed from warp 0 to the statistics warp
   int cnt_staged;
 };
 
@@ -523,9 +528,9 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   //             depend on the outcome, so it is computed off the critical path
   //   warps 2,3 visit counters at both nodes each police can end on (its node or its action target): the HBM
   //             round trip of the read-modify-write overlaps the moves
-  int spent = 0;
+  int spent = 0, moves = 0;
   if (warp == 0) {
-    if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent);
+    if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent, moves);
   } else if (warp == 1 && p.auto_reset && active) {
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
     const unsigned ep = (unsigned)(sm.episode[lane] + 1);
@@ -626,22 +631,17 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     }
   } else {
     // timestep, reveal schedule, same-step auto-reset, statistics
-    int n_step = 0, n_ep = 0, n_mrx = 0, n_pol = 0, n_trunc = 0, n_broke = 0, len_sum = 0;
+    int ep_spent = 0;
     int t_new = t, done = frozen, bel = BEL_KEEP, revealed = -1, episode = sm.episode[lane], gnew = g;
     bool clear_visits = false;
     if (live) {
       if (active) {
-        n_step = 1;
         t_new = t + 1;  // yard.py:355
         p.out.winner[b] = (int8_t)(status == ST_CAPTURE ? SY_WINNER_POLICE : (status == ST_RUNNING ? SY_WINNER_NONE : SY_WINNER_MRX));
         bel = BEL_PROPAGATE;
         if (status != ST_RUNNING) {
-          n_ep = 1;
-          n_pol = (status == ST_CAPTURE);
-          n_mrx = (status != ST_CAPTURE);
-          n_trunc = (status == ST_TIMEOUT);
-          n_broke = (status == ST_NO_MONEY);
-          len_sum = t_new;
+          ep_spent = P * p.agent_money;  // every police starts an episode with agent_money (yard.py:117-119)
+          for (int i = 1; i <= P; ++i) ep_spent -= money[i];
           if (p.auto_reset) {  // same-step auto-reset: the observation describes the fresh episode
             episode += 1;
             gnew = sm.reset_gid[lane];
@@ -673,37 +673,60 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     sm.bel[lane] = bel;
     sm.revealed[lane] = revealed;
     sm.clear[lane] = clear_visits;
-    if (p.out.stats) {
-      n_step = __reduce_add_sync(FULL, n_step);
-      n_ep = __reduce_add_sync(FULL, n_ep);
-      spent = __reduce_add_sync(FULL, spent);
-      if (n_ep) {  // warp-uniform
-        n_mrx = __reduce_add_sync(FULL, n_mrx);
-        n_pol = __reduce_add_sync(FULL, n_pol);
-        n_trunc = __reduce_add_sync(FULL, n_trunc);
-        n_broke = __reduce_add_sync(FULL, n_broke);
-        len_sum = __reduce_add_sync(FULL, len_sum);
-      }
-      if (lane == 0) {
-        unsigned long long* st = reinterpret_cast<unsigned long long*>(p.out.stats);
-        atomicAdd(st + SY_STAT_ENV_STEPS, (unsigned long long)n_step);
-        if (n_ep) {
-          atomicAdd(st + SY_STAT_EPISODES, (unsigned long long)n_ep);
-          atomicAdd(st + SY_STAT_MRX_WINS, (unsigned long long)n_mrx);
-          atomicAdd(st + SY_STAT_POLICE_WINS, (unsigned long long)n_pol);
-          atomicAdd(st + SY_STAT_TRUNCATIONS, (unsigned long long)n_trunc);
-          atomicAdd(st + SY_STAT_OUT_OF_MONEY, (unsigned long long)n_broke);
-          atomicAdd(st + SY_STAT_SUM_EPISODE_LENGTH, (unsigned long long)len_sum);
-        }
-        if (spent) atomicAdd(st + SY_STAT_SUM_BUDGET_SPENT, (unsigned long long)spent);
-      }
-    }
+    sm.ep_spent[lane] = ep_spent;
+    sm.spent[lane] = spent;
+    sm.moves[lane] = moves;
     PHASE_MARK(5);
   }
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(6);
 
-  // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85)
+  // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85); the last warp
+  // (lightest reward share) reduces the tile's episode statistics, off warp 0's critical path
+  if (warp == LOGIC_WARPS - 1 && p.out.stats) {
+    const int st = sm.status[lane];
+    const bool fin = active && st != ST_RUNNING;
+    const int len = fin ? t + 1 : 0;  // episode length = timestep after the final step (yard.py:355)
+    int n_step = active, n_ep = fin, n_pol = fin && st == ST_CAPTURE, n_mrx = fin && st != ST_CAPTURE;
+    int n_trunc = fin && st == ST_TIMEOUT, n_broke = fin && st == ST_NO_MONEY;
+    int len_sum = len, len_sq = len * len, len_pol = n_pol ? len : 0, len_mrx = n_mrx ? len : 0;
+    int ep_spent = sm.ep_spent[lane], spent = sm.spent[lane], moves = sm.moves[lane];
+    // per-tile sums -> one of STAT_REPLICAS library-owned accumulator lines (sy_stats folds them into the caller's
+    // vector): with a single shared line the 13 atomics of all 2048 tiles serialised in one L2 slice (8 us per step)
+    n_step = __reduce_add_sync(FULL, n_step);
+    n_ep = __reduce_add_sync(FULL, n_ep);
+    spent = __reduce_add_sync(FULL, spent);
+    moves = __reduce_add_sync(FULL, moves);
+    if (n_ep) {  // warp-uniform
+      n_mrx = __reduce_add_sync(FULL, n_mrx);
+      n_pol = __reduce_add_sync(FULL, n_pol);
+      n_trunc = __reduce_add_sync(FULL, n_trunc);
+      n_broke = __reduce_add_sync(FULL, n_broke);
+      len_sum = __reduce_add_sync(FULL, len_sum);
+      len_sq = __reduce_add_sync(FULL, len_sq);
+      len_pol = __reduce_add_sync(FULL, len_pol);
+      len_mrx = __reduce_add_sync(FULL, len_mrx);
+      ep_spent = __reduce_add_sync(FULL, ep_spent);
+    }
+    int v = 0;  // every lane holds all sums: lane k adds statistic k (one atomic instruction for the warp)
+    switch (lane) {
+      case SY_STAT_ENV_STEPS: v = n_step; break;
+      case SY_STAT_EPISODES: v = n_ep; break;
+      case SY_STAT_MRX_WINS: v = n_mrx; break;
+      case SY_STAT_POLICE_WINS: v = n_pol; break;
+      case SY_STAT_TRUNCATIONS: v = n_trunc; break;
+      case SY_STAT_OUT_OF_MONEY: v = n_broke; break;
+      case SY_STAT_SUM_EPISODE_LENGTH: v = len_sum; break;
+      case SY_STAT_SUM_BUDGET_SPENT: v = spent; break;
+      case SY_STAT_SUM_SQ_EPISODE_LENGTH: v = len_sq; break;
+      case SY_STAT_SUM_LENGTH_POLICE_WINS: v = len_pol; break;
+      case SY_STAT_SUM_LENGTH_MRX_WINS: v = len_mrx; break;
+      case SY_STAT_SUM_EPISODE_BUDGET_SPENT: v = ep_spent; break;
+      case SY_STAT_POLICE_MOVES: v = moves; break;
+      default: break;
+    }
+    if (v) atomicAdd(p.stats_rep + (size_t)(blockIdx.x % STAT_REPLICAS) * SY_NUM_STATS + lane, (unsigned long long)v);
+  }
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
@@ -1156,6 +1179,18 @@ __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
   }
 }
 
+// statistics: fold the replicated accumulators into the caller's vector and clear them
+__global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
+  const int k = threadIdx.x;
+  if (k >= SY_NUM_STATS) return;
+  unsigned long long sum = 0;
+  for (int r = 0; r < STAT_REPLICAS; ++r) {
+    sum += rep[r * SY_NUM_STATS + k];
+    rep[r * SY_NUM_STATS + k] = 0;
+  }
+  out[k] += (long long)sum;
+}
+
 // ---------------------------------------------------------------------------------------------
 // random valid policy: thread per (env, agent)
 // ---------------------------------------------------------------------------------------------
@@ -1283,6 +1318,7 @@ struct SyEnv {
   void* d_pack = nullptr;
   void* d_pack_ptr = nullptr;
   void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
+  void* d_stats_rep = nullptr;  // [STAT_REPLICAS, SY_NUM_STATS] u64
   void* d_exp = nullptr;
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
@@ -1336,6 +1372,7 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
     p.dbg_skip = dbg;
   }
   p.bel_flags = (uint8_t*)env->d_bel_flags;
+  p.stats_rep = (unsigned long long*)env->d_stats_rep;
   p.bel_fast = env->bel_fast;
   p.bel_off_out = env->bel_off_out;
   p.bel_off_part = env->bel_off_part;
@@ -1397,9 +1434,11 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
   SyEnv* e = new SyEnv();
   e->cfg = *c;
   e->A = c->num_police + 1;
-  if (cudaMalloc(&e->d_bel_flags, (size_t)c->num_envs) != cudaSuccess) {
-    delete e;
-    return fail(SY_ERR_CUDA, "cudaMalloc of the per-env flag buffer failed");
+  if (cudaMalloc(&e->d_bel_flags, (size_t)c->num_envs) != cudaSuccess ||
+      cudaMalloc(&e->d_stats_rep, (size_t)STAT_REPLICAS * SY_NUM_STATS * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(e->d_stats_rep, 0, (size_t)STAT_REPLICAS * SY_NUM_STATS * sizeof(unsigned long long)) != cudaSuccess) {
+    sy_destroy(e);
+    return fail(SY_ERR_CUDA, "cudaMalloc of the per-env flag / statistics buffers failed");
   }
   *out_env = e;
   return SY_OK;
@@ -1412,6 +1451,7 @@ void sy_destroy(SyEnv* e) {
   if (e->d_exp) cudaFree(e->d_exp);
   if (e->d_cov) cudaFree(e->d_cov);
   if (e->d_bel_flags) cudaFree(e->d_bel_flags);
+  if (e->d_stats_rep) cudaFree(e->d_stats_rep);
   delete e;
 }
 
@@ -1649,7 +1689,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
 int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaStream_t s) {
   const size_t n = (size_t)e->cfg.num_envs * e->A;
   struct Seg { char* dst; const char* src; size_t bytes; };
-  Seg segs[5];
+  Seg segs[5] = {};
   int m = 0;
   auto add = [&](void* dst, const void* src, size_t bytes) {
     if (!dst) return;
@@ -1723,6 +1763,15 @@ int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_
 
 int sy_sample_actions_i32(SyEnv* e, const SyState* st, uint32_t step_counter, int32_t* actions, sy_stream_t stream) {
   return sample_impl<int>(e, st, step_counter, actions, stream);
+}
+
+int sy_stats(SyEnv* e, int64_t* stats, sy_stream_t stream) {
+  if (!e || !stats) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / stats");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  sy_fold_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)e->d_stats_rep, reinterpret_cast<long long*>(stats));
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_OK;
 }
 
 int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,

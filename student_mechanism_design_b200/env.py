@@ -414,6 +414,7 @@ class BatchedScotlandYardEnv:
         all-reduce (NCCL over NVLink on a GPU box)."""
         if self.stats_vec is None:
             raise _cabi.SyError("collect_stats=False")
+        self._fold_stats()
         if reduce_group is not None:
             from .sharding import allreduce_stats
 
@@ -421,13 +422,44 @@ class BatchedScotlandYardEnv:
         h = self.stats_vec.cpu().tolist()
         return {k: int(h[i]) for i, k in enumerate(_cabi.STAT_NAMES)}
 
+    def metrics(self, reduce_group=None) -> Dict[str, float]:
+        """The aggregates of the reference's MetricsTracker.get_aggregated_metrics (src/eval/metrics.py:168-232) from
+        the device statistics vector -- same keys; `mean_belief_ce` / `belief_ce_std` are not tracked on the device."""
+        st = self.stats(reduce_group)
+        n = st["episodes"]
+        if n == 0:  # metrics.py:170-186
+            return dict(num_episodes=0, mrx_wins=0, police_wins=0, win_rate=0.5, win_rate_std=0.0, mean_episode_length=0.0,
+                        episode_length_std=0.0, mean_tolls_paid=0.0, mean_budget_spent=0.0, mean_budget_efficiency=0.0,
+                        mean_time_to_catch=0.0, mean_survival_time=0.0)
+        wr = st["mrx_wins"] / n
+        ml = st["sum_episode_length"] / n
+        var_l = max(st["sum_sq_episode_length"] / n - ml * ml, 0.0)
+        spent = st["sum_episode_budget_spent"] / n
+        initial = max(self.number_of_agents * self.agent_money, 1)
+        return dict(
+            num_episodes=n, mrx_wins=st["mrx_wins"], police_wins=st["police_wins"], win_rate=wr,
+            win_rate_std=float(np.sqrt(wr * (1.0 - wr))), mean_episode_length=ml, episode_length_std=float(np.sqrt(var_l)),
+            mean_tolls_paid=self.tolls * st["police_moves"] / n, mean_budget_spent=spent,
+            mean_budget_efficiency=spent / initial,
+            mean_time_to_catch=st["sum_length_police_wins"] / st["police_wins"] if st["police_wins"] else 0.0,
+            mean_survival_time=st["sum_length_mrx_wins"] / st["mrx_wins"] if st["mrx_wins"] else 0.0,
+        )
+
+    def _fold_stats(self):
+        """sy_stats: add what the kernels accumulated since the last call to `stats_vec`"""
+        if self.stats_vec is not None:
+            with torch.cuda.device(self.device):
+                _cabi.check(self._lib.sy_stats(self._handle, self.stats_vec.data_ptr(), self._stream()))
+
     def reset_stats(self):
         if self.stats_vec is not None:
+            self._fold_stats()
             self.stats_vec.zero_()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         keys = ["pos", "money", "timestep", "graph_id", "episode", "done", "visits", "belief_map", "action_mask",
                 "node_features", "agent_budget", "mrx_revealed", "stats_vec"]
+        self._fold_stats()
         return {k: getattr(self, k).clone() for k in keys if getattr(self, k) is not None}
 
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):

@@ -229,6 +229,23 @@ def test_random_policy_rollout_matches_oracle(torch_cuda, tables, ci):
     assert st["env_steps"] == c["B"] * c["steps"] and st["episodes"] == n_done
     assert st["mrx_wins"] + st["police_wins"] == n_done
     assert n_done > 0
+    # the aggregates of the reference's MetricsTracker (src/eval/metrics.py:168-232) from the device statistics
+    fin = np.asarray(ob.finished, dtype=np.int64)  # (length, winner, budget spent) per finished episode
+    lengths, winners, spent = fin[:, 0], fin[:, 1], fin[:, 2]
+    moves = sum(e.moves for e in ob.envs)
+    m = env.metrics()
+    assert m["num_episodes"] == len(fin) and m["mrx_wins"] == int((winners == so.WINNER_MRX).sum())
+    assert m["police_wins"] == int((winners == so.WINNER_POLICE).sum()) and st["police_moves"] == moves
+    np.testing.assert_allclose(m["win_rate"], np.mean(winners == so.WINNER_MRX), rtol=1e-12)
+    np.testing.assert_allclose(m["win_rate_std"], np.std((winners == so.WINNER_MRX).astype(float)), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(m["mean_episode_length"], lengths.mean(), rtol=1e-12)
+    np.testing.assert_allclose(m["episode_length_std"], lengths.std(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(m["mean_budget_spent"], spent.mean(), rtol=1e-12)
+    np.testing.assert_allclose(m["mean_budget_efficiency"], spent.mean() / max(c["P"] * c["money"], 1), rtol=1e-12)
+    np.testing.assert_allclose(m["mean_tolls_paid"], c["kw"].get("tolls", 0) * moves / len(fin), rtol=1e-12)
+    pol, mrx = lengths[winners == so.WINNER_POLICE], lengths[winners == so.WINNER_MRX]
+    np.testing.assert_allclose(m["mean_time_to_catch"], pol.mean() if len(pol) else 0.0, rtol=1e-12)
+    np.testing.assert_allclose(m["mean_survival_time"], mrx.mean() if len(mrx) else 0.0, rtol=1e-12)
     env.close()
 
 
@@ -573,6 +590,8 @@ def test_rollout_random_and_cuda_graph_replay(torch_cuda, tables):
         graph.replay()
         ref.rollout_random(4, step_counter=1)
     torch.cuda.synchronize()
+    for e in (a, b, g, ref):
+        e.stats()  # folds the library's accumulators into stats_vec
     for k in ("pos", "money", "timestep", "episode", "visits", "belief_map", "reward64", "terminated", "action_mask",
               "node_features", "stats_vec"):
         assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), k
