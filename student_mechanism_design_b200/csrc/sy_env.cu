@@ -441,12 +441,10 @@ struct LogicSmem {
   static constexpr int DS = MAXA * MAXA + 2;  // row stride (halfwords) of the pair-distance matrices: odd word count
   static constexpr int NPAIR = MAXA * (MAXA - 1) / 2;
   u16 pos[32 * HS];        // agents' nodes (post-move after P1, next-episode nodes after a same-step auto-reset)
-  u16 scratch[32 * HS];    // Philox scratch
   u16 reset_pos[32 * HS];  // start nodes of the next episode, drawn speculatively
-  u16 vis[32 * HS];        // visit counter at every police's node (before this step's increment)
-  u16 dmat[32 * DS];       // all-pairs distances between the env's agents
+  u16 dmat[32 * DS];       // all-pairs distances between the env's agents (P2); Philox scratch of warp 1 during P1
   u16 pair_ij[NPAIR];      // pair index -> (i << 8) | j, i < j
-  int act[32 * AS];        // normalised actions
+  int act[32 * AS];        // normalised actions (P0-P1); then visit counters at the police nodes (P2, as u16 rows)
   int money[32 * AS];
   RewardTables rt;
   uint8_t cnt[CNT_SMEM];   // move-count table of the tile's graph (when it fits and the tile sits on one graph)
@@ -535,7 +533,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
     const unsigned ep = (unsigned)(sm.episode[lane] + 1);
     sm.reset_gid[lane] = p.resample_graph ? philox_graph_choice(p, env_id, ep) : g;
-    philox_start_positions(p, env_id, ep, sm.reset_pos + lane * HS, sm.scratch + lane * HS);
+    philox_start_positions(p, env_id, ep, sm.reset_pos + lane * HS, sm.dmat + lane * HS);
   }
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(1);
@@ -579,7 +577,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
 #pragma unroll
     for (int k = 0; k < NVQ; ++k) {
       const int i = 1 + warp + k * LOGIC_WARPS;
-      if (active && i <= P) sm.vis[lane * HS + i] = (u16)vq[k];
+      if (active && i <= P) reinterpret_cast<u16*>(sm.act)[lane * HS + i] = (u16)vq[k];
     }
   }
   if (warp == 0) PHASE_MARK(1);
@@ -595,7 +593,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
         int visits_here = 0;
         const int u = pos[a];
         if (a > 0) {  // police never share a node (yard.py:231): the P counters of an env are distinct addresses
-          visits_here = (int)sm.vis[lane * HS + a] + 1;
+          visits_here = (int)reinterpret_cast<const u16*>(sm.act)[lane * HS + a] + 1;
           p.st.visits[(size_t)b * N + u] = (uint16_t)min(visits_here, 0xFFFF);
         }
         RewardInputs<MAXA> in;
