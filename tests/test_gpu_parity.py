@@ -693,3 +693,43 @@ def test_crowded_and_broke_edge_cases(torch_cuda, tables):
         if money == 0 or kw.get("tolls", 0) > money:
             assert st["out_of_money"] == st["episodes"] == 64 * 25  # every step ends an episode
         env.close()
+
+
+def test_rollout_collector_with_a_policy(torch_cuda, tables):
+    """the batched rollout loop with a policy in it (a hand-written `chase MrX` heuristic over the
+    batched observation: logits = -distance to the last known MrX node) -- actions are legal or DEFAULT_ACTION, the
+    stored trajectory is consistent with the env, and the heuristic police catch MrX more often than random play."""
+    torch = torch_cuda
+    pkg = _pkg()
+    N, P, B, T = 40, 4, 512, 60
+    pool = pkg.generate_graph_pool(1, N, 75, seed=8)
+    mk = lambda: pkg.BatchedScotlandYardEnv(B, P, 30, graphs=pool, seed=2, auto_reset=True, reward_tables=tables)  # noqa: E731
+    env = mk()
+    env.reset()
+    D = torch.from_numpy(env.graph_tables(0)[1].astype(np.int64)).cuda().float()  # [N, N]
+    gd = pkg.batched_graph_data(env)
+    assert gd["x"].data_ptr() == env.node_features.data_ptr() and gd["edge_index"].shape == (1, 2, len(pool[0].edges))
+
+    def chase(obs):
+        mrx = obs["MrX_pos"].long()  # [B]
+        to_mrx = -D[mrx]  # [B, N]: police prefer nodes close to MrX
+        away = D[obs["Polices_pos"].long()].min(dim=1).values  # [B, N]: MrX prefers nodes far from the nearest police
+        return torch.cat([away.unsqueeze(1), to_mrx.unsqueeze(1).expand(-1, P, -1)], dim=1)
+
+    col = pkg.RolloutCollector(env, chase, T, greedy=True)
+    traj = col.collect()
+    acts, pos0, money0 = traj["actions"], traj["pos"], traj["money"]
+    W = torch.from_numpy(env.graph_tables(0)[0].astype(np.int64)).cuda()
+    w = W[pos0.long(), acts.clamp_min(0)]  # weight of the chosen edge
+    legal = (w > 0) & (w <= money0)
+    assert bool((legal | (acts == -1)).all()), "the collector produced an illegal action"
+    assert traj["reward"].shape == (T, B, P + 1) and bool(torch.isfinite(traj["reward"]).all())
+    chase_stats = env.metrics()
+    rnd = mk()
+    rnd.reset()
+    rnd.rollout_random(T)
+    rnd_stats = rnd.metrics()
+    assert chase_stats["num_episodes"] > 0 and rnd_stats["num_episodes"] > 0
+    assert chase_stats["police_wins"] / chase_stats["num_episodes"] > rnd_stats["police_wins"] / rnd_stats["num_episodes"]
+    env.close()
+    rnd.close()

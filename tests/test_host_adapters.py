@@ -179,3 +179,29 @@ def test_oracle_shards_reproduce_the_global_batch():
         for k in ("pos", "money", "timestep", "visits", "belief", "revealed"):
             got = np.concatenate([getattr(sh, k)() for sh in shards])
             assert np.array_equal(got, getattr(full, k)()), (k, s)
+
+
+def test_masked_sample_respects_mask_and_default_action():
+    from student_mechanism_design_b200 import masked_sample
+
+    g = torch.Generator().manual_seed(0)
+    B, A, N = 64, 3, 11
+    mask = torch.rand(B, A, N, generator=g) < 0.3
+    mask[0, 1] = False  # an agent without legal moves
+    logits = torch.randn(B, A, N, generator=g)
+    for greedy in (False, True):
+        a = masked_sample(logits, mask, generator=g, greedy=greedy)
+        assert a.shape == (B, A) and a.dtype == torch.int64 and a[0, 1] == -1
+        ok = mask.any(-1)
+        assert bool((a[~ok] == -1).all()) and bool(mask.gather(-1, a.clamp_min(0).unsqueeze(-1)).squeeze(-1)[ok].all())
+    # greedy picks the best legal logit
+    best = torch.where(mask, logits, torch.full_like(logits, -1e30)).argmax(-1)
+    assert torch.equal(masked_sample(logits, mask, greedy=True)[mask.any(-1)], best[mask.any(-1)])
+    # sampling frequencies follow softmax over the legal nodes
+    m1 = torch.zeros(1, 1, 4, dtype=torch.bool)
+    m1[..., :3] = True
+    lg = torch.tensor([[[0.0, 1.0, 2.0, 9.0]]])
+    draws = torch.stack([masked_sample(lg.expand(4096, 1, 4), m1.expand(4096, 1, 4), generator=g) for _ in range(4)]).flatten()
+    freq = torch.bincount(draws, minlength=4).float() / draws.numel()
+    want = torch.softmax(lg[0, 0, :3], -1)
+    assert freq[3] == 0 and torch.allclose(freq[:3], want, atol=0.02)
