@@ -447,7 +447,7 @@ struct LogicSmem {
   int act[32 * AS];        // normalised actions (P0-P1); then visit counters at the police nodes (P2, as u16 rows)
   int money[32 * AS];
   RewardTables rt;
-  uint8_t cnt[CNT_SMEM];   // move-count table of the tile's graph (when it fits and the tile sits on one graph)
+  alignas(16) uint8_t cnt[CNT_SMEM];   // move-count table of the tile's graph (when it fits and the tile sits on one graph)
   int reset_gid[32];
   int t[32], gid[32], episode[32], frozen[32], status[32];
   int t_new[32], done[32], bel[32], revealed[32], clear[32];
@@ -507,8 +507,15 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     const int bytes = N * (p.tb.wcap + 1);
     const bool ok = bytes <= CNT_SMEM && __all_sync(FULL, gl == g_first);
     if (tid == 0) sm.cnt_staged = ok;
-    if (ok)
-      for (int i = tid; i < bytes; i += LOGIC_THREADS) sm.cnt[i] = __ldg(p.tb.cnt + (size_t)g_first * bytes + i);
+    if (ok) {
+      const uint8_t* src = p.tb.cnt + (size_t)g_first * bytes;
+      if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {  // 16-byte copies; the tail past `bytes` is never read
+        for (int i = tid * 16; i < bytes; i += LOGIC_THREADS * 16)
+          *reinterpret_cast<uint4*>(sm.cnt + i) = __ldg(reinterpret_cast<const uint4*>(src + i));
+      } else {
+        for (int i = tid; i < bytes; i += LOGIC_THREADS) sm.cnt[i] = __ldg(src + i);
+      }
+    }
   }
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(0);
@@ -1524,7 +1531,7 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   CUDA_TRY(cudaMalloc(&e->d_row_ptr, (size_t)G * (N + 1) * sizeof(int32_t)));
   CUDA_TRY(cudaMalloc(&e->d_col, (size_t)G * nnz_stride * sizeof(uint16_t)));
   CUDA_TRY(cudaMalloc(&e->d_wgt, (size_t)G * nnz_stride));
-  CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1)));
+  CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1) + 16));  // + 16: vector loads of the last row's tail
   CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_pack, pack.size() * sizeof(int2)));
   CUDA_TRY(cudaMemcpyAsync(e->d_pack, pack.data(), pack.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
