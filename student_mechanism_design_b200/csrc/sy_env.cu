@@ -1668,6 +1668,10 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   // persistent observe grid (the block scheduler drains the older grid first: no overlap), and one persistent kernel
   // whose logic warps run one tile ahead of the observe warps (the logic's loads and shared-memory accesses queue
   // behind the writers' store stream in the SM's in-order LSU: the times added up, 159 vs 136 us).
+  // A persistent single-launch kernel that dedicates every k-th SM to the logic (SM roles elected at run time, tiles
+  // handed over through epoch flags) was correct but slower for every k (159 us at k = 4, 241 us at k = 8): both kernels
+  // are bound by SM issue/latency throughput as much as by HBM, so taking SMs away from either one loses more than the
+  // overlap gains.
   // Also measured: an L2 persisting access-policy window on the belief map (52 MB at c3) slowed the step to 166-255 us
   // (the carve-out starves the write stream of L2), so no residency hints are set.
   if (p.dbg_skip & 32) {
