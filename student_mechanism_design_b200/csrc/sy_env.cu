@@ -117,7 +117,7 @@ struct Params {
   const long long* actions;  // int64 [B, A] ...
   const int* actions32;      // ... or int32 [B, A] (narrow wire format of the host-buffer path), exactly one is set
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
-  int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr, wr_nf_fast;  // writer warps: smem staging layout (bytes) and path flags
+  int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr;  // writer warps: smem staging layout (bytes) and path flag
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
@@ -841,23 +841,14 @@ __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src
 }
 
 // node_features of one env: n = N*A floats, all zero except the agents' one-hot entries at flat index fpos[a]
-// (yard.py:279-290).  Every 16-byte chunk is written exactly once: lane a assembles and stores the chunk that holds
-// agent a's one (a per-lane bitmask, filled through shared memory, tells the zero-fill loop to skip those chunks).
+// (yard.py:279-290).  The region is zero-filled with 16-byte stores; lane a then overwrites, with one full 16-byte
+// store, the chunk that holds agent a's one (assembled in registers from all agents that fall into it).  Measured:
+// rewriting a handful of whole chunks costs nothing, whereas byte-sized ones after the fill cost 60 %.
 __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const int* fpos /*smem, A entries, -1 = none*/,
-                                                          unsigned long long* bits /*smem, 32 words, all zero*/, int A, int lane) {
+                                                          int A, int lane) {
   const int head = min(n, (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(nf) & 15u)) & 15u) >> 2));
   const int nvec = (n - head) >> 2;
   const int tail0 = head + (nvec << 2);
-  int myc = -1;  // body chunk that holds this lane's agent
-  if (lane < A) {
-    const int f = fpos[lane] - head;
-    if (fpos[lane] >= 0 && f >= 0 && f < (nvec << 2)) {
-      myc = f >> 2;
-      atomicOr(bits + (myc & 31), 1ull << (myc >> 5));
-    }
-  }
-  __syncwarp();
-  const unsigned long long mine = bits[lane];  // bit t: chunk t * 32 + lane holds a one
   if (lane < head || (lane >= 32 - (n - tail0))) {  // the few floats before / after the aligned body
     const int f = lane < head ? lane : tail0 + (lane - (32 - (n - tail0)));
     float v = 0.0f;
@@ -866,34 +857,35 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
   }
   uint4* body = reinterpret_cast<uint4*>(nf + head);
   const uint4 z = make_uint4(0, 0, 0, 0);
-  unsigned long long m = mine;
 #pragma unroll 4
-  for (int i = lane; i < nvec; i += 32, m >>= 1)
-    if (!(m & 1ull)) store_obs16(body + i, z);
-  __syncwarp();
-  if (mine) bits[lane] = 0ull;
-  if (myc >= 0) {
-    uint4 v = z;
-    for (int a = 0; a < A; ++a) {
-      const int f = fpos[a] - head;
-      if (fpos[a] >= 0 && (f >> 2) == myc) {
-        const unsigned one = 0x3f800000u;
-        const int sub = f & 3;
-        v.x = sub == 0 ? one : v.x;
-        v.y = sub == 1 ? one : v.y;
-        v.z = sub == 2 ? one : v.z;
-        v.w = sub == 3 ? one : v.w;
+  for (int i = lane; i < nvec; i += 32) store_obs16(body + i, z);
+  __syncwarp();  // orders the zero stores before the chunks below (same warp, same addresses)
+  if (lane < A) {
+    const int f0 = fpos[lane] - head;
+    if (fpos[lane] >= 0 && f0 >= 0 && f0 < (nvec << 2)) {
+      const int myc = f0 >> 2;  // body chunk that holds this lane's agent
+      uint4 v = z;
+      for (int a = 0; a < A; ++a) {
+        const int f = fpos[a] - head;
+        if (fpos[a] >= 0 && (f >> 2) == myc) {
+          const unsigned one = 0x3f800000u;
+          const int sub = f & 3;
+          v.x = sub == 0 ? one : v.x;
+          v.y = sub == 1 ? one : v.y;
+          v.z = sub == 2 ? one : v.z;
+          v.w = sub == 3 ? one : v.w;
+        }
       }
+      store_obs16(body + myc, v);
     }
-    store_obs16(body + myc, v);
   }
 }
 
 // writer warps: stream the dense observations of the tile.  Everything the ones depend on is staged into shared
 // memory first (one round trip for the whole tile): agents' nodes and budgets, reveal flags and -- when the tile sits
 // on one graph and its CSR fits -- the graph's row pointers / neighbours / weights.  Each env's action_mask rows are
-// assembled in a per-warp shared-memory image and copied out, node_features are assembled in registers: every byte of
-// the observations is stored exactly once (measured: byte-sized ones stored after a zero-fill cost 60% extra time).
+// assembled in a per-warp shared-memory image and copied out, node_features are zero-filled and the (at most A) chunks
+// with a one rewritten whole: no byte-sized stores anywhere (they cost 60 % extra time when tried).
 __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
   const Tables& tb = p.tb;
   const int N = p.N, A = p.A;
@@ -902,8 +894,7 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   int* s_rev = s_money + TILE * A;                      // [TILE]
   int* s_gid = s_rev + TILE;                            // [TILE]
   int* s_fpos = s_gid + TILE;                           // [WR_WARPS * SY_MAX_AGENTS] flat node_features index per agent
-  unsigned long long* bits = reinterpret_cast<unsigned long long*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + w * 32;  // [WR_WARPS * 32]
-  uint8_t* s_img = reinterpret_cast<uint8_t*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + WR_WARPS * 32 * 8 + (size_t)w * p.wr_img_stride;  // mask image
+  uint8_t* s_img = reinterpret_cast<uint8_t*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + (size_t)w * p.wr_img_stride;  // mask image
   int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);  // [N + 1]
   uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
   uint8_t* s_wgt = reinterpret_cast<uint8_t*>(s_col + tb.nnz_stride);
@@ -929,7 +920,6 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
     }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
-  bits[lane] = 0ull;
   named_barrier(2, WR_WARPS * 32);
   int* fpos = s_fpos + w * SY_MAX_AGENTS;
   const int lpa = 32 / A;
@@ -961,13 +951,7 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
     }
     __syncwarp();
     warp_copy_bytes(mask, img, A * N, lane);
-    if (p.wr_nf_fast)
-      warp_write_node_features(nf, N * A, fpos, bits, A, lane);
-    else {  // very large N * A: zero-fill, then the ones (same warp, ordered by the __syncwarp)
-      warp_zero_bytes(reinterpret_cast<uint8_t*>(nf), N * A * (int)sizeof(float), lane);
-      __syncwarp();
-      if (lane < A && fpos[lane] >= 0) nf[fpos[lane]] = 1.0f;
-    }
+    warp_write_node_features(nf, N * A, fpos, A, lane);
     __syncwarp();
     for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
     __syncwarp();
@@ -1328,7 +1312,7 @@ struct SyEnv {
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
-  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, wr_nf_fast = 0;
+  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0;
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
 
@@ -1387,7 +1371,6 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.wr_off_csr = env->wr_off_csr;
   p.wr_img_stride = env->wr_img_stride;
   p.wr_stage_csr = env->wr_stage_csr;
-  p.wr_nf_fast = env->wr_nf_fast;
   p.st = *st;
   if (ob) p.ob = *ob;
   if (out) p.out = *out;
@@ -1592,13 +1575,12 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   {  // writer staging area: pos, money [TILE, A], revealed, graph id [TILE], per-warp flat one-hot indices and
      // action_mask images, then (optionally) the graph's CSR
     const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
-    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + WR_WARPS * SY_MAX_AGENTS) * sizeof(int) + WR_WARPS * 32 * 8 + WR_WARPS * img_stride;
+    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + WR_WARPS * SY_MAX_AGENTS) * sizeof(int) + WR_WARPS * img_stride;
     const size_t csr = (size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3 + 16;
     e->wr_off = (int)((e->bel_smem + 15) & ~(size_t)15);
     e->wr_img_stride = (int)img_stride;
     e->wr_off_csr = (int)(((size_t)e->wr_off + base + 15) & ~(size_t)15);
     e->wr_stage_csr = (csr <= 32 * 1024 && (size_t)e->wr_off_csr + csr <= 200 * 1024) ? 1 : 0;
-    e->wr_nf_fast = ((size_t)N * e->A <= 8000) ? 1 : 0;  // chunk bitmask of warp_write_node_features is 64 bits
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
     CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
