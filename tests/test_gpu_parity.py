@@ -733,3 +733,29 @@ def test_rollout_collector_with_a_policy(torch_cuda, tables):
     assert chase_stats["police_wins"] / chase_stats["num_episodes"] > rnd_stats["police_wins"] / rnd_stats["num_episodes"]
     env.close()
     rnd.close()
+
+
+def test_million_envs_config5_scale(torch_cuda):
+    """BASELINE config 5's batch (1 048 576 envs of the 200-node / 6-police config) on one GPU: index arithmetic beyond
+    2^31 bytes per tensor, statistics add up, observations stay consistent with the state."""
+    torch = torch_cuda
+    pkg = _pkg()
+    N, P, B = 200, 6, 1 << 20
+    env = pkg.BatchedScotlandYardEnv(B, P, 20, graph_nodes=N, graph_edges=400, seed=4, auto_reset=True, tolls=1, belief=True,
+                                     reveal_interval=5)
+    env.reset()
+    assert env.node_features.numel() * 4 > 2**31  # 5.9 GB tensor
+    env.rollout_random(6)
+    st = env.stats()
+    assert st["env_steps"] == 6 * B and st["episodes"] == int(env.episode.sum())
+    # the last tile is as healthy as the first: one-hot features, masks consistent with budgets, belief rows sum to 1
+    W = torch.from_numpy(env.graph_tables(0)[0].astype(np.int32)).cuda()
+    for sl in (slice(0, 4096), slice(B - 4096, B)):
+        pos, money = env.pos[sl].long(), env.money[sl]
+        rows = W[pos]
+        assert bool((((rows > 0) & (rows + 1 <= money.unsqueeze(-1))) == env.action_mask[sl]).all())
+        nf = env.node_features[sl]
+        assert bool((nf.sum(dim=1)[:, 1:] == 1).all()) and bool((nf[:, :, 1:].gather(1, pos[:, None, 1:]) == 1).all())
+        assert float((env.belief_map[sl].sum(dim=1) - 1).abs().max()) < 1e-5
+    assert float(env.node_features.sum()) == float((P + (env.mrx_revealed >= 0).float()).sum())
+    env.close()
