@@ -1308,6 +1308,8 @@ struct SyEnv {
   void* d_pack_ptr = nullptr;
   void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
   void* d_stats_rep = nullptr;  // [STAT_REPLICAS, SY_NUM_STATS] u64
+  cudaStream_t aux_stream = nullptr;  // host-buffer path: result copies overlap the observe kernel
+  cudaEvent_t ev_logic = nullptr, ev_copied = nullptr;
   void* d_exp = nullptr;
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
@@ -1428,6 +1430,12 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
     sy_destroy(e);
     return fail(SY_ERR_CUDA, "cudaMalloc of the per-env flag / statistics buffers failed");
   }
+  if (cudaStreamCreateWithFlags(&e->aux_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_logic, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_copied, cudaEventDisableTiming) != cudaSuccess) {
+    sy_destroy(e);
+    return fail(SY_ERR_CUDA, "stream / event creation failed");
+  }
   *out_env = e;
   return SY_OK;
 }
@@ -1440,6 +1448,9 @@ void sy_destroy(SyEnv* e) {
   if (e->d_cov) cudaFree(e->d_cov);
   if (e->d_bel_flags) cudaFree(e->d_bel_flags);
   if (e->d_stats_rep) cudaFree(e->d_stats_rep);
+  if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->ev_logic) cudaEventDestroy(e->ev_logic);
+  if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   delete e;
 }
 
@@ -1631,8 +1642,9 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
 }  // extern "C"
 
 namespace {
+// after_logic (optional): recorded between the two kernels -- rewards / flags are final once the logic kernel is done
 int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
-              sy_stream_t stream) {
+              sy_stream_t stream, cudaEvent_t after_logic = nullptr) {
   if (!e || (!actions && !actions32)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   if (!out || !out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
@@ -1669,14 +1681,17 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
   if (!(p.dbg_skip & 16)) sy_observe_kernel<<<grid, THREADS, e->obs_smem, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
 }
 
-// D2H of the step results.  Members that are adjacent in both device and host memory (the host mirror allocates each
-// side as one block) are merged into a single copy: one PCIe transaction instead of five.
+// D2H of the step results, overlapped with the observe kernel: the rewards / flags are final after the logic kernel, so
+// they are copied on the handle's auxiliary stream while the (much longer) observation stream still runs on the
+// caller's stream; both are joined before returning.  Members that are adjacent in both device and host memory (the
+// host mirror allocates each side as one block) are merged into a single copy.
 int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaStream_t s) {
   const size_t n = (size_t)e->cfg.num_envs * e->A;
   struct Seg { char* dst; const char* src; size_t bytes; };
@@ -1694,7 +1709,10 @@ int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaS
   add(ho->truncated, out->truncated, n);
   add(ho->done, out->done, n);
   add(ho->winner, out->winner, (size_t)e->cfg.num_envs);
-  for (int i = 0; i < m; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_logic, 0));
+  for (int i = 0; i < m; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDeviceToHost, e->aux_stream));
+  CUDA_TRY(cudaEventRecord(e->ev_copied, e->aux_stream));
+  CUDA_TRY(cudaStreamWaitEvent(s, e->ev_copied, 0));  // later work on the caller's stream is ordered after the copy
   CUDA_TRY(cudaStreamSynchronize(s));
   return SY_OK;
 }
@@ -1731,7 +1749,7 @@ int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, co
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)e->cfg.num_envs * e->A;
   CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-  const int rc = step_impl(e, actions_dev, nullptr, st, ob, out, stream);
+  const int rc = step_impl(e, actions_dev, nullptr, st, ob, out, stream, e->ev_logic);
   if (rc) return rc;
   return copy_results_and_sync(e, out, ho, s);
 }
@@ -1743,7 +1761,7 @@ int sy_step_host_i32(SyEnv* e, const int32_t* actions_host, int32_t* actions_dev
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)e->cfg.num_envs * e->A;
   CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  const int rc = step_impl(e, nullptr, actions_dev, st, ob, out, stream);
+  const int rc = step_impl(e, nullptr, actions_dev, st, ob, out, stream, e->ev_logic);
   if (rc) return rc;
   return copy_results_and_sync(e, out, ho, s);
 }
