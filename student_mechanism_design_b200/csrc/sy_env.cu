@@ -989,10 +989,10 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
       const float inv = 1.0f / tot;
-      constexpr int U = 4;  // nodes per lane in flight: their list bounds, then their first blocks, are loaded together
+      constexpr int U = 2;  // nodes per lane in flight: their list bounds, then their first TWO blocks, are loaded together
       _Pragma("unroll 1") for (int j0 = lane; j0 < N; j0 += 32 * U) {
         int qa[U], qb[U];
-        int4 e0[U], e1[U];
+        int4 e[U][4];
         float acc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1005,25 +1005,27 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          e0[u] = e1[u] = make_int4(0, 0, 0, 0);
-          if (qa[u] < qb[u]) {  // lists are padded to multiples of 4 with {0, 0.0f}
-            e0[u] = __ldg(reinterpret_cast<const int4*>(gpack + qa[u]));
-            e1[u] = __ldg(reinterpret_cast<const int4*>(gpack + qa[u] + 2));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // lists are padded to multiples of 4 entries ({0, 0.0f}); 2 entries per int4
+            e[u][k] = make_int4(0, 0, 0, 0);
+            if (qa[u] + 2 * k < qb[u]) e[u][k] = __ldg(reinterpret_cast<const int4*>(gpack + qa[u] + 2 * k));
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           // entries hold the byte offset of the neighbour's row in the fast path's transposed tile: node * BSTRIDE * 4
-          float a = sb[(unsigned)e0[u].x / (BSTRIDE * 4u)] * __int_as_float(e0[u].y);
-          a = fmaf(sb[(unsigned)e0[u].z / (BSTRIDE * 4u)], __int_as_float(e0[u].w), a);
-          a = fmaf(sb[(unsigned)e1[u].x / (BSTRIDE * 4u)], __int_as_float(e1[u].y), a);
-          a = fmaf(sb[(unsigned)e1[u].z / (BSTRIDE * 4u)], __int_as_float(e1[u].w), a);
+          float a = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            a = fmaf(sb[(unsigned)e[u][k].x / (BSTRIDE * 4u)], __int_as_float(e[u][k].y), a);
+            a = fmaf(sb[(unsigned)e[u][k].z / (BSTRIDE * 4u)], __int_as_float(e[u][k].w), a);
+          }
           acc[u] = a;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int j = j0 + 32 * u;
-          _Pragma("unroll 1") for (int q = qa[u] + 4; q < qb[u]; q += 4) {  // nodes with more than 4 neighbours
+          _Pragma("unroll 1") for (int q = qa[u] + 8; q < qb[u]; q += 4) {  // nodes with more than 8 neighbours
             const int4 f0 = __ldg(reinterpret_cast<const int4*>(gpack + q)), f1 = __ldg(reinterpret_cast<const int4*>(gpack + q + 2));
             acc[u] = fmaf(sb[(unsigned)f0.x / (BSTRIDE * 4u)], __int_as_float(f0.y), acc[u]);
             acc[u] = fmaf(sb[(unsigned)f0.z / (BSTRIDE * 4u)], __int_as_float(f0.w), acc[u]);
