@@ -62,8 +62,17 @@ enum {
   SY_STAT_SUM_LENGTH_POLICE_WINS = 9, /* -> mean_time_to_catch */
   SY_STAT_SUM_LENGTH_MRX_WINS = 10,   /* -> mean_survival_time */
   SY_STAT_SUM_EPISODE_BUDGET_SPENT = 11, /* budget spent inside FINISHED episodes -> mean_budget_spent / efficiency */
-  SY_STAT_POLICE_MOVES = 12              /* over all steps; x toll = tolls paid */
+  SY_STAT_POLICE_MOVES = 12,             /* over all steps; x toll = tolls paid */
+  /* belief quality at reveal steps (src/eval/belief_quality.py:8-11 via metrics.py:127-147): cross-entropy of the
+   * predicted belief at MrX's true node, scored before the reveal collapses the map; Q24 fixed point (value * 2^24,
+   * integer sums are order-independent).  Counted while config.belief == SY_BELIEF_SCORED and statistics are on
+   * (scoring costs the observe kernel ~4 us per step at 65 536 envs, hence opt-in). */
+  SY_STAT_REVEALS = 13,
+  SY_STAT_SUM_BELIEF_CE_Q24 = 14,   /* -> mean_belief_ce */
+  SY_STAT_SUM_SQ_BELIEF_CE_Q24 = 15 /* -> belief_ce_std */
 };
+
+#define SY_BELIEF_SCORED 2
 
 typedef void* sy_stream_t;
 typedef struct SyEnv SyEnv;
@@ -81,7 +90,7 @@ typedef struct SyConfig {
   int32_t max_timestep;    /* 250, reward_calculator.py:68 */
   int32_t reveal_interval; /* 0 = MrX always visible (reference behaviour) */
   int32_t toll;            /* 0 = reference behaviour; else legality and police charge use w + toll */
-  int32_t belief;          /* 0/1: maintain belief_map */
+  int32_t belief;          /* 0 off | 1 maintain belief_map | SY_BELIEF_SCORED (2): also score it at reveal steps */
   int32_t reward_mode;     /* SY_REWARD_FP64 (python-float weights) | SY_REWARD_FP32 (0-dim fp32 tensors) */
   int32_t auto_reset;      /* 0/1: same-step auto-reset of finished envs (Philox start nodes) */
   int32_t resample_graph;  /* 0/1: on (auto-)reset draw graph_id uniformly from the pool */

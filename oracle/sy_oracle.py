@@ -281,6 +281,13 @@ def belief_update(belief, graph: Graph, reveal: Optional[int] = None, hint: Opti
     return out / s
 
 
+def belief_cross_entropy(belief, true_index) -> float:
+    """src/eval/belief_quality.py:8-11: clip to [1e-8, 1], renormalise, -log at the true node."""
+    b = np.clip(np.asarray(belief, dtype=np.float64), 1e-8, 1.0)
+    b = b / b.sum()
+    return float(-np.log(b[int(true_index)]))
+
+
 def is_reveal(t, interval) -> bool:
     """src/eval/run_ablations.py:225-229."""
     return bool(interval and interval > 0 and t > 0 and t % interval == 0)
@@ -437,7 +444,10 @@ class OracleEnv:
             self.revealed = pos[0] if rev else -1
         else:
             self.revealed = pos[0]
+        self.last_ce = None
         if self.cfg.belief:
+            if rev:  # score the prediction before the reveal collapses it (metrics.py:142-147)
+                self.last_ce = belief_cross_entropy(belief_update(self.belief, self.graph), pos[0])
             self.belief = belief_update(self.belief, self.graph, reveal=pos[0] if rev else None)
         return rewards, terminated, truncated, winner
 
@@ -600,6 +610,7 @@ class OracleBatch:
         self.episode = [0] * len(self.envs)
         self.done = [False] * len(self.envs)
         self.finished = []
+        self.belief_ces = []  # cross-entropies at reveal steps (not scored when the same step auto-resets the env)
 
     @classmethod
     def from_seed(cls, cfg, graphs, num_envs, seed=0, env_offset=0, auto_reset=True, resample_graph=False):
@@ -629,6 +640,8 @@ class OracleBatch:
             r, te, tr, win = env.step([int(x) for x in actions[b]])
             out["reward"][b] = r
             out["terminated"][b], out["truncated"][b], out["winner"][b] = te, tr, win
+            if env.last_ce is not None and not ((te or tr) and self.auto_reset):
+                self.belief_ces.append(env.last_ce)
             if te or tr:
                 # (episode length, winner, budget spent) of the finished episode: what metrics.py:EpisodeMetrics records
                 self.finished.append((env.t, int(win), self.cfg.num_police * self.cfg.agent_money - sum(env.money[1:])))

@@ -18,7 +18,9 @@ STAT_NAMES = [
     "env_steps", "episodes", "mrx_wins", "police_wins", "truncations", "out_of_money",
     "sum_episode_length", "sum_budget_spent", "sum_sq_episode_length", "sum_length_police_wins",
     "sum_length_mrx_wins", "sum_episode_budget_spent", "police_moves",
+    "reveals", "sum_belief_ce_q24", "sum_sq_belief_ce_q24",
 ]
+BELIEF_CE_SCALE = float(1 << 24)  # fixed-point scale of the two belief cross-entropy sums (include/sy_env.h)
 
 
 class SyConfig(C.Structure):

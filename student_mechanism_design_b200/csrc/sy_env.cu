@@ -105,7 +105,7 @@ struct Tables {
 struct Params {
   int B, N, P, A;
   int inv_A;  // ceil(2^16 / A): (i * inv_A) >> 16 == i / A for i < 2^12
-  int agent_money, mrx_money, max_t, reveal, toll, belief_on, auto_reset, resample_graph, reward_mode;
+  int agent_money, mrx_money, max_t, reveal, toll, belief_on, belief_score, auto_reset, resample_graph, reward_mode;
   unsigned long long env_offset;
   unsigned seed_lo, seed_hi;
   double w64[SY_NUM_REWARD_WEIGHTS];
@@ -963,17 +963,54 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
 // {node, 1/deg} straight from the (L1-resident) pool tables.  The normaliser is the sum of the INPUT row: the
 // propagation conserves mass exactly (sum_j sum_{i in nbr(j)} b_i/deg_i = sum_i b_i on an undirected graph, isolated
 // nodes keep theirs), so it equals the reference's sum of the output up to fp32 rounding and needs no second buffer.
-__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane) {
+// Belief quality at reveal steps (src/eval/belief_quality.py:8-11 as fed by MetricsTracker.record_step,
+// src/eval/metrics.py:127-147): cross-entropy of the PREDICTED belief (the propagated row, before the reveal collapses
+// it) at MrX's true node.  Per-warp accumulator, flushed once per warp into the statistics lines as Q24 fixed point
+// (integer sums: order-independent, so runs and shardings reproduce bit for bit).
+struct CeAcc {
+  int n = 0;
+  long long sum_q = 0, sq_q = 0;
+};
+constexpr float CE_CLIP = 1e-8f;
+constexpr float CE_Q = 16777216.0f;  // 2^24
+
+__device__ __forceinline__ float ce_clip(float v) { return fminf(fmaxf(v, CE_CLIP), 1.0f); }
+
+// lanes hold partial clipped sums `S` and (one lane) the clipped value at the true node `vx`
+__device__ __forceinline__ void ce_record(CeAcc& acc, float S, float vx) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S += __shfl_xor_sync(FULL, S, o);
+    vx = fmaxf(vx, __shfl_xor_sync(FULL, vx, o));
+  }
+  const float ce = logf(S) - logf(vx);  // -log(vx / S); both logs are of normal floats (vx >= 1e-8)
+  acc.n += 1;
+  acc.sum_q += __float2ll_rn(ce * CE_Q);
+  acc.sq_q += __float2ll_rn(ce * ce * CE_Q);
+}
+
+__device__ __forceinline__ void ce_flush(const Params& p, const CeAcc& acc, int lane) {
+  if (acc.n && lane == 0) {
+    unsigned long long* line = p.stats_rep + (size_t)(blockIdx.x % STAT_REPLICAS) * SY_NUM_STATS;
+    atomicAdd(line + SY_STAT_REVEALS, (unsigned long long)acc.n);
+    atomicAdd(line + SY_STAT_SUM_BELIEF_CE_Q24, (unsigned long long)acc.sum_q);
+    atomicAdd(line + SY_STAT_SUM_SQ_BELIEF_CE_Q24, (unsigned long long)acc.sq_q);
+  }
+}
+
+__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane, CeAcc& ce) {
   const int N = p.N;
   const Tables& tb = p.tb;
   float* bel = p.st.belief + (size_t)b * N;
   const float unif = 1.0f / (float)N;
+  const bool score = op == BEL_DELTA && p.belief_score && p.out.stats != nullptr;  // reveal: score the prediction, then collapse it
+  const int x = op == BEL_DELTA ? p.st.pos[(size_t)b * p.A] : -1;
   if (op == BEL_UNIFORM) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
-  } else if (op == BEL_DELTA) {
-    const int x = p.st.pos[(size_t)b * p.A];
+  } else if (op == BEL_DELTA && !score) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
-  } else if (op == BEL_PROPAGATE) {
+  } else if (op == BEL_PROPAGATE || score) {
+    float S = 0.0f, vx = 0.0f;
     const int g = p.st.graph_id[b];
     const int32_t* gptr = tb.pack_ptr + (size_t)g * (N + 1);
     const int2* gpack = tb.nbr_pack + (size_t)g * tb.pack_stride;
@@ -986,7 +1023,12 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
     if (tot == 0.0f) {  // belief_module.py:36-37
-      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+      if (score) {
+        S = lane == 0 ? (float)N * ce_clip(unif) : 0.0f;
+        vx = ce_clip(unif);
+      } else {
+        _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+      }
     } else {
       const float inv = 1.0f / tot;
       constexpr int U = 2;  // nodes per lane in flight: their list bounds, then their first TWO blocks, are loaded together
@@ -1034,10 +1076,21 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
           }
           if (j < N) {
             if (qa[u] == qb[u]) acc[u] = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
-            bel[j] = acc[u] * inv;
+            const float v = acc[u] * inv;
+            if (!score) {
+              bel[j] = v;
+            } else {
+              const float c = ce_clip(v);
+              S += c;
+              if (j == x) vx = c;
+            }
           }
         }
       }
+    }
+    if (score) {
+      ce_record(ce, S, vx);
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
     }
   }
 }
@@ -1050,14 +1103,18 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
     op = p.bel_flags[tile0 + lane];
     g = p.st.graph_id[tile0 + lane];
   }
-  const unsigned prop = __ballot_sync(FULL, op == BEL_PROPAGATE);
+  // rows that go through the propagation: moving envs, plus revealed ones while their prediction is being scored
+  const bool score = p.belief_score && p.out.stats != nullptr;
+  const unsigned prop = __ballot_sync(FULL, op == BEL_PROPAGATE || (score && op == BEL_DELTA));
   const unsigned any = __ballot_sync(FULL, op != BEL_KEEP);
   if (!any) return;
+  CeAcc ce;
   const int g0 = __shfl_sync(FULL, g, prop ? __ffs(prop) - 1 : 0);
-  const bool fast = p.bel_fast && prop && __all_sync(FULL, op != BEL_PROPAGATE || g == g0);
+  const bool fast = p.bel_fast && prop && __all_sync(FULL, !((prop >> lane) & 1u) || g == g0);
   if (!fast) {
     float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * N;
-    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane);
+    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce);
+    ce_flush(p, ce, lane);
     return;
   }
   // fast path: tin[j * BSTRIDE + e] (transposed) so that lane = env: the CSR walk is warp-uniform (no divergence,
@@ -1151,9 +1208,27 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
       const int x = p.st.pos[(size_t)(tile0 + e) * p.A];
+      if (score) {
+        float tot = 0.0f, vx = 0.0f, S = 0.0f;
+#pragma unroll
+        for (int ww = 0; ww < BEL_WARPS; ++ww) tot += part[ww * 32 + e];
+        if (tot == 0.0f) {
+          S = lane == 0 ? (float)N * ce_clip(unif) : 0.0f;
+          vx = ce_clip(unif);
+        } else {
+          const float inv = 1.0f / tot;
+          _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
+            const float c = ce_clip(tout[j * BSTRIDE + e] * inv);
+            S += c;
+            if (j == x) vx = c;
+          }
+        }
+        ce_record(ce, S, vx);
+      }
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
     }
   }
+  ce_flush(p, ce, lane);
 }
 
 __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
@@ -1348,7 +1423,8 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.max_t = c.max_timestep;
   p.reveal = c.reveal_interval;
   p.toll = c.toll;
-  p.belief_on = c.belief;
+  p.belief_on = c.belief != 0;
+  p.belief_score = c.belief == SY_BELIEF_SCORED;
   p.auto_reset = c.auto_reset;
   p.resample_graph = c.resample_graph;
   p.reward_mode = c.reward_mode;

@@ -64,7 +64,7 @@ class BatchedScotlandYardEnv:
     def __init__(self, num_envs: int, number_of_agents: int, agent_money: int, reward_weights: Optional[Dict] = None,
                  logger=None, epoch: int = 0, graph_nodes: int = 50, graph_edges: Optional[int] = 110, vis_configs=None,
                  *, graphs: Optional[Sequence[GraphSpec]] = None, num_graphs: int = 1, reveal_interval: int = 0,
-                 tolls: float = 0, belief: bool = False, reward_mode: Optional[str] = None, seed: int = 0,
+                 tolls: float = 0, belief: bool = False, belief_ce: bool = False, reward_mode: Optional[str] = None, seed: int = 0,
                  auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
                  device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True):
         if not torch.cuda.is_available():
@@ -111,7 +111,9 @@ class BatchedScotlandYardEnv:
         cfg.struct_bytes = C.sizeof(_cabi.SyConfig)
         cfg.device, cfg.num_envs, cfg.num_nodes, cfg.num_police = dev_index, B, N, self.number_of_agents
         cfg.agent_money, cfg.mrx_money, cfg.max_timestep = self.agent_money, MAX_MONEY_LIMIT, int(max_timestep)
-        cfg.reveal_interval, cfg.toll, cfg.belief = int(reveal_interval or 0), int(tolls), int(bool(belief))
+        cfg.reveal_interval, cfg.toll = int(reveal_interval or 0), int(tolls)
+        # belief_ce: also score the predicted belief at reveal steps (stats "reveals" / "sum_belief_ce_q24", metrics())
+        cfg.belief = 2 if (belief and belief_ce) else int(bool(belief))
         cfg.reward_mode = _cabi.SY_REWARD_FP32 if reward_mode == "fp32" else _cabi.SY_REWARD_FP64
         cfg.auto_reset, cfg.resample_graph = int(bool(auto_reset)), int(bool(resample_graph))
         cfg.env_offset, cfg.seed = int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -424,12 +426,18 @@ class BatchedScotlandYardEnv:
 
     def metrics(self, reduce_group=None) -> Dict[str, float]:
         """The aggregates of the reference's MetricsTracker.get_aggregated_metrics (src/eval/metrics.py:168-232) from
-        the device statistics vector -- same keys; `mean_belief_ce` / `belief_ce_std` are not tracked on the device."""
+        the device statistics vector -- same keys.  `mean_belief_ce` / `belief_ce_std` (metrics.py:194-197,217-218):
+        cross-entropy of the predicted belief at MrX's node over all reveal steps (belief_quality.py:8-11), scored
+        inside the observe kernel before the reveal collapses the map."""
         st = self.stats(reduce_group)
         n = st["episodes"]
+        r = st["reveals"]
+        mean_ce = st["sum_belief_ce_q24"] / _cabi.BELIEF_CE_SCALE / r if r else 0.0
+        var_ce = max(st["sum_sq_belief_ce_q24"] / _cabi.BELIEF_CE_SCALE / r - mean_ce * mean_ce, 0.0) if r else 0.0
         if n == 0:  # metrics.py:170-186
             return dict(num_episodes=0, mrx_wins=0, police_wins=0, win_rate=0.5, win_rate_std=0.0, mean_episode_length=0.0,
-                        episode_length_std=0.0, mean_tolls_paid=0.0, mean_budget_spent=0.0, mean_budget_efficiency=0.0,
+                        episode_length_std=0.0, mean_belief_ce=mean_ce, belief_ce_std=float(np.sqrt(var_ce)),
+                        mean_tolls_paid=0.0, mean_budget_spent=0.0, mean_budget_efficiency=0.0,
                         mean_time_to_catch=0.0, mean_survival_time=0.0)
         wr = st["mrx_wins"] / n
         ml = st["sum_episode_length"] / n
@@ -439,6 +447,7 @@ class BatchedScotlandYardEnv:
         return dict(
             num_episodes=n, mrx_wins=st["mrx_wins"], police_wins=st["police_wins"], win_rate=wr,
             win_rate_std=float(np.sqrt(wr * (1.0 - wr))), mean_episode_length=ml, episode_length_std=float(np.sqrt(var_l)),
+            mean_belief_ce=mean_ce, belief_ce_std=float(np.sqrt(var_ce)),
             mean_tolls_paid=self.tolls * st["police_moves"] / n, mean_budget_spent=spent,
             mean_budget_efficiency=spent / initial,
             mean_time_to_catch=st["sum_length_police_wins"] / st["police_wins"] if st["police_wins"] else 0.0,

@@ -162,7 +162,7 @@ def _make_pair(pkg, c, tables, auto_reset=True, seed=17, env_offset=0, max_times
     env = pkg.BatchedScotlandYardEnv(B, c["P"], c["money"], graphs=pool, seed=seed, auto_reset=auto_reset,
                                      reward_mode=c["mode"], keep_reward64=True, reward_tables=tables,
                                      env_offset=env_offset, max_timestep=max_timestep, resample_graph=resample_graph,
-                                     **c["kw"])
+                                     belief_ce=True, **c["kw"])
     ocfg = so.OracleConfig(num_police=c["P"], agent_money=c["money"], reward_mode=c["mode"],
                            reveal_interval=c["kw"].get("reveal_interval", 0), toll=c["kw"].get("tolls", 0),
                            belief=c["kw"].get("belief", False), max_timestep=max_timestep,
@@ -246,6 +246,16 @@ def test_random_policy_rollout_matches_oracle(torch_cuda, tables, ci):
     pol, mrx = lengths[winners == so.WINNER_POLICE], lengths[winners == so.WINNER_MRX]
     np.testing.assert_allclose(m["mean_time_to_catch"], pol.mean() if len(pol) else 0.0, rtol=1e-12)
     np.testing.assert_allclose(m["mean_survival_time"], mrx.mean() if len(mrx) else 0.0, rtol=1e-12)
+    # belief quality at reveal steps (belief_quality.py:8-11): device fp32 prediction vs the float64 oracle
+    ces = np.asarray(ob.belief_ces)
+    assert st["reveals"] == len(ces)
+    if c["kw"].get("belief") and c["kw"].get("reveal_interval", 0) > 0:
+        assert len(ces) > 0
+    if len(ces):
+        np.testing.assert_allclose(m["mean_belief_ce"], ces.mean(), rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(m["belief_ce_std"], ces.std(), rtol=1e-4, atol=1e-5)
+    else:
+        assert m["mean_belief_ce"] == 0.0 and m["belief_ce_std"] == 0.0
     env.close()
 
 
@@ -401,6 +411,7 @@ def test_full_size_properties(torch_cuda):
     st = env.stats()
     assert st["env_steps"] == B * 25
     assert st["episodes"] == int(env.episode.sum()) == st["mrx_wins"] + st["police_wins"]
+    assert st["reveals"] == 0 and env.metrics()["mean_belief_ce"] == 0.0  # belief scoring is opt-in (belief_ce=True)
     env.close()
 
 
