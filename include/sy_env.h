@@ -157,6 +157,23 @@ int sy_set_reward_tables(SyEnv* env, const double* exp_neg, int32_t n_exp, const
  * row_ptr [G, N+1] (offsets local to each graph), col / w [G, nnz_stride]. */
 int sy_load_graphs(SyEnv* env, int32_t num_graphs, const int32_t* row_ptr, const int32_t* col,
                    const int32_t* w, int32_t nnz_stride, sy_stream_t stream);
+/* Sample the whole pool ON THE DEVICE: replaces ConnectedGraph.sample (graph_layout.py:9-80: random recursive tree
+ * over a uniform insertion order, extra edges first-fit over a uniform shuffle under the degree cap, weights
+ * U{1..max_weight-1}) and the resample-until-the-edge-count-matches loop of CustomEnvironment.__init__/reset
+ * (yard.py:67-101: the first sample fixes the count, later ones are redrawn up to 100 times) -- same distribution,
+ * Philox streams keyed by (seed; graph_offset + slot, generation, attempt), one warp per pool slot; then the tables of
+ * sy_load_graphs are built from the result.  A new `generation` refreshes the pool ("new graph on reset" at scale);
+ * with an unchanged shape the tables keep their addresses.  Envs must be reset afterwards.  attempts_host (HOST,
+ * [num_graphs], may be NULL) receives the 0-based attempt that produced each slot.  Fails with SY_ERR_STATE and the
+ * reference's message when a slot cannot reach the edge count.  num_nodes <= 8192.  Synchronises the stream. */
+int sy_generate_graphs(SyEnv* env, int32_t num_graphs, int32_t num_edges, int32_t max_edges_per_node, int32_t max_weight,
+                       uint64_t seed, uint32_t generation, uint32_t graph_offset, int32_t* attempts_host,
+                       sy_stream_t stream);
+/* Edge lists of a device-sampled pool in the reference's order (tree edges, then the extras) = GraphInstance
+ * .edge_links / .edges (graph_layout.py:53).  HOST buffers: edge_links int32 [G, max_edges, 2], weights int32
+ * [G, max_edges], counts int32 [G]; rows valid up to counts[g].  Synchronises the stream. */
+int sy_read_graph_edges(SyEnv* env, int32_t* edge_links, int32_t* weights, int32_t* counts, int32_t max_edges,
+                        sy_stream_t stream);
 /* copy graph g's tables to HOST buffers (any may be NULL): weights u8 [N, N], apsp u16 [N, N]
  * (0xFFFF = unreachable).  Synchronises the stream.  For tests / get_distance parity. */
 int sy_read_graph_tables(SyEnv* env, int32_t g, uint8_t* weights, uint16_t* apsp, sy_stream_t stream);

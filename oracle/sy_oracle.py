@@ -348,6 +348,121 @@ def philox_graph_choice(seed, env, episode, n_graphs) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# Counter-based graph sampler: the SAME DISTRIBUTION as sample_connected_graph above
+# (= ConnectedGraph.sample, graph_layout.py:9-80) from Philox streams keyed by (seed; graph index, generation /
+# attempt), in a form a GPU warp can run per graph.  Why the distribution is the same:
+#   * `_create_tree` (graph_layout.py:55-80) starts at a uniform node and always joins a uniform (visited, unvisited)
+#     pair = a uniform unvisited node to a uniform visited node: a uniformly random insertion order whose k-th node
+#     attaches to a uniform earlier one.
+#   * the extra edges are a first-fit scan over a uniform shuffle of all non-tree pairs under the degree cap
+#     (graph_layout.py:24-48).  A node only ever goes from "open" (degree < cap) to "closed", so a pair that was
+#     scanned and skipped stays unacceptable for good, and a pair whose two ends are still open cannot have been
+#     scanned without being accepted.  Hence the next accepted edge is uniform over the non-adjacent pairs of the
+#     currently open nodes, and the scan ends early exactly when no such pair is left.  That is what is sampled here
+#     (rejection over ordered pairs of open nodes, with the number V of acceptable pairs tracked exactly).
+#   * weights are iid U{1..max_weight-1} (np.random.randint(1, MAX_WEIGHT), graph_layout.py:17,47).
+# --------------------------------------------------------------------------------------
+RNG_GEN_PERM, RNG_GEN_PARENT, RNG_GEN_TREE_W, RNG_GEN_PAIR, RNG_GEN_EXTRA_W = 16, 17, 18, 19, 20
+GEN_MAX_ATTEMPTS = 100  # yard.py:89-101
+GEN_MAX_DRAWS = 1 << 22
+
+
+class _GenStream:
+    """k-th 32-bit word of the stream (seed; graph, generation * 128 + attempt, purpose, k >> 2)."""
+
+    def __init__(self, seed, graph, generation, attempt, purpose):
+        self.key = (seed & _M32, (seed >> 32) & _M32)
+        self.c0, self.c1, self.c2 = graph & _M32, (generation * 128 + attempt) & _M32, purpose
+        self.blk, self.words = -1, None
+
+    def word(self, k):
+        if (k >> 2) != self.blk:
+            self.blk = k >> 2
+            self.words = philox4x32((self.c0, self.c1, self.c2, self.blk), self.key)
+        return self.words[k & 3]
+
+
+def philox_sample_graph_once(seed, graph, generation, attempt, num_nodes, num_edges, max_edges_per_node=4,
+                             max_weight=5) -> Graph:
+    N, cap, wr = int(num_nodes), int(max_edges_per_node), int(max_weight) - 1
+    perm_s, par_s, tw_s, pair_s, xw_s = [_GenStream(seed, graph, generation, attempt, pu) for pu in
+                                         (RNG_GEN_PERM, RNG_GEN_PARENT, RNG_GEN_TREE_W, RNG_GEN_PAIR, RNG_GEN_EXTRA_W)]
+    order = list(range(N))
+    for k in range(N - 1):  # Fisher-Yates
+        j = k + ((perm_s.word(k) * (N - k)) >> 32)
+        order[k], order[j] = order[j], order[k]
+    adj = np.zeros((N, N), dtype=bool)
+    deg = [0] * N
+    links, weights = [], []
+    for k in range(1, N):
+        u, v = order[(par_s.word(k) * k) >> 32], order[k]
+        links.append((u, v))
+        weights.append(1 + ((tw_s.word(k) * wr) >> 32))
+        adj[u, v] = adj[v, u] = True
+        deg[u] += 1
+        deg[v] += 1
+    extra = (N - 1 if num_edges is None else int(num_edges)) - (N - 1)
+    open_nodes = [u for u in range(N) if deg[u] < cap]  # ascending
+    pos = {u: i for i, u in enumerate(open_nodes)}
+    n_open = len(open_nodes)
+    V = n_open * (n_open - 1) // 2 - sum(1 for u, v in links if deg[u] < cap and deg[v] < cap)
+    draw = n_extra = 0
+    while extra > 0 and V > 0:
+        if draw >= GEN_MAX_DRAWS:
+            raise RuntimeError("graph sampler: draw budget exhausted")
+        a = (pair_s.word(draw) * n_open) >> 32
+        b = (pair_s.word(draw + 1) * (n_open - 1)) >> 32
+        draw += 2
+        if b >= a:
+            b += 1
+        i, j = open_nodes[a], open_nodes[b]
+        if adj[i, j]:
+            continue
+        links.append((i, j))
+        weights.append(1 + ((xw_s.word(n_extra) * wr) >> 32))
+        adj[i, j] = adj[j, i] = True
+        deg[i] += 1
+        deg[j] += 1
+        V -= 1
+        extra -= 1
+        n_extra += 1
+        for x in (i, j):
+            if deg[x] >= cap:  # x closes: swap-with-last removal, its still-acceptable pairs disappear
+                last = open_nodes[n_open - 1]
+                open_nodes[pos[x]] = last
+                pos[last] = pos[x]
+                n_open -= 1
+                open_nodes.pop()
+                del pos[x]
+                V -= sum(1 for k in open_nodes if not adj[x, k])
+    return Graph(N, np.asarray(links, dtype=np.int32).reshape(-1, 2), np.asarray(weights, dtype=np.int64))
+
+
+def philox_sample_graph(seed, graph, generation, num_nodes, num_edges, want_edges=0, max_edges_per_node=4, max_weight=5):
+    """One pool slot: resample (attempt 0, 1, ...) until the edge count equals `want_edges` (0 = take the first), as
+    CustomEnvironment.reset does against the count frozen at construction (yard.py:87-101).  Returns (Graph, attempt)."""
+    for attempt in range(GEN_MAX_ATTEMPTS):
+        g = philox_sample_graph_once(seed, graph, generation, attempt, num_nodes, num_edges, max_edges_per_node, max_weight)
+        if want_edges <= 0 or len(g.edges) == want_edges:
+            return g, attempt
+    raise RuntimeError(f"Failed to generate graph with {want_edges} edges after {GEN_MAX_ATTEMPTS} attempts.")
+
+
+def philox_graph_pool(seed, num_graphs, num_nodes, num_edges, generation=0, graph_offset=0, max_edges_per_node=4,
+                      max_weight=5):
+    """Slot `graph_offset` + 0 of generation `generation` fixes the edge count (the constructor's probe sample,
+    yard.py:67-76); every other slot is resampled until it matches."""
+    first, _ = philox_sample_graph(seed, 0, generation, num_nodes, num_edges, 0, max_edges_per_node, max_weight)
+    want = len(first.edges)
+    pool = []
+    for g in range(num_graphs):
+        gg = graph_offset + g
+        pool.append(first if gg == 0 else philox_sample_graph(seed, gg, generation, num_nodes, num_edges, want,
+                                                              max_edges_per_node, max_weight)[0])
+    return pool
+
+
+# --------------------------------------------------------------------------------------
 # The environment
 # --------------------------------------------------------------------------------------
 @dataclass

@@ -60,6 +60,9 @@ SIGNATURES = {
     "sy_set_reward_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_load_graphs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_read_graph_tables": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_generate_graphs": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
+                                     C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sy_read_graph_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SyState),
                            C.POINTER(SyObs), C.c_void_p]),
     "sy_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),

@@ -1346,6 +1346,242 @@ __global__ void sy_apsp_kernel(int G, int N, int nnz_stride, const int32_t* row_
 }
 
 // ---------------------------------------------------------------------------------------------
+// device-side graph sampler: ConnectedGraph.sample (graph_layout.py:9-80) plus the
+// resample-until-the-edge-count-matches loop of CustomEnvironment.reset (yard.py:87-101), one warp per pool slot.
+// Same distribution as the reference (argument in oracle/sy_oracle.py above philox_sample_graph_once, which restates
+// this kernel draw for draw): uniform insertion order (Fisher-Yates), every node attaches to a uniform earlier one,
+// then the extra edges one at a time, each uniform over the non-adjacent pairs of the nodes still under the degree
+// cap (rejection sampling over ordered pairs of open nodes; the number V of acceptable pairs is tracked exactly, so
+// the loop ends when the reference's scan would find nothing more).  Every lane carries the same scalars; lane 0
+// writes, the warp shares the counting loops.  The adjacency being built is the pool's dense weight table itself.
+// ---------------------------------------------------------------------------------------------
+enum { RNG_GEN_PERM = 16, RNG_GEN_PARENT = 17, RNG_GEN_TREE_W = 18, RNG_GEN_PAIR = 19, RNG_GEN_EXTRA_W = 20 };
+constexpr int GEN_MAX_ATTEMPTS = 100;  // yard.py:89
+constexpr unsigned GEN_MAX_DRAWS = 1u << 22;
+constexpr int GEN_MAX_NODES = 8192;
+
+struct GenStream {  // k-th 32-bit word of Philox(seed; graph, generation * 128 + attempt, purpose, k >> 2)
+  uint2 key;
+  unsigned c0, c1, c2;
+  int blk;
+  uint4 w;
+  __device__ GenStream(uint2 key_, unsigned graph, unsigned ga, unsigned purpose) : key(key_), c0(graph), c1(ga), c2(purpose), blk(-1), w(make_uint4(0, 0, 0, 0)) {}
+  __device__ unsigned word(int k) {
+    if ((k >> 2) != blk) {
+      blk = k >> 2;
+      w = philox4x32(make_uint4(c0, c1, c2, (unsigned)blk), key);
+    }
+    return word_of(w, k & 3);
+  }
+};
+
+struct GenParams {
+  int N, Ns, max_edges, num_edges, cap, wrange;
+  unsigned seed_lo, seed_hi, generation, graph_offset;
+  int probe;            // 1: sample GLOBAL graph 0 into slot 0 and publish its edge count (the constructor's probe, yard.py:67-76)
+  int* want;            // device scalar: the edge count every slot must reach
+  uint8_t* W;           // [G, N, Ns]
+  ushort2* edges;       // [G, max_edges] in the reference's order: tree edges, then the extras
+  uint8_t* edge_w;      // [G, max_edges]
+  int* edge_count;      // [G]
+  int* status;          // [G] attempts used (0-based), -1 = no sample with the wanted count, -2 = draw budget exhausted
+};
+
+__global__ void __launch_bounds__(32) sy_sample_graphs_kernel(const GenParams q) {
+  extern __shared__ __align__(16) unsigned char gen_smem[];
+  const int N = q.N, Ns = q.Ns, lane = threadIdx.x;
+  int* deg = reinterpret_cast<int*>(gen_smem);
+  uint16_t* order = reinterpret_cast<uint16_t*>(deg + N);
+  uint16_t* open = order + N;
+  uint16_t* opos = open + N;
+  const int g = blockIdx.x;
+  const unsigned gid = q.probe ? 0u : q.graph_offset + (unsigned)g;
+  const int want = q.probe ? 0 : *q.want;
+  const uint2 key = make_uint2(q.seed_lo, q.seed_hi);
+  uint8_t* Wg = q.W + (size_t)g * N * Ns;
+  volatile uint8_t* Wv = Wg;
+  ushort2* edges = q.edges + (size_t)g * q.max_edges;
+  uint8_t* ew = q.edge_w + (size_t)g * q.max_edges;
+  int E = 0, attempt = 0, status = -1;
+  for (; attempt < GEN_MAX_ATTEMPTS; ++attempt) {
+    const unsigned ga = q.generation * 128u + (unsigned)attempt;
+    uint4* W16 = reinterpret_cast<uint4*>(Wg);
+    for (int i = lane; i < N * (Ns >> 4); i += 32) W16[i] = make_uint4(0, 0, 0, 0);
+    for (int i = lane; i < N; i += 32) {
+      order[i] = (uint16_t)i;
+      deg[i] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) {  // uniform insertion order
+      GenStream ps(key, gid, ga, RNG_GEN_PERM);
+      for (int k = 0; k < N - 1; ++k) {
+        const int j = k + (int)__umulhi(ps.word(k), (unsigned)(N - k));
+        const uint16_t t = order[k];
+        order[k] = order[j];
+        order[j] = t;
+      }
+    }
+    __syncwarp();
+    for (int k = 1 + lane; k < N; k += 32) {  // tree: the k-th node joins a uniform earlier one
+      const uint4 rp = philox4x32(make_uint4(gid, ga, RNG_GEN_PARENT, (unsigned)(k >> 2)), key);
+      const uint4 rw = philox4x32(make_uint4(gid, ga, RNG_GEN_TREE_W, (unsigned)(k >> 2)), key);
+      const int u = order[__umulhi(word_of(rp, k & 3), (unsigned)k)], v = order[k];
+      const int wt = 1 + (int)__umulhi(word_of(rw, k & 3), (unsigned)q.wrange);
+      Wv[(size_t)u * Ns + v] = (uint8_t)wt;
+      Wv[(size_t)v * Ns + u] = (uint8_t)wt;
+      edges[k - 1] = make_ushort2((unsigned short)u, (unsigned short)v);
+      ew[k - 1] = (uint8_t)wt;
+      atomicAdd(deg + u, 1);
+      atomicAdd(deg + v, 1);
+    }
+    __threadfence_block();
+    __syncwarp();
+    int n_open = 0;  // nodes under the degree cap, ascending
+    for (int base = 0; base < N; base += 32) {
+      const int u = base + lane;
+      const bool o = u < N && deg[u] < q.cap;
+      const unsigned m = __ballot_sync(FULL, o);
+      if (o) {
+        const int idx = n_open + __popc(m & ((1u << lane) - 1u));
+        open[idx] = (uint16_t)u;
+        opos[u] = (uint16_t)idx;
+      }
+      n_open += __popc(m);
+    }
+    __syncwarp();
+    int both = 0;
+    for (int k = lane; k < N - 1; k += 32) {
+      const ushort2 e = edges[k];
+      both += (deg[e.x] < q.cap && deg[e.y] < q.cap);
+    }
+    both = __reduce_add_sync(FULL, both);
+    long long V = (long long)n_open * (n_open - 1) / 2 - both;  // acceptable pairs
+    int extra = q.num_edges - (N - 1), n_extra = 0;
+    unsigned draw = 0;
+    bool exhausted = false;
+    GenStream pair_s(key, gid, ga, RNG_GEN_PAIR), xw_s(key, gid, ga, RNG_GEN_EXTRA_W);
+    while (extra > 0 && V > 0) {
+      if (draw >= GEN_MAX_DRAWS) {
+        exhausted = true;
+        break;
+      }
+      const int a = (int)__umulhi(pair_s.word((int)draw), (unsigned)n_open);
+      int b = (int)__umulhi(pair_s.word((int)draw + 1), (unsigned)(n_open - 1));
+      draw += 2;
+      if (b >= a) ++b;
+      const int i = open[a], j = open[b];
+      if (Wv[(size_t)i * Ns + j]) continue;
+      const int wt = 1 + (int)__umulhi(xw_s.word(n_extra), (unsigned)q.wrange);
+      if (lane == 0) {
+        Wv[(size_t)i * Ns + j] = (uint8_t)wt;
+        Wv[(size_t)j * Ns + i] = (uint8_t)wt;
+        edges[N - 1 + n_extra] = make_ushort2((unsigned short)i, (unsigned short)j);
+        ew[N - 1 + n_extra] = (uint8_t)wt;
+        deg[i] += 1;
+        deg[j] += 1;
+      }
+      __threadfence_block();
+      __syncwarp();
+      --V;
+      --extra;
+      ++n_extra;
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int x = side ? j : i;
+        if (deg[x] >= q.cap) {  // x closes: swap-with-last removal; its still-acceptable pairs disappear
+          __syncwarp();
+          if (lane == 0) {
+            const uint16_t last = open[n_open - 1], px = opos[x];
+            open[px] = last;
+            opos[last] = px;
+          }
+          --n_open;
+          __syncwarp();
+          int c = 0;
+          for (int t = lane; t < n_open; t += 32) c += (Wv[(size_t)x * Ns + open[t]] == 0);
+          V -= __reduce_add_sync(FULL, c);
+        }
+      }
+    }
+    E = N - 1 + n_extra;
+    if (exhausted) {
+      status = -2;
+      break;
+    }
+    if (want <= 0 || E == want) {
+      status = attempt;
+      break;
+    }
+  }
+  if (lane == 0) {
+    q.edge_count[g] = E;
+    q.status[g] = status;
+    if (q.probe) *q.want = E;
+  }
+}
+
+// CSR, padded neighbour lists and their offsets from the dense weight table; one CTA per graph
+__global__ void __launch_bounds__(256) sy_csr_from_dense_kernel(int N, int Ns, int nnz_stride, int pack_stride, const uint8_t* W,
+                                                                int32_t* row_ptr, uint16_t* col, uint8_t* wgt, int2* pack,
+                                                                int32_t* pack_ptr, int* status) {
+  extern __shared__ int csr_smem[];
+  int* sdeg = csr_smem;            // [N]
+  int* srow = csr_smem + N;        // [N + 1]
+  int* spk = csr_smem + 2 * N + 1; // [N + 1]
+  const int g = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* Wg = W + (size_t)g * N * Ns;
+  for (int u = tid; u < N; u += blockDim.x) {
+    const uint4* row = reinterpret_cast<const uint4*>(Wg + (size_t)u * Ns);
+    int d = 0;
+    for (int v = 0; v < (Ns >> 4); ++v) {
+      const uint4 x = row[v];
+      const unsigned wds[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) d += ((wds[q] >> (8 * b)) & 0xFFu) != 0;
+    }
+    sdeg[u] = d;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0, b = 0, bad = 0;
+    for (int u = 0; u < N; ++u) {
+      const int d = sdeg[u];
+      srow[u] = a;
+      spk[u] = b;
+      a += d;
+      b += (d + 3) & ~3;
+      bad |= d > 255;
+    }
+    srow[N] = a;
+    spk[N] = b;
+    if (bad || a > nnz_stride || b > pack_stride) status[g] = -3;
+  }
+  __syncthreads();
+  if (srow[N] > nnz_stride || spk[N] > pack_stride) return;
+  for (int u = tid; u <= N; u += blockDim.x) {
+    row_ptr[(size_t)g * (N + 1) + u] = srow[u];
+    pack_ptr[(size_t)g * (N + 1) + u] = spk[u];
+  }
+  for (int u = tid; u < N; u += blockDim.x) {
+    int k = srow[u], pk = spk[u];
+    const uint8_t* row = Wg + (size_t)u * Ns;
+    for (int v = 0; v < N; ++v) {
+      const int w = row[v];
+      if (w) {
+        col[(size_t)g * nnz_stride + k] = (uint16_t)v;
+        wgt[(size_t)g * nnz_stride + k] = (uint8_t)w;
+        pack[(size_t)g * pack_stride + pk] = make_int2(v * BSTRIDE * (int)sizeof(float), __float_as_int(1.0f / (float)sdeg[v]));
+        ++k;
+        ++pk;
+      }
+    }
+    for (; pk < spk[u + 1]; ++pk) pack[(size_t)g * pack_stride + pk] = make_int2(0, 0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // dense float64 action mask == compute_action_mask (action_mask.py:30-83); one CTA per query
 // ---------------------------------------------------------------------------------------------
 __global__ void sy_mask_dense_kernel(int N, const double* adj, const double* w, const double* toll_m, double toll_s,
@@ -1383,6 +1619,14 @@ struct SyEnv {
   void* d_inv_deg = nullptr;
   void* d_pack = nullptr;
   void* d_pack_ptr = nullptr;
+  // device graph sampler (sy_generate_graphs): edge lists in the reference's order, per-slot edge count / status
+  void* d_edges = nullptr;
+  void* d_edge_w = nullptr;
+  void* d_edge_count = nullptr;
+  void* d_gen_status = nullptr;
+  void* d_gen_want = nullptr;
+  int gen_max_edges = 0;  // > 0: the pool was sampled on the device
+  int alloc_G = 0, alloc_nnz = 0, alloc_wcap = 0, alloc_pack = 0;  // shape of the current table allocations
   void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
   void* d_stats_rep = nullptr;  // [STAT_REPLICAS, SY_NUM_STATS] u64
   cudaStream_t aux_stream = nullptr;  // host-buffer path: result copies overlap the observe kernel
@@ -1398,11 +1642,39 @@ struct SyEnv {
 namespace {
 
 void free_graph_tables(SyEnv* e) {
-  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack, &e->d_pack_ptr}) {
+  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack, &e->d_pack_ptr,
+                     &e->d_edges, &e->d_edge_w, &e->d_edge_count, &e->d_gen_status, &e->d_gen_want}) {
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
   }
   e->graphs_loaded = false;
+  e->gen_max_edges = 0;
+  e->alloc_G = e->alloc_nnz = e->alloc_wcap = e->alloc_pack = 0;
+}
+
+int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stride, cudaStream_t s);
+
+// (re)allocate the pool tables; an unchanged shape keeps the allocations, so pointers baked into captured CUDA
+// graphs stay valid across pool refreshes
+int alloc_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stride) {
+  const int N = e->cfg.num_nodes;
+  if (e->d_W && e->alloc_G == G && e->alloc_nnz == nnz_stride && e->alloc_wcap == wcap && e->alloc_pack == pack_stride) return SY_OK;
+  free_graph_tables(e);
+  const int Ns = (N + 15) & ~15;
+  CUDA_TRY(cudaMalloc(&e->d_W, (size_t)G * N * Ns));
+  CUDA_TRY(cudaMalloc(&e->d_D, (size_t)G * N * N * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&e->d_row_ptr, (size_t)G * (N + 1) * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&e->d_col, (size_t)G * nnz_stride * sizeof(uint16_t)));
+  CUDA_TRY(cudaMalloc(&e->d_wgt, (size_t)G * nnz_stride));
+  CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1) + 16));  // + 16: vector loads of the last row's tail
+  CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&e->d_pack, (size_t)G * pack_stride * sizeof(int2)));
+  CUDA_TRY(cudaMalloc(&e->d_pack_ptr, (size_t)G * (N + 1) * sizeof(int32_t)));
+  e->alloc_G = G;
+  e->alloc_nnz = nnz_stride;
+  e->alloc_wcap = wcap;
+  e->alloc_pack = pack_stride;
+  return SY_OK;
 }
 
 int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOut* out, Params& p) {
@@ -1595,24 +1867,25 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   if ((long long)wcap * (N - 1) >= DIST_INF) return fail(SY_ERR_INVALID_ARGUMENT, "max path length does not fit u16");
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  free_graph_tables(e);
-  const int Ns = (N + 15) & ~15;
-  const size_t nW = (size_t)G * N * Ns, nD = (size_t)G * N * N;
-  CUDA_TRY(cudaMalloc(&e->d_W, nW));
-  CUDA_TRY(cudaMalloc(&e->d_D, nD * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&e->d_row_ptr, (size_t)G * (N + 1) * sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&e->d_col, (size_t)G * nnz_stride * sizeof(uint16_t)));
-  CUDA_TRY(cudaMalloc(&e->d_wgt, (size_t)G * nnz_stride));
-  CUDA_TRY(cudaMalloc(&e->d_cnt, (size_t)G * N * (wcap + 1) + 16));  // + 16: vector loads of the last row's tail
-  CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&e->d_pack, pack.size() * sizeof(int2)));
+  e->graphs_loaded = false;
+  e->gen_max_edges = 0;
+  if (int rc = alloc_graph_tables(e, G, nnz_stride, wcap, pack_stride)) return rc;
   CUDA_TRY(cudaMemcpyAsync(e->d_pack, pack.data(), pack.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMalloc(&e->d_pack_ptr, pack_ptr.size() * sizeof(int32_t)));
   CUDA_TRY(cudaMemcpyAsync(e->d_pack_ptr, pack_ptr.data(), pack_ptr.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_row_ptr, row_ptr, (size_t)G * (N + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_col, col16.data(), col16.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(e->d_wgt, w8.data(), w8.size(), cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaStreamSynchronize(s));  // the staging vectors die at return
+  return finish_graph_tables(e, G, nnz_stride, wcap, pack_stride, s);
+}
+
+}  // extern "C"
+
+namespace {
+// everything derived from the CSR (dense weights, move counts, 1/deg, all-pairs distances) + the kernels' smem plans
+int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stride, cudaStream_t s) {
+  const int N = e->cfg.num_nodes;
+  const int Ns = (N + 15) & ~15;
   sy_build_rows_kernel<<<dim3(N, G), 64, 0, s>>>(N, Ns, nnz_stride, wcap, (const int32_t*)e->d_row_ptr, (const uint16_t*)e->d_col,
                                                  (const uint8_t*)e->d_wgt, (uint8_t*)e->d_W, (uint8_t*)e->d_cnt, (float*)e->d_inv_deg);
   g_launches++;
@@ -1679,6 +1952,115 @@ int sy_load_graphs(SyEnv* e, int32_t G, const int32_t* row_ptr, const int32_t* c
   e->tb.nnz_stride = nnz_stride;
   e->tb.wcap = wcap;
   e->graphs_loaded = true;
+  return SY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+// Replaces ConnectedGraph.sample (graph_layout.py:9-80) + the resample loop of yard.py:67-101 for a whole pool, on the
+// device.  Slot g of this handle is global graph `graph_offset + g`; global graph 0 of the generation fixes the edge
+// count (it is sampled first, as a probe, into slot 0).
+int sy_generate_graphs(SyEnv* e, int32_t G, int32_t num_edges, int32_t max_edges_per_node, int32_t max_weight, uint64_t seed,
+                       uint32_t generation, uint32_t graph_offset, int32_t* attempts_host, sy_stream_t stream) {
+  if (!e || G <= 0 || G > 65535) return fail(SY_ERR_INVALID_ARGUMENT, "1..65535 graphs in the pool");
+  const int N = e->cfg.num_nodes;
+  if (N > GEN_MAX_NODES) return fail(SY_ERR_INVALID_ARGUMENT, "device graph sampler: at most %d nodes", GEN_MAX_NODES);
+  if (max_edges_per_node < 1 || max_weight < 2 || max_weight > 256) return fail(SY_ERR_INVALID_ARGUMENT, "bad degree cap / max_weight");
+  if (generation >= (1u << 25)) return fail(SY_ERR_INVALID_ARGUMENT, "generation must be below 2^25");
+  if ((long long)(max_weight - 1) * (N - 1) >= DIST_INF) return fail(SY_ERR_INVALID_ARGUMENT, "max path length does not fit u16");
+  const long long all_pairs = (long long)N * (N - 1) / 2;
+  if (num_edges < N - 1) num_edges = N - 1;  // graph_layout.py:20-21: the tree is the minimum
+  if (num_edges > all_pairs) num_edges = (int32_t)all_pairs;
+  const int max_edges = num_edges, nnz_stride = 2 * max_edges > 0 ? 2 * max_edges : 1, wcap = max_weight - 1;
+  const int pack_stride = ((nnz_stride + 3 * N + 3) & ~3) + 4;
+  const int Ns = (N + 15) & ~15;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  e->graphs_loaded = false;
+  if (int rc = alloc_graph_tables(e, G, nnz_stride, wcap, pack_stride)) return rc;
+  if (!e->d_edges || e->gen_max_edges != max_edges) {
+    for (void** ptr : {&e->d_edges, &e->d_edge_w, &e->d_edge_count, &e->d_gen_status, &e->d_gen_want}) {
+      if (*ptr) cudaFree(*ptr);
+      *ptr = nullptr;
+    }
+    CUDA_TRY(cudaMalloc(&e->d_edges, (size_t)G * max_edges * sizeof(ushort2)));
+    CUDA_TRY(cudaMalloc(&e->d_edge_w, (size_t)G * max_edges));
+    CUDA_TRY(cudaMalloc(&e->d_edge_count, (size_t)G * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&e->d_gen_status, (size_t)G * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&e->d_gen_want, sizeof(int)));
+  }
+  e->gen_max_edges = max_edges;
+  CUDA_TRY(cudaMemsetAsync(e->d_col, 0, (size_t)G * nnz_stride * sizeof(uint16_t), s));
+  CUDA_TRY(cudaMemsetAsync(e->d_wgt, 0, (size_t)G * nnz_stride, s));
+  GenParams q{};
+  q.N = N;
+  q.Ns = Ns;
+  q.max_edges = max_edges;
+  q.num_edges = num_edges;
+  q.cap = max_edges_per_node;
+  q.wrange = max_weight - 1;
+  q.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
+  q.seed_hi = (unsigned)(seed >> 32);
+  q.generation = generation;
+  q.graph_offset = graph_offset;
+  q.want = (int*)e->d_gen_want;
+  q.W = (uint8_t*)e->d_W;
+  q.edges = (ushort2*)e->d_edges;
+  q.edge_w = (uint8_t*)e->d_edge_w;
+  q.edge_count = (int*)e->d_edge_count;
+  q.status = (int*)e->d_gen_status;
+  const size_t gen_smem = (size_t)N * (sizeof(int) + 3 * sizeof(uint16_t));
+  if (gen_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sy_sample_graphs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gen_smem));
+  q.probe = 1;
+  sy_sample_graphs_kernel<<<1, 32, gen_smem, s>>>(q);
+  q.probe = 0;
+  sy_sample_graphs_kernel<<<G, 32, gen_smem, s>>>(q);
+  g_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  const size_t csr_smem = (size_t)(3 * N + 2) * sizeof(int);
+  if (csr_smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(sy_csr_from_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csr_smem));
+  sy_csr_from_dense_kernel<<<G, 256, csr_smem, s>>>(N, Ns, nnz_stride, pack_stride, (const uint8_t*)e->d_W, (int32_t*)e->d_row_ptr,
+                                                    (uint16_t*)e->d_col, (uint8_t*)e->d_wgt, (int2*)e->d_pack, (int32_t*)e->d_pack_ptr,
+                                                    (int*)e->d_gen_status);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  std::vector<int> status((size_t)G);
+  int want = 0;
+  CUDA_TRY(cudaMemcpyAsync(status.data(), e->d_gen_status, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(&want, e->d_gen_want, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int g = 0; g < G; ++g) {
+    if (attempts_host) attempts_host[g] = status[g];
+    if (status[g] == -1)  // the reference's RuntimeError, yard.py:96-101
+      return fail(SY_ERR_STATE, "Failed to generate graph with %d edges after %d attempts (pool slot %d).", want, GEN_MAX_ATTEMPTS, g);
+    if (status[g] < 0) return fail(SY_ERR_STATE, "device graph sampler failed for pool slot %d (status %d)", g, status[g]);
+  }
+  return finish_graph_tables(e, G, nnz_stride, wcap, pack_stride, s);
+}
+
+// edge lists of a device-sampled pool in the reference's order (tree edges, then the extras): what GraphInstance
+// holds as edge_links / edges (graph_layout.py:53).  HOST buffers: edge_links int32 [G, max_edges, 2], weights
+// int32 [G, max_edges], counts int32 [G]; rows are valid up to counts[g].
+int sy_read_graph_edges(SyEnv* e, int32_t* edge_links, int32_t* weights, int32_t* counts, int32_t max_edges, sy_stream_t stream) {
+  if (!e || !e->graphs_loaded || e->gen_max_edges <= 0) return fail(SY_ERR_STATE, "the pool was not sampled on the device");
+  if (!edge_links || !weights || !counts || max_edges < e->gen_max_edges) return fail(SY_ERR_INVALID_ARGUMENT, "bad edge buffers (need max_edges >= %d)", e->gen_max_edges);
+  const int G = e->tb.G, M = e->gen_max_edges;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  std::vector<ushort2> ed((size_t)G * M);
+  std::vector<uint8_t> ew((size_t)G * M);
+  CUDA_TRY(cudaMemcpyAsync(ed.data(), e->d_edges, ed.size() * sizeof(ushort2), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(ew.data(), e->d_edge_w, ew.size(), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(counts, e->d_edge_count, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int g = 0; g < G; ++g)
+    for (int k = 0; k < max_edges; ++k) {
+      const bool live = k < M && k < counts[g];
+      edge_links[((size_t)g * max_edges + k) * 2] = live ? ed[(size_t)g * M + k].x : 0;
+      edge_links[((size_t)g * max_edges + k) * 2 + 1] = live ? ed[(size_t)g * M + k].y : 0;
+      weights[(size_t)g * max_edges + k] = live ? ew[(size_t)g * M + k] : 0;
+    }
   return SY_OK;
 }
 

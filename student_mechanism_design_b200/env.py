@@ -51,8 +51,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class BatchedScotlandYardEnv:
     """B independent games stepped by one kernel launch.
 
-    Parameters mirror yard.py:18-28; extras: `num_envs`, `graphs` (a pool of GraphSpec, or
-    None to generate `num_graphs` with the reference's distribution), `reveal_interval`,
+    Parameters mirror yard.py:18-28; extras: `num_envs`, `graphs` (a pool of GraphSpec, None to
+    generate `num_graphs` on the host, or "device" to sample them on the GPU -- both with the
+    reference's distribution; `regenerate_graphs` then refreshes a device pool), `reveal_interval`,
     `tolls`, `belief`, `reward_mode` ("fp64" | "fp32" | None = infer from the weight types, as
     the reference's arithmetic follows them), `seed`, `auto_reset`, `resample_graph`,
     `env_offset` (global index of env 0 when the batch is sharded over GPUs).
@@ -66,7 +67,8 @@ class BatchedScotlandYardEnv:
                  *, graphs: Optional[Sequence[GraphSpec]] = None, num_graphs: int = 1, reveal_interval: int = 0,
                  tolls: float = 0, belief: bool = False, belief_ce: bool = False, reward_mode: Optional[str] = None, seed: int = 0,
                  auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
-                 device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True):
+                 device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True,
+                 graph_offset: int = 0, max_edges_per_node: int = 4, max_weight: int = 5):
         if not torch.cuda.is_available():
             raise _cabi.SyError("BatchedScotlandYardEnv needs a CUDA device; there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -98,13 +100,21 @@ class BatchedScotlandYardEnv:
                  for k in REWARD_WEIGHT_NAMES]
 
         # ---- graph pool
-        if graphs is None:
-            graphs = generate_graph_pool(num_graphs, graph_nodes, graph_edges, seed=seed)
-        self.graphs: List[GraphSpec] = list(graphs)
-        self.graph_nodes = self.graphs[0].num_nodes
+        self._device_pool = isinstance(graphs, str)
+        self._gen = dict(graph_offset=int(graph_offset), cap=int(max_edges_per_node), max_weight=int(max_weight), generation=0)
+        if self._device_pool:
+            if graphs != "device":
+                raise ValueError("graphs must be a sequence of GraphSpec, None or 'device'")
+            self.graphs: List[GraphSpec] = []
+            self.graph_nodes, self.num_graphs, self.actual_num_edges = int(graph_nodes), int(num_graphs), 0
+        else:
+            if graphs is None:
+                graphs = generate_graph_pool(num_graphs, graph_nodes, graph_edges, seed=seed)
+            self.graphs = list(graphs)
+            self.graph_nodes = self.graphs[0].num_nodes
+            self.actual_num_edges = len(self.graphs[0].edges)  # yard.py:70
+            self.num_graphs = len(self.graphs)
         self.graph_edges = graph_edges
-        self.actual_num_edges = len(self.graphs[0].edges)  # yard.py:70
-        self.num_graphs = len(self.graphs)
         N, A, B = self.graph_nodes, self.num_agents, self.num_envs
 
         cfg = _cabi.SyConfig()
@@ -132,10 +142,13 @@ class BatchedScotlandYardEnv:
             coverage = np.ascontiguousarray(coverage, dtype=np.float64)
             _cabi.check(self._lib.sy_set_reward_tables(self._handle, exp_neg.ctypes.data, len(exp_neg),
                                                        coverage.ctypes.data, len(coverage), stream))
-            row_ptr, col, wgt, stride = pack_csr(self.graphs)
-            self._csr = (row_ptr, col, wgt)
-            _cabi.check(self._lib.sy_load_graphs(self._handle, self.num_graphs, row_ptr.ctypes.data, col.ctypes.data,
-                                                 wgt.ctypes.data, stride, stream))
+            if self._device_pool:
+                self._generate_on_device(0)
+            else:
+                row_ptr, col, wgt, stride = pack_csr(self.graphs)
+                self._csr = (row_ptr, col, wgt)
+                _cabi.check(self._lib.sy_load_graphs(self._handle, self.num_graphs, row_ptr.ctypes.data, col.ctypes.data,
+                                                     wgt.ctypes.data, stride, stream))
 
             dev = self.device
             z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
@@ -335,6 +348,39 @@ class BatchedScotlandYardEnv:
         host[key].copy_(dev_actions, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return host[key]
+
+    # ------------------------------------------------------------------ device graph pool
+    def _generate_on_device(self, generation: int):
+        """sy_generate_graphs + read the edge lists back (the host keeps GraphSpec views for the static observation
+        tensors, exactly what the reference's `env.board` holds)."""
+        N, G = self.graph_nodes, self.num_graphs
+        want_e = N - 1 if self.graph_edges is None else int(self.graph_edges)
+        max_e = min(max(want_e, N - 1), N * (N - 1) // 2)
+        attempts = np.zeros(G, dtype=np.int32)
+        _cabi.check(self._lib.sy_generate_graphs(self._handle, G, want_e, self._gen["cap"], self._gen["max_weight"],
+                                                 self.seed & 0xFFFFFFFFFFFFFFFF, int(generation), self._gen["graph_offset"],
+                                                 attempts.ctypes.data, self._stream()))
+        links = np.zeros((G, max_e, 2), dtype=np.int32)
+        weights = np.zeros((G, max_e), dtype=np.int32)
+        counts = np.zeros(G, dtype=np.int32)
+        _cabi.check(self._lib.sy_read_graph_edges(self._handle, links.ctypes.data, weights.ctypes.data, counts.ctypes.data,
+                                                  max_e, self._stream()))
+        self.graphs = [GraphSpec(N, links[g, : counts[g]], weights[g, : counts[g]]) for g in range(G)]
+        self.actual_num_edges = int(counts[0])
+        self.generation_attempts = attempts
+        self._gen["generation"] = int(generation)
+        row_ptr, col, wgt, _ = pack_csr(self.graphs)
+        self._csr = (row_ptr, col, wgt)
+        self._static = None
+
+    def regenerate_graphs(self, generation: Optional[int] = None):
+        """Refresh a device-sampled pool with a new generation of graphs (the reference draws a new graph on every
+        reset, yard.py:87-101; here the whole pool is redrawn between rollouts).  Every env must be reset afterwards."""
+        if not self._device_pool:
+            raise _cabi.SyError("regenerate_graphs needs graphs='device'")
+        with torch.cuda.device(self.device):
+            self._generate_on_device(self._gen["generation"] + 1 if generation is None else int(generation))
+        self._is_reset = False
 
     # ------------------------------------------------------------------ observations
     def _static_tensors(self):

@@ -770,3 +770,60 @@ def test_million_envs_config5_scale(torch_cuda):
         assert float((env.belief_map[sl].sum(dim=1) - 1).abs().max()) < 1e-5
     assert float(env.node_features.sum()) == float((P + (env.mrx_revealed >= 0).float()).sum())
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,E,G,P", [(50, 110, 24, 3), (200, 400, 6, 6), (12, 11, 5, 2), (33, 80, 40, 4)])
+def test_device_graph_sampler_matches_oracle(torch_cuda, tables, N, E, G, P):
+    """the pool sampled ON THE DEVICE (sy_generate_graphs: ConnectedGraph.sample + the edge-count
+    resample loop, graph_layout.py:9-80 / yard.py:67-101) is, draw for draw, the oracle's counter-based sampler
+    (whose distribution is checked against the reference sampler in tests/test_graph_sampler.py): same edge lists in
+    the reference's order, same attempts, same dense weights / APSP; a rollout on the sampled graphs (belief on, so the
+    device-built neighbour lists are exercised) matches the oracle; pool refresh and pool sharding reproduce."""
+    pkg = _pkg()
+    seed, B = 21, 70
+    kw = dict(belief=True, reveal_interval=4, tolls=1)
+    env = pkg.BatchedScotlandYardEnv(B, P, 12, graph_nodes=N, graph_edges=E, graphs="device", num_graphs=G, seed=seed,
+                                     auto_reset=True, reward_mode="fp64", keep_reward64=True, reward_tables=tables, **kw)
+
+    def check_pool(e, generation, offset=0):
+        want_pool = so.philox_graph_pool(seed, len(e.graphs), N, E, generation=generation, graph_offset=offset)
+        for g, (got, want) in enumerate(zip(e.graphs, want_pool)):
+            assert np.array_equal(got.edge_links, want.edge_links), (generation, g)
+            assert np.array_equal(got.edges, want.edges), (generation, g)
+            W, D = e.graph_tables(g)
+            assert np.array_equal(W.astype(np.int64), want.weight_matrix()), (generation, g)
+            assert np.array_equal(D.astype(np.int64), want.apsp()), (generation, g)
+        assert len({len(g.edges) for g in e.graphs}) == 1
+        return want_pool
+
+    pool = check_pool(env, 0)
+    first_edges = len(pool[0].edges)
+    for g in range(1, G):  # attempts used per slot (yard.py:89-101)
+        assert env.generation_attempts[g] == so.philox_sample_graph(seed, g, 0, N, E, first_edges)[1]
+    for generation in (0, 1):
+        if generation:
+            env.regenerate_graphs()
+            pool = check_pool(env, generation)
+            with pytest.raises(pkg.SyError):
+                env.step(env.sample_actions())  # a refreshed pool needs a reset
+        ocfg = so.OracleConfig(num_police=P, agent_money=12, reward_mode="fp64", reveal_interval=4, toll=1, belief=True,
+                               exp_table=tables[0], cov_table=tables[1])
+        ob = so.OracleBatch.from_seed(ocfg, pool, B, seed=seed, auto_reset=True)
+        env.reset()
+        c = dict(kw=kw, mode="fp64")
+        _compare_state(env, ob, c, ("reset", generation))
+        for s in range(6):
+            acts = env.sample_actions(step_counter=s)
+            a_h = acts.cpu().numpy()
+            assert np.array_equal(a_h, ob.sample_actions(s))
+            env.step(acts)
+            want = ob.step(a_h)
+            _compare_out(env, want, c, ("out", generation, s))
+            _compare_state(env, ob, c, ("state", generation, s))
+    env.close()
+    if G >= 6:  # the second half of the pool as its own shard
+        half = pkg.BatchedScotlandYardEnv(8, P, 12, graph_nodes=N, graph_edges=E, graphs="device", num_graphs=G - G // 2,
+                                          seed=seed, graph_offset=G // 2)
+        check_pool(half, 0, offset=G // 2)
+        half.close()
