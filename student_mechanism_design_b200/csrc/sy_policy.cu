@@ -1,0 +1,674 @@
+// sy_policy.cu -- batched policy forward for the reference's two shipped agents, sm_100a.
+// C ABI: include/sy_policy.h.  Stand-alone: reads the env's state buffers and the graph pool through plain pointers.
+//
+// Reference code paths replaced (file:line under /root/reference):
+//   src/agent/gnn_agent.py:45-82     GNNAgent.select_action      -> sy_gnn_act_kernel (epsilon-greedy over valid moves)
+//   src/agent/gnn_agent.py:230-257   GNNModel.forward            -> q_at_node (2 x AntiSymmetricConv + ReLU, Linear)
+//   src/training/utils.py:151-211    create_graph_data           -> feature columns (SY_FEATURES_REFERENCE) / the env's
+//                                                                   node_features (SY_FEATURES_ENV), never materialised
+//   src/agent/mappo_agent.py:6-29    AgentPolicy.forward         -> sy_mappo_act_kernel (MLP + softmax)
+//   src/agent/mappo_agent.py:87-142  MappoAgent.select_action    -> sy_mappo_act_kernel (mask, renormalise, sample, log-prob)
+//   src/agent/mappo_agent.py:32-44   CentralCritic.forward       -> sy_mappo_values_kernel
+//
+// GNN design: the input features are one-hot columns (at most A non-zero rows of x), the graph is shared, and
+// epsilon-greedy only ever compares the Q values of an agent's VALID MOVES (its affordable neighbours).  So instead of
+// two dense message-passing layers over all N nodes per env and agent, every candidate move gets one lane that
+// evaluates Q at that node from its 2-hop in-neighbourhood: layer-1 rows are recomputed on the fly (a node nobody
+// "touches" has the constant row relu(eps * tanh(bias1))), layer 2 aggregates the in-neighbours' rows first and applies
+// the K x K matrices once (A (X Theta) = (A X) Theta).  Weights live in shared memory, K is padded to 4/8/16 so rows are
+// float4 broadcasts, everything is fp32 like the reference.  The dense [B, 2, N] Q tensor (training targets) comes from
+// the same per-node routine with lane = node.
+//
+// MAPPO design: one CTA per (128-env tile, agent): hidden layer into shared memory, then thread = action node keeps its
+// W2 row chunk in registers and walks the tile's rows (fp32 FMA-bound), logits tile in shared memory, one warp per row
+// for softmax / mask / renormalise / inverse-CDF sampling / log-prob.
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/sy_policy.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int GNN_WARPS = 8;
+enum { RNG_GNN_POLICY = 3, RNG_MAPPO_POLICY = 4 };
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) return fail(SY_POLICY_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));     \
+  } while (0)
+
+// Philox4x32-10, same counter layout as the env library (oracle/sy_oracle.py:philox4x32)
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+
+__device__ __forceinline__ float u01(unsigned w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }  // [0, 1), 24 bits
+
+// ---------------------------------------------------------------------------------------------
+// GNN
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int gnn_kp(int K) { return K <= 4 ? 4 : (K <= 8 ? 8 : 16); }
+__host__ __device__ constexpr int gnn_model_floats(int KP) { return 2 * (2 * KP * KP + KP) + KP + 4; }
+
+struct GnnParams {
+  SyPolicyGraphs g;
+  SyPolicyState st;
+  const float* params;  // [2][gnn_model_floats(KP)]
+  int K, feature_mode;
+  float conv_eps, eps_mrx, eps_police;
+  unsigned seed_lo, seed_hi, step;
+};
+
+template <int KP>
+struct ModelView {  // pointers into the shared-memory copy of one model
+  const float* WasT[2];
+  const float* ThT[2];
+  const float* bias[2];
+  const float* out_w;
+  const float* c1;  // relu(eps * tanh(bias1)): layer-1 row of a node no feature touches
+  float out_b;
+  __device__ ModelView(const float* m, const float* c1_) {
+    for (int c = 0; c < 2; ++c) {
+      WasT[c] = m + c * (2 * KP * KP + KP);
+      ThT[c] = WasT[c] + KP * KP;
+      bias[c] = ThT[c] + KP * KP;
+    }
+    out_w = m + 2 * (2 * KP * KP + KP);
+    out_b = out_w[KP];
+    c1 = c1_;
+  }
+};
+
+struct GraphView {
+  const int32_t* in_ptr;
+  const int32_t* in_src;
+  const float* in_coef;
+  const float* self_coef;
+};
+
+template <int KP>
+__device__ __forceinline__ void matvec_acc(float (&acc)[KP], const float (&x)[KP], const float* __restrict__ MT) {
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const float xk = x[k];
+    const float4* row = reinterpret_cast<const float4*>(MT + k * KP);
+#pragma unroll
+    for (int c4 = 0; c4 < KP / 4; ++c4) {
+      const float4 m = row[c4];
+      acc[4 * c4 + 0] = fmaf(xk, m.x, acc[4 * c4 + 0]);
+      acc[4 * c4 + 1] = fmaf(xk, m.y, acc[4 * c4 + 1]);
+      acc[4 * c4 + 2] = fmaf(xk, m.z, acc[4 * c4 + 2]);
+      acc[4 * c4 + 3] = fmaf(xk, m.w, acc[4 * c4 + 3]);
+    }
+  }
+}
+
+// layer-1 output row of node m: relu(x0 + eps * tanh(x0 Was^T + (A_hat x0) Theta^T + b)), x0 one-hot columns at colnode[]
+template <int KP>
+__device__ __forceinline__ void x1_at(const ModelView<KP>& mv, const GraphView& gv, const int* __restrict__ colnode, int m, float eps,
+                                      float (&x1)[KP]) {
+  float x0[KP], z[KP];
+  const float sc = __ldg(gv.self_coef + m);
+  bool touched = false;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    const bool here = colnode[k] == m;
+    x0[k] = here ? 1.0f : 0.0f;
+    z[k] = here ? sc : 0.0f;
+    touched |= here;
+  }
+  const int e0 = __ldg(gv.in_ptr + m), e1 = __ldg(gv.in_ptr + m + 1);
+  for (int e = e0; e < e1; ++e) {
+    const int s = __ldg(gv.in_src + e);
+    const float c = __ldg(gv.in_coef + e);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const bool from = colnode[k] == s;
+      z[k] += from ? c : 0.0f;
+      touched |= from;
+    }
+  }
+  if (!touched) {
+#pragma unroll
+    for (int k = 0; k < KP; ++k) x1[k] = mv.c1[k];
+    return;
+  }
+  float acc[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) acc[k] = mv.bias[0][k];
+  matvec_acc<KP>(acc, x0, mv.WasT[0]);
+  matvec_acc<KP>(acc, z, mv.ThT[0]);
+#pragma unroll
+  for (int k = 0; k < KP; ++k) x1[k] = fmaxf(x0[k] + eps * tanhf(acc[k]), 0.0f);
+}
+
+// Q value of node n (gnn_agent.py:249-257)
+template <int KP>
+__device__ __forceinline__ float q_at_node(const ModelView<KP>& mv, const GraphView& gv, const int* __restrict__ colnode, int n, float eps) {
+  float x1n[KP], z[KP], x1s[KP];
+  x1_at<KP>(mv, gv, colnode, n, eps, x1n);
+  const float sc = __ldg(gv.self_coef + n);
+#pragma unroll
+  for (int k = 0; k < KP; ++k) z[k] = sc * x1n[k];
+  const int e0 = __ldg(gv.in_ptr + n), e1 = __ldg(gv.in_ptr + n + 1);
+  for (int e = e0; e < e1; ++e) {
+    const float c = __ldg(gv.in_coef + e);
+    x1_at<KP>(mv, gv, colnode, __ldg(gv.in_src + e), eps, x1s);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) z[k] = fmaf(c, x1s[k], z[k]);
+  }
+  float acc[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) acc[k] = mv.bias[1][k];
+  matvec_acc<KP>(acc, x1n, mv.WasT[1]);
+  matvec_acc<KP>(acc, z, mv.ThT[1]);
+  float q = mv.out_b;
+#pragma unroll
+  for (int k = 0; k < KP; ++k) q = fmaf(fmaxf(x1n[k] + eps * tanhf(acc[k]), 0.0f), mv.out_w[k], q);
+  return q;
+}
+
+// shared memory: both models + their c1 rows, then per warp: colnode[KP], cstart[17], apos[16], amoney[16]
+template <int KP>
+struct GnnSmem {
+  float model[2][gnn_model_floats(KP)];
+  float c1[2][KP];
+  int colnode[GNN_WARPS][KP];
+  int cstart[GNN_WARPS][SY_POLICY_MAX_FEATURES + 1];
+  int apos[GNN_WARPS][SY_POLICY_MAX_FEATURES];
+  int amoney[GNN_WARPS][SY_POLICY_MAX_FEATURES];
+};
+
+template <int KP>
+__device__ __forceinline__ void gnn_load_models(const GnnParams& p, GnnSmem<KP>& sm) {
+  for (int i = threadIdx.x; i < 2 * gnn_model_floats(KP); i += blockDim.x) (&sm.model[0][0])[i] = __ldg(p.params + i);
+  __syncthreads();
+  if (threadIdx.x < 2 * KP) {
+    const int m = threadIdx.x / KP, k = threadIdx.x % KP;
+    const float b1 = sm.model[m][2 * KP * KP + k];
+    sm.c1[m][k] = fmaxf(0.0f + p.conv_eps * tanhf(b1), 0.0f);
+  }
+  __syncthreads();
+}
+
+// feature columns of env b: colnode[k] = node carrying column k, -2 = none (see SY_FEATURES_*)
+template <int KP>
+__device__ __forceinline__ void gnn_feature_columns(const GnnParams& p, int b, int lane, int* colnode) {
+  const int A = p.st.num_agents, N = p.g.num_nodes;
+  if (lane < KP) {
+    int node = -2;
+    const int rev = p.st.mrx_revealed ? p.st.mrx_revealed[b] : 0;
+    if (p.feature_mode == SY_FEATURES_ENV) {
+      if (lane < A && lane < p.K && !(lane == 0 && rev < 0)) node = p.st.pos[(size_t)b * A + lane];
+    } else {  // utils.py:176-199
+      if (lane == 0) node = rev < 0 ? N - 1 : p.st.pos[(size_t)b * A];  // numpy index -1 while MrX is hidden
+      else if (lane < A - 1 && lane < p.K) node = p.st.pos[(size_t)b * A + 1];  // range(number_of_agents - 1), always Polices_pos[0]
+    }
+    colnode[lane] = node;
+  }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_q_dense_kernel(const GnnParams p, float* __restrict__ q) {
+  __shared__ __align__(16) GnnSmem<KP> sm;
+  gnn_load_models<KP>(p, sm);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * GNN_WARPS + w;
+  if (b >= p.st.num_envs) return;
+  const int N = p.g.num_nodes;
+  gnn_feature_columns<KP>(p, b, lane, sm.colnode[w]);
+  __syncwarp();
+  const int g = p.st.graph_id[b];
+  const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
+                     p.g.self_coef + (size_t)g * N};
+  for (int m = 0; m < 2; ++m) {
+    const ModelView<KP> mv(sm.model[m], sm.c1[m]);
+    for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_at_node<KP>(mv, gv, sm.colnode[w], n, p.conv_eps);
+  }
+}
+
+__device__ __forceinline__ unsigned ordered_key(float f) {  // monotone float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+template <int KP>
+__global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_act_kernel(const GnnParams p, int64_t* __restrict__ actions, float* __restrict__ q_taken) {
+  __shared__ __align__(16) GnnSmem<KP> sm;
+  gnn_load_models<KP>(p, sm);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * GNN_WARPS + w;
+  if (b >= p.st.num_envs) return;
+  const int N = p.g.num_nodes, A = p.st.num_agents;
+  gnn_feature_columns<KP>(p, b, lane, sm.colnode[w]);
+  const int g = p.st.graph_id[b];
+  const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
+  const int32_t* col = p.g.col + (size_t)g * p.g.nnz_stride;
+  const int32_t* wt = p.g.w + (size_t)g * p.g.nnz_stride;
+  const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
+                     p.g.self_coef + (size_t)g * N};
+  // lane a < A owns agent a: its node, budget, neighbour range, number of valid moves, explore decision
+  int my_pos = 0, my_money = 0, r0 = 0, deg = 0, n_valid = 0;
+  if (lane < A) {
+    my_pos = p.st.pos[(size_t)b * A + lane];
+    my_money = p.st.money[(size_t)b * A + lane];
+    r0 = __ldg(rp + my_pos);
+    deg = __ldg(rp + my_pos + 1) - r0;
+    for (int k = 0; k < deg; ++k) n_valid += (__ldg(wt + r0 + k) + p.st.toll <= my_money);
+    sm.apos[w][lane] = r0;
+    sm.amoney[w][lane] = my_money;
+  }
+  int incl = deg;  // inclusive prefix of the degrees over lanes -> candidate ranges
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane < A) sm.cstart[w][lane + 1] = incl;
+  if (lane == 0) sm.cstart[w][0] = 0;
+  const int C = __shfl_sync(FULL, incl, A - 1);
+  bool explore = false;
+  int target = 0;
+  if (lane < A) {
+    const uint4 r = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_GNN_POLICY, (unsigned)lane), make_uint2(p.seed_lo, p.seed_hi));
+    explore = u01(r.x) < (lane == 0 ? p.eps_mrx : p.eps_police);  // np.random.rand() <= epsilon (gnn_agent.py:69)
+    target = (int)__umulhi(r.y, (unsigned)n_valid);                // np.random.choice(valid_actions)
+  }
+  __syncwarp();
+  int seen = 0;             // lane a: valid candidates of agent a in earlier chunks
+  int best_node = -1;       // lane a: running choice
+  unsigned best_key = 0;
+  float best_q = CUDART_NAN_F;
+  const ModelView<KP> mv0(sm.model[0], sm.c1[0]), mv1(sm.model[1], sm.c1[1]);
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    const int c = c0 + lane;
+    int a = -1, node = -1;
+    bool valid = false;
+    if (c < C) {
+      a = 0;
+      while (c >= sm.cstart[w][a + 1]) ++a;
+      const int k = sm.apos[w][a] + (c - sm.cstart[w][a]);
+      node = __ldg(col + k);
+      valid = __ldg(wt + k) + p.st.toll <= sm.amoney[w][a];
+    }
+    const unsigned explore_mask = __ballot_sync(FULL, explore);
+    float qv = 0.0f;
+    if (valid && !((explore_mask >> a) & 1u)) qv = q_at_node<KP>(a == 0 ? mv0 : mv1, gv, sm.colnode[w], node, p.conv_eps);
+    const unsigned key = valid ? ordered_key(qv) : 0u;
+    __syncwarp();
+    const int a_lo = __shfl_sync(FULL, a, 0), a_hi = __shfl_sync(FULL, a, min(31, C - c0 - 1));
+    for (int aa = a_lo; aa <= a_hi; ++aa) {  // agents with candidates in this chunk (warp-uniform)
+      const unsigned vm = __ballot_sync(FULL, valid && a == aa);
+      const bool ex = (explore_mask >> aa) & 1u;
+      const int seen_a = __shfl_sync(FULL, seen, aa), target_a = __shfl_sync(FULL, target, aa);
+      int pick_lane = -1;
+      unsigned kmax = 0;
+      if (ex) {  // the target-th valid candidate
+        const int rank = seen_a + __popc(vm & ((1u << lane) - 1u));
+        const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && rank == target_a);
+        if (hit) pick_lane = __ffs(hit) - 1;
+      } else if (vm) {
+        kmax = __reduce_max_sync(FULL, ((vm >> lane) & 1u) ? key : 0u);
+        const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && key == kmax);
+        pick_lane = __ffs(hit) - 1;  // first maximum (np.argmax, gnn_agent.py:75)
+      }
+      const int pn = __shfl_sync(FULL, node, max(pick_lane, 0));
+      const float pq = __shfl_sync(FULL, qv, max(pick_lane, 0));
+      if (lane == aa) {
+        if (pick_lane >= 0 && (ex || best_node < 0 || kmax > best_key)) {
+          best_node = pn;
+          best_key = kmax;
+          best_q = ex ? CUDART_NAN_F : pq;
+        }
+        seen += __popc(vm);
+      }
+    }
+  }
+  if (lane < A) {
+    actions[(size_t)b * A + lane] = best_node;  // -1: no valid move (DEFAULT_ACTION)
+    if (q_taken) q_taken[(size_t)b * A + lane] = best_q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MAPPO
+// ---------------------------------------------------------------------------------------------
+constexpr int MP_ROWS = 128;     // envs per CTA
+constexpr int MP_THREADS = 256;
+constexpr int MP_HC = 32;        // hidden units per register chunk
+
+struct MappoParams {
+  SyPolicyGraphs g;
+  SyPolicyState st;
+  const float* obs;
+  const float* params;
+  int obs_size, H, HP, policy_floats;
+  int policy_of_agent[SY_POLICY_MAX_FEATURES];
+  unsigned seed_lo, seed_hi, step;
+};
+
+__global__ void __launch_bounds__(MP_THREADS) sy_mappo_act_kernel(const MappoParams p, int64_t* __restrict__ actions,
+                                                                   float* __restrict__ log_probs, float* __restrict__ probs_out) {
+  extern __shared__ __align__(16) float mp_smem[];
+  const int N = p.g.num_nodes, A = p.st.num_agents, H = p.H, HP = p.HP, D = p.obs_size;
+  float* hid = mp_smem;                    // [MP_ROWS][HP]
+  float* logits = mp_smem + MP_ROWS * HP;  // [MP_ROWS][N]
+  const int a = blockIdx.y, row0 = blockIdx.x * MP_ROWS;
+  const int nrows = min(MP_ROWS, p.st.num_envs - row0);
+  const float* pol = p.params + (size_t)p.policy_of_agent[a] * p.policy_floats;
+  const float* W1 = pol;                     // [H, D]
+  const float* b1 = W1 + (size_t)H * D;      // [H]
+  const float* W2 = b1 + H;                  // [N, H]
+  const float* b2 = W2 + (size_t)N * H;      // [N]
+  const int tid = threadIdx.x;
+  // hidden layer: relu(W1 obs + b1)
+  for (int i = tid; i < MP_ROWS * HP; i += MP_THREADS) {
+    const int r = i / HP, h = i - r * HP;
+    float v = 0.0f;
+    if (r < nrows && h < H) {
+      const float* x = p.obs + ((size_t)(row0 + r) * A + a) * D;
+      v = __ldg(b1 + h);
+      for (int o = 0; o < D; ++o) v = fmaf(__ldg(W1 + (size_t)h * D + o), __ldg(x + o), v);
+      v = fmaxf(v, 0.0f);
+    }
+    hid[i] = v;
+  }
+  __syncthreads();
+  // logits: thread = action node, W2 row chunk in registers, walk the rows
+  for (int n = tid; n < N; n += MP_THREADS) {
+    const float bias = __ldg(b2 + n);
+    for (int hc = 0; hc < HP; hc += MP_HC) {
+      float wreg[MP_HC];
+#pragma unroll
+      for (int j = 0; j < MP_HC; ++j) wreg[j] = (hc + j < H) ? __ldg(W2 + (size_t)n * H + hc + j) : 0.0f;
+#pragma unroll 2
+      for (int r = 0; r < nrows; ++r) {
+        const float4* hv = reinterpret_cast<const float4*>(hid + r * HP + hc);
+        float acc = hc == 0 ? bias : logits[r * N + n];
+#pragma unroll
+        for (int j4 = 0; j4 < MP_HC / 4; ++j4) {
+          const float4 h4 = hv[j4];
+          acc = fmaf(wreg[4 * j4 + 0], h4.x, acc);
+          acc = fmaf(wreg[4 * j4 + 1], h4.y, acc);
+          acc = fmaf(wreg[4 * j4 + 2], h4.z, acc);
+          acc = fmaf(wreg[4 * j4 + 3], h4.w, acc);
+        }
+        logits[r * N + n] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  // softmax, mask, renormalise, sample, log-prob: warp per row (mappo_agent.py:102-142)
+  const int lane = tid & 31, w = tid >> 5;
+  for (int r = w; r < nrows; r += MP_THREADS / 32) {
+    const int b = row0 + r;
+    float* lr = logits + r * N;
+    float mx = -CUDART_INF_F;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, lr[n]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    float Z = 0.0f;
+    for (int n = lane; n < N; n += 32) {
+      const float e = expf(lr[n] - mx);
+      lr[n] = e;
+      Z += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL, Z, o);
+    __syncwarp();
+    const int g = p.st.graph_id[b];
+    const int pos = p.st.pos[(size_t)b * A + a], money = p.st.money[(size_t)b * A + a];
+    const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
+    const int r0 = __ldg(rp + pos), deg = __ldg(rp + pos + 1) - r0;
+    const int32_t* col = p.g.col + (size_t)g * p.g.nnz_stride + r0;
+    const int32_t* wt = p.g.w + (size_t)g * p.g.nnz_stride + r0;
+    // masked softmax mass over the valid moves
+    float Sv = 0.0f;
+    int nv = 0;
+    for (int k = lane; k < deg; k += 32) {
+      if (__ldg(wt + k) + p.st.toll <= money) {
+        Sv += lr[__ldg(col + k)] / Z;
+        nv += 1;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Sv += __shfl_xor_sync(FULL, Sv, o);
+      nv += __shfl_xor_sync(FULL, nv, o);
+    }
+    // mode 0: softmax * mask / (sum + 1e-8); 1: uniform over the mask; 2: uniform over all nodes
+    const int mode = Sv > 1e-8f ? 0 : (nv > 0 ? 1 : 2);
+    const uint4 rnd = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_MAPPO_POLICY, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
+    const float u = u01(rnd.x);
+    int action;
+    float pa, total;
+    if (mode == 2) {
+      action = min((int)(u * (float)N), N - 1);
+      pa = 1.0f / (float)N;
+      total = 1.0f;  // N * (1/N) up to rounding; Categorical renormalises
+      if (probs_out)
+        for (int n = lane; n < N; n += 32) probs_out[((size_t)b * A + a) * N + n] = pa;
+    } else {
+      // current_probs over the valid moves (ascending), Categorical's own normalisation, inverse CDF
+      if (probs_out)
+        for (int n = lane; n < N; n += 32) probs_out[((size_t)b * A + a) * N + n] = 0.0f;
+      __syncwarp();
+      total = 0.0f;
+      for (int k = lane; k < deg; k += 32) {
+        if (__ldg(wt + k) + p.st.toll <= money) {
+          const float pk = mode == 0 ? (lr[__ldg(col + k)] / Z) / (Sv + 1e-8f) : 1.0f / (float)nv;
+          total += pk;
+          if (probs_out) probs_out[((size_t)b * A + a) * N + __ldg(col + k)] = pk;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
+      // sequential inverse CDF in ascending node order (uniform across lanes)
+      const float thr = u * total;
+      float cum = 0.0f;
+      action = -1;
+      pa = 0.0f;
+      int last = -1;
+      float plast = 0.0f;
+      for (int k = 0; k < deg; ++k) {
+        if (__ldg(wt + k) + p.st.toll <= money) {
+          const float pk = mode == 0 ? (lr[__ldg(col + k)] / Z) / (Sv + 1e-8f) : 1.0f / (float)nv;
+          cum += pk;
+          last = __ldg(col + k);
+          plast = pk;
+          if (action < 0 && thr < cum) {
+            action = last;
+            pa = pk;
+          }
+        }
+      }
+      if (action < 0) {  // rounding at the top of the CDF
+        action = last;
+        pa = plast;
+      }
+    }
+    if (lane == 0) {
+      actions[(size_t)b * A + a] = action;
+      // Categorical(probs).log_prob: log(clamp(p / sum p, eps, 1 - eps)) (torch.distributions.utils.probs_to_logits)
+      const float eps = 1.1920928955078125e-07f;
+      log_probs[(size_t)b * A + a] = logf(fminf(fmaxf(pa / total, eps), 1.0f - eps));
+    }
+    __syncwarp();
+  }
+}
+
+// CentralCritic: thread per row
+__global__ void sy_mappo_values_kernel(const float* __restrict__ x, int M, int D, int H, const float* __restrict__ params, float* __restrict__ out) {
+  extern __shared__ float cw[];  // W1 [H, D], b1 [H], W2 [H], b2
+  const int total = H * D + 2 * H + 1;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) cw[i] = __ldg(params + i);
+  __syncthreads();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= M) return;
+  const float* W1 = cw;
+  const float* b1 = cw + H * D;
+  const float* W2 = b1 + H;
+  float v = W2[H];
+  const float* xr = x + (size_t)r * D;
+  for (int h = 0; h < H; ++h) {
+    float s = b1[h];
+    for (int o = 0; o < D; ++o) s = fmaf(W1[h * D + o], __ldg(xr + o), s);
+    v = fmaf(fmaxf(s, 0.0f), W2[h], v);
+  }
+  out[r] = v;
+}
+
+int check_common(const SyPolicyGraphs* g, const SyPolicyState* st) {
+  if (!g || !st) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL graphs / state");
+  if (g->num_graphs <= 0 || g->num_nodes <= 1 || !g->row_ptr || !g->col || !g->w) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad graph pool");
+  if (st->num_envs <= 0 || st->num_agents < 2 || st->num_agents > SY_POLICY_MAX_FEATURES) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad batch shape");
+  if (!st->pos || !st->money || !st->graph_id) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL state members");
+  return SY_POLICY_OK;
+}
+
+int fill_gnn(const SyPolicyGraphs* g, const SyPolicyState* st, const float* params, int K, float conv_eps, int mode, GnnParams& p) {
+  if (int rc = check_common(g, st)) return rc;
+  if (!g->in_ptr || !g->in_src || !g->in_coef || !g->self_coef) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL in-edge lists");
+  if (!params || K < 1 || K > SY_POLICY_MAX_FEATURES) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad GNN parameters (K = %d)", K);
+  if (mode != SY_FEATURES_ENV && mode != SY_FEATURES_REFERENCE) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad feature mode");
+  std::memset(&p, 0, sizeof(p));
+  p.g = *g;
+  p.st = *st;
+  p.params = params;
+  p.K = K;
+  p.feature_mode = mode;
+  p.conv_eps = conv_eps;
+  return SY_POLICY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sy_policy_abi_version(void) { return SY_POLICY_ABI_VERSION; }
+const char* sy_policy_last_error(void) { return g_err; }
+long long sy_policy_launch_count(void) { return g_launches.load(); }
+
+int32_t sy_gnn_param_count(int32_t K) { return (K < 1 || K > SY_POLICY_MAX_FEATURES) ? 0 : gnn_model_floats(gnn_kp(K)); }
+
+int sy_gnn_q_values(const SyPolicyGraphs* graphs, const SyPolicyState* state, const float* params, int32_t K, float conv_epsilon,
+                    int32_t feature_mode, float* q, sy_policy_stream_t stream) {
+  GnnParams p;
+  if (int rc = fill_gnn(graphs, state, params, K, conv_epsilon, feature_mode, p)) return rc;
+  if (!q) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL q");
+  const unsigned grid = (unsigned)((state->num_envs + GNN_WARPS - 1) / GNN_WARPS);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (gnn_kp(K)) {
+    case 4: sy_gnn_q_dense_kernel<4><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
+    case 8: sy_gnn_q_dense_kernel<8><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
+    default: sy_gnn_q_dense_kernel<16><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
+  }
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_POLICY_OK;
+}
+
+int sy_gnn_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const float* params, int32_t K, float conv_epsilon,
+               int32_t feature_mode, float epsilon_mrx, float epsilon_police, uint64_t seed, uint32_t step_counter, int64_t* actions,
+               float* q_taken, sy_policy_stream_t stream) {
+  GnnParams p;
+  if (int rc = fill_gnn(graphs, state, params, K, conv_epsilon, feature_mode, p)) return rc;
+  if (!actions) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL actions");
+  p.eps_mrx = epsilon_mrx;
+  p.eps_police = epsilon_police;
+  p.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
+  p.seed_hi = (unsigned)(seed >> 32);
+  p.step = step_counter;
+  const unsigned grid = (unsigned)((state->num_envs + GNN_WARPS - 1) / GNN_WARPS);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (gnn_kp(K)) {
+    case 4: sy_gnn_act_kernel<4><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
+    case 8: sy_gnn_act_kernel<8><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
+    default: sy_gnn_act_kernel<16><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
+  }
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_POLICY_OK;
+}
+
+int32_t sy_mappo_param_count(int32_t obs_size, int32_t hidden, int32_t num_nodes) {
+  if (obs_size < 1 || hidden < 1 || num_nodes < 1) return 0;
+  return hidden * obs_size + hidden + num_nodes * hidden + num_nodes;
+}
+
+int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const float* obs, int32_t obs_size, int32_t hidden,
+                 const float* params, const int32_t* policy_of_agent, uint64_t seed, uint32_t step_counter, int64_t* actions,
+                 float* log_probs, float* probs, sy_policy_stream_t stream) {
+  if (int rc = check_common(graphs, state)) return rc;
+  if (!obs || !params || !policy_of_agent || !actions || !log_probs) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL MAPPO arguments");
+  if (obs_size < 1 || hidden < 1 || hidden > 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad MAPPO layer sizes");
+  MappoParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.g = *graphs;
+  p.st = *state;
+  p.obs = obs;
+  p.params = params;
+  p.obs_size = obs_size;
+  p.H = hidden;
+  p.HP = (hidden + MP_HC - 1) / MP_HC * MP_HC;
+  p.policy_floats = sy_mappo_param_count(obs_size, hidden, graphs->num_nodes);
+  for (int a = 0; a < state->num_agents; ++a) {
+    if (policy_of_agent[a] < 0) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "negative policy index");
+    p.policy_of_agent[a] = policy_of_agent[a];
+  }
+  p.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
+  p.seed_hi = (unsigned)(seed >> 32);
+  p.step = step_counter;
+  const size_t smem = (size_t)MP_ROWS * (p.HP + graphs->num_nodes) * sizeof(float);
+  if (smem > 220 * 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "hidden + num_nodes too large for the MAPPO kernel's shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(sy_mappo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 grid((unsigned)((state->num_envs + MP_ROWS - 1) / MP_ROWS), (unsigned)state->num_agents);
+  sy_mappo_act_kernel<<<grid, MP_THREADS, smem, (cudaStream_t)stream>>>(p, actions, log_probs, probs);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_POLICY_OK;
+}
+
+int sy_mappo_values(const float* global_obs, int32_t num_rows, int32_t obs_size, int32_t hidden, const float* params, float* values,
+                    sy_policy_stream_t stream) {
+  if (!global_obs || !params || !values || num_rows <= 0 || obs_size < 1 || hidden < 1)
+    return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad critic arguments");
+  const size_t smem = (size_t)(hidden * obs_size + 2 * hidden + 1) * sizeof(float);
+  if (smem > 200 * 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "critic too large for shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(sy_mappo_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sy_mappo_values_kernel<<<(unsigned)((num_rows + 255) / 256), 256, smem, (cudaStream_t)stream>>>(global_obs, num_rows, obs_size, hidden, params, values);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_POLICY_OK;
+}
+
+}  // extern "C"

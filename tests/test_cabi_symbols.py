@@ -9,8 +9,8 @@ import pytest
 from conftest import ROOT
 
 
-def _declared_functions():
-    text = open(os.path.join(ROOT, "include", "sy_env.h")).read()
+def _declared_functions(header="sy_env.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(sy_[a-z0-9_]+)\s*\(", text)))
 
@@ -33,6 +33,23 @@ def test_library_exports_every_declared_symbol():
     lib.sy_abi_version.restype = ctypes.c_int
     assert lib.sy_abi_version() == _cabi.SY_ABI_VERSION
     assert ctypes.sizeof(_cabi.SyConfig) == 160
+
+
+def test_policy_header_and_library_agree():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from student_mechanism_design_b200 import _policy_cabi
+
+    declared = _declared_functions("sy_policy.h")
+    assert declared == sorted(_policy_cabi.SIGNATURES)
+    lib = ctypes.CDLL(_policy_cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.sy_policy_abi_version.restype = ctypes.c_int
+    assert lib.sy_policy_abi_version() == _policy_cabi.SY_POLICY_ABI_VERSION
+    lib.sy_gnn_param_count.restype = ctypes.c_int32
+    assert lib.sy_gnn_param_count(7) == 2 * (2 * 64 + 8) + 8 + 4 and lib.sy_gnn_param_count(17) == 0
 
 
 def test_no_cpu_fallback():

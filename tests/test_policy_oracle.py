@@ -1,0 +1,77 @@
+"""The MAPPO restatement in oracle/policy_oracle.py against tests/golden/mappo.npz, which was recorded from the
+UNMODIFIED reference modules (oracle/gen_policy_golden.py; src/agent/mappo_agent.py:6-44, 87-142): the masked,
+renormalised distribution incl. its fall-back branches, Categorical's log-prob of the reference's sampled action,
+the central critic.  Plus sanity properties of the GNN restatement (parity unpinned: torch_geometric is absent)."""
+import os
+
+import numpy as np
+
+from conftest import ROOT
+from oracle import policy_oracle as po
+from oracle import sy_oracle as so
+
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "mappo.npz"))
+
+
+def _policy_sd(ci, pid):
+    return {k: GOLD[f"c{ci}_p{pid}_{k}"] for k in ("actor.0.weight", "actor.0.bias", "actor.2.weight", "actor.2.bias")}
+
+
+def test_mappo_distribution_and_log_prob_match_reference():
+    branches = set()
+    for ci, (n_agents, obs_size, hidden, n_nodes) in enumerate(GOLD["cases"].tolist()):
+        for t in range(len(GOLD[f"c{ci}_obs"])):
+            sd = _policy_sd(ci, int(GOLD[f"c{ci}_pid"][t]))
+            mask, want = GOLD[f"c{ci}_mask"][t], GOLD[f"c{ci}_probs"][t]
+            got = po.mappo_probs(GOLD[f"c{ci}_obs"][t], sd, mask, dtype=np.float32)
+            np.testing.assert_allclose(got, want, rtol=2e-5, atol=1e-9)
+            a = int(GOLD[f"c{ci}_action"][t])
+            np.testing.assert_allclose(po.categorical_log_prob(got, a, np.float32), GOLD[f"c{ci}_logp"][t], rtol=2e-5, atol=2e-6)
+            if mask.sum() == 0:
+                branches.add("no mask")
+                assert np.allclose(want, 1.0 / n_nodes)
+            elif np.allclose(want[mask > 0], 1.0 / mask.sum()) and mask.sum() > 1:
+                branches.add("uniform over mask")
+            else:
+                branches.add("softmax")
+            assert want[mask == 0].sum() == 0 or mask.sum() == 0
+    assert branches == {"no mask", "uniform over mask", "softmax"}
+
+
+def test_critic_matches_reference():
+    for ci in range(len(GOLD["cases"])):
+        sd = {k: GOLD[f"c{ci}_{k}"] for k in ("critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias")}
+        got = [po.critic_value(x, sd) for x in GOLD[f"c{ci}_gobs"]]
+        np.testing.assert_allclose(got, GOLD[f"c{ci}_values"], rtol=1e-5, atol=1e-6)
+
+
+def test_mappo_sampler_follows_the_distribution():
+    p = np.zeros(30, dtype=np.float32)
+    p[[3, 7, 21]] = [0.2, 0.5, 0.3]
+    draws = np.bincount([po.mappo_sample(p, 5, e, 0, 1) for e in range(4000)], minlength=30)
+    assert set(np.nonzero(draws)[0]) == {3, 7, 21}
+    np.testing.assert_allclose(draws[[3, 7, 21]] / 4000.0, [0.2, 0.5, 0.3], atol=0.03)
+
+
+def test_gnn_restatement_properties():
+    rng = np.random.default_rng(0)
+    g = so.philox_sample_graph_once(1, 0, 0, 0, 20, 35)
+    K = 4
+    sd = {"conv1.W": rng.normal(size=(K, K)), "conv1.bias": rng.normal(size=K) * 0.1, "conv1.phi.lin.weight": rng.normal(size=(K, K)),
+          "conv2.W": rng.normal(size=(K, K)), "conv2.bias": rng.normal(size=K) * 0.1, "conv2.phi.lin.weight": rng.normal(size=(K, K)),
+          "output_layer.weight": rng.normal(size=(1, K)), "output_layer.bias": rng.normal(size=1)}
+    x = po.graph_features(po.FEATURES_ENV, [3, 5, 9, 11], 3, 20, K)
+    assert x.sum() == 4 and x[3, 0] == 1 and x[11, 3] == 1
+    assert po.graph_features(po.FEATURES_ENV, [3, 5, 9, 11], -1, 20, K)[:, 0].sum() == 0
+    xr = po.graph_features(po.FEATURES_REFERENCE, [3, 5, 9, 11], -1, 20, K)
+    assert xr[19, 0] == 1 and xr[5, 1] == 1 and xr[5, 2] == 1 and xr[:, 3].sum() == 0  # utils.py:176-199 as written
+    q = po.gnn_forward(x, g.edge_links, sd)
+    assert q.shape == (20,) and np.isfinite(q).all()
+    # a symmetric W has no antisymmetric part: W - W^T = 0, only the -gamma damping and the GCN term remain
+    sd2 = dict(sd)
+    sd2["conv1.W"] = sd["conv1.W"] + sd["conv1.W"].T
+    sd3 = dict(sd)
+    sd3["conv1.W"] = np.zeros((K, K))
+    np.testing.assert_allclose(po.gnn_forward(x, g.edge_links, sd2), po.gnn_forward(x, g.edge_links, sd3), rtol=1e-12)
+    # messages follow the stored edge direction only: reversing every edge changes the result
+    assert not np.allclose(q, po.gnn_forward(x, g.edge_links[:, ::-1], sd))
