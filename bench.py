@@ -38,6 +38,9 @@ WORKLOADS = {
                desc="200-node graph, 6 police, budgets+tolls, 65536 envs per GPU, belief_map on, reveal every 5"),
     "c4": dict(N=1000, E=2000, P=6, money=20, toll=1, belief=True, reveal=5, B=32768,
                desc="1000-node synthetic random graph, 6 police, 32768 envs per GPU (262144 over 8)"),
+    # BASELINE config 5: the policy forward of the reference's agents in the loop (--policy gnn | mappo, default gnn)
+    "c5": dict(N=200, E=400, P=6, money=20, toll=1, belief=True, reveal=5, B=131072, policy="gnn",
+               desc="GNN/MAPPO policy rollout, 200-node graph, 6 police, 131072 envs per GPU (1M over 8), belief_map on"),
 }
 METRIC, UNIT = "batched_env_steps_per_sec", "env-steps/s"
 
@@ -223,6 +226,35 @@ def run_cuda_arm(args, wl):
     actions = torch.empty(B, A, dtype=torch.int64, device=dev)
     K, W = args.steps, args.warmup
     sampler = ClockSampler(local)
+    # the policy that picks the actions: the on-device random-valid sampler (configs 2-4) or the batched forward of
+    # the reference's agents (config 5; random-init weights of the reference architectures, epsilon-greedy / sampling)
+    policy = args.policy or wl.get("policy", "random")
+    plib = None
+    if policy == "gnn":
+        from student_mechanism_design_b200 import GNNPolicy, _policy_cabi
+
+        plib = _policy_cabi.load_library()
+        gnn = GNNPolicy(env, seed=0)
+
+        def choose(counter):
+            gnn.act(args.epsilon, args.epsilon, step_counter=counter, out=actions)
+        policy_desc = f"GNNAgent x2 (2 x AntiSymmetricConv + Linear, K={A}), epsilon-greedy eps={args.epsilon}, fused sy_gnn_act"
+    elif policy == "mappo":
+        from student_mechanism_design_b200 import MappoPolicy, _policy_cabi
+
+        plib = _policy_cabi.load_library()
+        mappo = MappoPolicy(env, obs_size=A, hidden_size=64, seed=0)
+
+        def choose(counter):
+            obs = (env.pos.float() / N).unsqueeze(1).expand(B, A, A).contiguous()  # all agents' nodes, obs_size = A
+            a, _ = mappo.act(obs, step_counter=counter)
+            actions.copy_(a)
+        policy_desc = f"MappoAgent actors (Linear({A},64)-ReLU-Linear(64,{N})-softmax, one per agent), masked sampling, fused sy_mappo_act"
+    else:
+        def choose(counter):
+            env.sample_actions(out=actions, step_counter=counter)
+        policy_desc = "on-device Philox random valid"
+    py_loop = args.python_loop or policy != "random"
 
     def barrier():
         if dist is not None:
@@ -239,17 +271,17 @@ def run_cuda_arm(args, wl):
     # ---- device-resident throughput (`value`)
     counter = 0
     for _ in range(W):
-        env.sample_actions(out=actions, step_counter=counter)
+        choose(counter)
         env.step(actions)
         counter += 1
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.active = True
-    launches0 = lib.sy_launch_count()
+    launches0 = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0)
     ev0.record()
-    if args.python_loop:
+    if py_loop:
         for k in range(K):
-            env.sample_actions(out=actions, step_counter=counter)
+            choose(counter)
             env.step(actions)
             counter += 1
     else:  # the K steps are issued by one C-ABI call (sy_rollout_random): no Python between steps
@@ -259,24 +291,27 @@ def run_cuda_arm(args, wl):
     ev1.record()
     barrier()
     sampler.active = False
-    launches = lib.sy_launch_count() - launches0
+    launches = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0) - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     value = world * B * K / (ms_total * 1e-3)
 
     # ---- duration of the sy_step call alone (its two kernels), CUDA events around every call, for the roofline
     Kk = min(K, 300)
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kk)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(Kk)]
     barrier()
     sampler.active = True
     for k in range(Kk):
-        env.sample_actions(out=actions, step_counter=counter)
+        kev[k][2].record()
+        choose(counter)
         kev[k][0].record()
         env.step(actions)
         kev[k][1].record()
         counter += 1
     barrier()
     sampler.active = False
-    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in kev)
+    policy_ms = statistics.mean(c.elapsed_time(a) for a, _, c in kev)
 
     # ---- end to end through the host-buffer API
     Ke = max(3, min(K, args.e2e_steps))
@@ -321,7 +356,7 @@ def run_cuda_arm(args, wl):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
-                       "envs_per_gpu": B, "global_envs": world * B, "policy": "on-device Philox random valid", "loop": "python" if args.python_loop else "sy_rollout_random (C)",
+                       "envs_per_gpu": B, "global_envs": world * B, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": "python" if py_loop else "sy_rollout_random (C)",
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -351,6 +386,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype) instead of int32")
+    ap.add_argument("--policy", default=None, choices=["random", "gnn", "mappo"],
+                    help="who picks the actions (default: the workload's; c5 = gnn)")
+    ap.add_argument("--epsilon", type=float, default=0.05, help="exploration rate of the GNN agents")
     ap.add_argument("--python-loop", action="store_true", help="issue every step from Python instead of sy_rollout_random")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
