@@ -88,24 +88,13 @@ struct GnnParams {
   unsigned seed_lo, seed_hi, step;
 };
 
+// model layout in shared memory (floats): conv c at c * CONV: WasT [KP][KP], ThT [KP][KP], bias [KP]; then out_w [KP], out_b
 template <int KP>
-struct ModelView {  // pointers into the shared-memory copy of one model
-  const float* WasT[2];
-  const float* ThT[2];
-  const float* bias[2];
-  const float* out_w;
-  const float* c1;  // relu(eps * tanh(bias1)): layer-1 row of a node no feature touches
-  float out_b;
-  __device__ ModelView(const float* m, const float* c1_) {
-    for (int c = 0; c < 2; ++c) {
-      WasT[c] = m + c * (2 * KP * KP + KP);
-      ThT[c] = WasT[c] + KP * KP;
-      bias[c] = ThT[c] + KP * KP;
-    }
-    out_w = m + 2 * (2 * KP * KP + KP);
-    out_b = out_w[KP];
-    c1 = c1_;
-  }
+struct Lay {
+  static constexpr int CONV = 2 * KP * KP + KP;
+  static constexpr int WAS = 0, TH = KP * KP, BIAS = 2 * KP * KP;
+  static constexpr int OUT_W = 2 * CONV, OUT_B = 2 * CONV + KP;
+  static constexpr int MF = gnn_model_floats(KP);
 };
 
 struct GraphView {
@@ -115,144 +104,163 @@ struct GraphView {
   const float* self_coef;
 };
 
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the fast exp / divide units: |error| ~1e-6, an order below the fp32 noise the
+// reference itself has between its CPU and CUDA runs of the same model, 30x fewer instructions than tanhf
+__device__ __forceinline__ float tanh_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));  // exp(2x) = 2^(2x log2 e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+}
+
 template <int KP>
-__device__ __forceinline__ void matvec_acc(float (&acc)[KP], const float (&x)[KP], const float* __restrict__ MT) {
+__device__ __forceinline__ void row_acc(float (&acc)[KP], float xk, const float* __restrict__ row) {
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    const float xk = x[k];
-    const float4* row = reinterpret_cast<const float4*>(MT + k * KP);
-#pragma unroll
-    for (int c4 = 0; c4 < KP / 4; ++c4) {
-      const float4 m = row[c4];
-      acc[4 * c4 + 0] = fmaf(xk, m.x, acc[4 * c4 + 0]);
-      acc[4 * c4 + 1] = fmaf(xk, m.y, acc[4 * c4 + 1]);
-      acc[4 * c4 + 2] = fmaf(xk, m.z, acc[4 * c4 + 2]);
-      acc[4 * c4 + 3] = fmaf(xk, m.w, acc[4 * c4 + 3]);
-    }
+  for (int c4 = 0; c4 < KP / 4; ++c4) {
+    const float4 m = reinterpret_cast<const float4*>(row)[c4];
+    acc[4 * c4 + 0] = fmaf(xk, m.x, acc[4 * c4 + 0]);
+    acc[4 * c4 + 1] = fmaf(xk, m.y, acc[4 * c4 + 1]);
+    acc[4 * c4 + 2] = fmaf(xk, m.z, acc[4 * c4 + 2]);
+    acc[4 * c4 + 3] = fmaf(xk, m.w, acc[4 * c4 + 3]);
   }
 }
 
-// layer-1 output row of node m: relu(x0 + eps * tanh(x0 Was^T + (A_hat x0) Theta^T + b)), x0 one-hot columns at colnode[]
 template <int KP>
-__device__ __forceinline__ void x1_at(const ModelView<KP>& mv, const GraphView& gv, const int* __restrict__ colnode, int m, float eps,
-                                      float (&x1)[KP]) {
-  float x0[KP], z[KP];
-  const float sc = __ldg(gv.self_coef + m);
-  bool touched = false;
+__device__ __forceinline__ void matvec_acc(float (&acc)[KP], const float (&x)[KP], const float* __restrict__ MT) {
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    const bool here = colnode[k] == m;
-    x0[k] = here ? 1.0f : 0.0f;
-    z[k] = here ? sc : 0.0f;
-    touched |= here;
+  for (int k = 0; k < KP; ++k) row_acc<KP>(acc, x[k], MT + k * KP);
+}
+
+// layer-1 output row of node m: relu(x0 + eps * tanh(x0 Was^T + (A_hat x0) Theta^T + b)).  x0 is given as a per-node
+// bitmask of feature columns (feat[node], bit k = column k is 1 there): almost every node and in-neighbour has none,
+// and a node nothing touches has the constant row c1; for the others only the rows of the non-zero entries are added.
+template <int KP>
+__device__ __forceinline__ void x1_at(const float* __restrict__ ms, const float* __restrict__ c1, const GraphView& gv,
+                                      const unsigned* __restrict__ feat, int m, float eps, float (&x1)[KP]) {
+  const unsigned fm = feat[m];
+  float acc[KP];
+  bool touched = fm != 0;
+  if (fm) {
+    const float sc = __ldg(gv.self_coef + m);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[k] = ms[Lay<KP>::BIAS + k];
+    for (unsigned bits = fm; bits; bits &= bits - 1) {  // x0[m] has column k: its Was row, and its Theta row times the self-loop weight
+      const int k = __ffs(bits) - 1;
+      row_acc<KP>(acc, 1.0f, ms + Lay<KP>::WAS + k * KP);
+      row_acc<KP>(acc, sc, ms + Lay<KP>::TH + k * KP);
+    }
   }
   const int e0 = __ldg(gv.in_ptr + m), e1 = __ldg(gv.in_ptr + m + 1);
   for (int e = e0; e < e1; ++e) {
-    const int s = __ldg(gv.in_src + e);
-    const float c = __ldg(gv.in_coef + e);
+    const unsigned fs = feat[__ldg(gv.in_src + e)];
+    if (fs) {
+      const float c = __ldg(gv.in_coef + e);
+      if (!touched) {
+        touched = true;
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const bool from = colnode[k] == s;
-      z[k] += from ? c : 0.0f;
-      touched |= from;
+        for (int k = 0; k < KP; ++k) acc[k] = ms[Lay<KP>::BIAS + k];
+      }
+      for (unsigned bits = fs; bits; bits &= bits - 1) row_acc<KP>(acc, c, ms + Lay<KP>::TH + (__ffs(bits) - 1) * KP);
     }
   }
   if (!touched) {
 #pragma unroll
-    for (int k = 0; k < KP; ++k) x1[k] = mv.c1[k];
+    for (int k = 0; k < KP; ++k) x1[k] = c1[k];
     return;
   }
-  float acc[KP];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) acc[k] = mv.bias[0][k];
-  matvec_acc<KP>(acc, x0, mv.WasT[0]);
-  matvec_acc<KP>(acc, z, mv.ThT[0]);
-#pragma unroll
-  for (int k = 0; k < KP; ++k) x1[k] = fmaxf(x0[k] + eps * tanhf(acc[k]), 0.0f);
+  for (int k = 0; k < KP; ++k) x1[k] = fmaxf((((fm >> k) & 1u) ? 1.0f : 0.0f) + eps * tanh_fast(acc[k]), 0.0f);
 }
 
 // Q value of node n (gnn_agent.py:249-257)
 template <int KP>
-__device__ __forceinline__ float q_at_node(const ModelView<KP>& mv, const GraphView& gv, const int* __restrict__ colnode, int n, float eps) {
+__device__ __forceinline__ float q_at_node(const float* __restrict__ ms, const float* __restrict__ c1, const GraphView& gv,
+                                           const unsigned* __restrict__ feat, int n, float eps) {
   float x1n[KP], z[KP], x1s[KP];
-  x1_at<KP>(mv, gv, colnode, n, eps, x1n);
+  x1_at<KP>(ms, c1, gv, feat, n, eps, x1n);
   const float sc = __ldg(gv.self_coef + n);
 #pragma unroll
   for (int k = 0; k < KP; ++k) z[k] = sc * x1n[k];
   const int e0 = __ldg(gv.in_ptr + n), e1 = __ldg(gv.in_ptr + n + 1);
   for (int e = e0; e < e1; ++e) {
     const float c = __ldg(gv.in_coef + e);
-    x1_at<KP>(mv, gv, colnode, __ldg(gv.in_src + e), eps, x1s);
+    x1_at<KP>(ms, c1, gv, feat, __ldg(gv.in_src + e), eps, x1s);
 #pragma unroll
     for (int k = 0; k < KP; ++k) z[k] = fmaf(c, x1s[k], z[k]);
   }
+  const float* ms2 = ms + Lay<KP>::CONV;
   float acc[KP];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) acc[k] = mv.bias[1][k];
-  matvec_acc<KP>(acc, x1n, mv.WasT[1]);
-  matvec_acc<KP>(acc, z, mv.ThT[1]);
-  float q = mv.out_b;
+  for (int k = 0; k < KP; ++k) acc[k] = ms2[Lay<KP>::BIAS + k];
+  matvec_acc<KP>(acc, x1n, ms2 + Lay<KP>::WAS);
+  matvec_acc<KP>(acc, z, ms2 + Lay<KP>::TH);
+  float q = ms[Lay<KP>::OUT_B];
 #pragma unroll
-  for (int k = 0; k < KP; ++k) q = fmaf(fmaxf(x1n[k] + eps * tanhf(acc[k]), 0.0f), mv.out_w[k], q);
+  for (int k = 0; k < KP; ++k) q = fmaf(fmaxf(x1n[k] + eps * tanh_fast(acc[k]), 0.0f), ms[Lay<KP>::OUT_W + k], q);
   return q;
 }
 
-// shared memory: both models + their c1 rows, then per warp: colnode[KP], cstart[17], apos[16], amoney[16]
+// static shared memory: both models + their c1 rows, per-warp candidate bookkeeping; dynamic: per-warp feat[N] bitmasks
 template <int KP>
 struct GnnSmem {
   float model[2][gnn_model_floats(KP)];
   float c1[2][KP];
-  int colnode[GNN_WARPS][KP];
   int cstart[GNN_WARPS][SY_POLICY_MAX_FEATURES + 1];
   int apos[GNN_WARPS][SY_POLICY_MAX_FEATURES];
   int amoney[GNN_WARPS][SY_POLICY_MAX_FEATURES];
 };
 
 template <int KP>
-__device__ __forceinline__ void gnn_load_models(const GnnParams& p, GnnSmem<KP>& sm) {
+__device__ __forceinline__ void gnn_load_models(const GnnParams& p, GnnSmem<KP>& sm, unsigned* feat_all, int n_feat) {
   for (int i = threadIdx.x; i < 2 * gnn_model_floats(KP); i += blockDim.x) (&sm.model[0][0])[i] = __ldg(p.params + i);
+  for (int i = threadIdx.x; i < n_feat; i += blockDim.x) feat_all[i] = 0;
   __syncthreads();
   if (threadIdx.x < 2 * KP) {
     const int m = threadIdx.x / KP, k = threadIdx.x % KP;
-    const float b1 = sm.model[m][2 * KP * KP + k];
-    sm.c1[m][k] = fmaxf(0.0f + p.conv_eps * tanhf(b1), 0.0f);
+    sm.c1[m][k] = fmaxf(0.0f + p.conv_eps * tanh_fast(sm.model[m][Lay<KP>::BIAS + k]), 0.0f);
   }
   __syncthreads();
 }
 
-// feature columns of env b: colnode[k] = node carrying column k, -2 = none (see SY_FEATURES_*)
-template <int KP>
-__device__ __forceinline__ void gnn_feature_columns(const GnnParams& p, int b, int lane, int* colnode) {
+// feature column k of env b sits at node ... (-2 = nowhere); see SY_FEATURES_*
+__device__ __forceinline__ int gnn_feature_node(const GnnParams& p, int b, int k) {
   const int A = p.st.num_agents, N = p.g.num_nodes;
-  if (lane < KP) {
-    int node = -2;
-    const int rev = p.st.mrx_revealed ? p.st.mrx_revealed[b] : 0;
-    if (p.feature_mode == SY_FEATURES_ENV) {
-      if (lane < A && lane < p.K && !(lane == 0 && rev < 0)) node = p.st.pos[(size_t)b * A + lane];
-    } else {  // utils.py:176-199
-      if (lane == 0) node = rev < 0 ? N - 1 : p.st.pos[(size_t)b * A];  // numpy index -1 while MrX is hidden
-      else if (lane < A - 1 && lane < p.K) node = p.st.pos[(size_t)b * A + 1];  // range(number_of_agents - 1), always Polices_pos[0]
-    }
-    colnode[lane] = node;
+  if (k >= p.K) return -2;
+  const int rev = p.st.mrx_revealed ? p.st.mrx_revealed[b] : 0;
+  if (p.feature_mode == SY_FEATURES_ENV) return (k < A && !(k == 0 && rev < 0)) ? p.st.pos[(size_t)b * A + k] : -2;
+  if (k == 0) return rev < 0 ? N - 1 : p.st.pos[(size_t)b * A];  // utils.py:176-199: numpy index -1 while MrX is hidden
+  return k < A - 1 ? p.st.pos[(size_t)b * A + 1] : -2;           // range(number_of_agents - 1), always Polices_pos[0]
+}
+
+// set (on = true) or clear this env's feature bits in the warp's feat[]; lane k < KP owns column k (several columns
+// may share a node, hence the shared-memory atomicOr)
+template <int KP>
+__device__ __forceinline__ void gnn_mark_features(unsigned* feat, int my_node, int lane, bool on) {
+  __syncwarp();
+  if (my_node >= 0) {
+    if (on) atomicOr(feat + my_node, 1u << lane);
+    else feat[my_node] = 0u;
   }
+  __syncwarp();
 }
 
 template <int KP>
 __global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_q_dense_kernel(const GnnParams p, float* __restrict__ q) {
   __shared__ __align__(16) GnnSmem<KP> sm;
-  gnn_load_models<KP>(p, sm);
+  extern __shared__ __align__(16) unsigned feat_all[];
+  const int N = p.g.num_nodes, NF = (N + 7) & ~7;
+  gnn_load_models<KP>(p, sm, feat_all, GNN_WARPS * NF);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = blockIdx.x * GNN_WARPS + w;
-  if (b >= p.st.num_envs) return;
-  const int N = p.g.num_nodes;
-  gnn_feature_columns<KP>(p, b, lane, sm.colnode[w]);
-  __syncwarp();
-  const int g = p.st.graph_id[b];
-  const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
-                     p.g.self_coef + (size_t)g * N};
-  for (int m = 0; m < 2; ++m) {
-    const ModelView<KP> mv(sm.model[m], sm.c1[m]);
-    for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_at_node<KP>(mv, gv, sm.colnode[w], n, p.conv_eps);
+  unsigned* feat = feat_all + w * NF;
+  for (int b = blockIdx.x * GNN_WARPS + w; b < p.st.num_envs; b += gridDim.x * GNN_WARPS) {
+    const int my_node = lane < KP ? gnn_feature_node(p, b, lane) : -2;
+    gnn_mark_features<KP>(feat, my_node, lane, true);
+    const int g = p.st.graph_id[b];
+    const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
+                       p.g.self_coef + (size_t)g * N};
+    for (int m = 0; m < 2; ++m)
+      for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_at_node<KP>(sm.model[m], sm.c1[m], gv, feat, n, p.conv_eps);
+    gnn_mark_features<KP>(feat, my_node, lane, false);
   }
 }
 
@@ -262,100 +270,108 @@ __device__ __forceinline__ unsigned ordered_key(float f) {  // monotone float ->
 }
 
 template <int KP>
-__global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_act_kernel(const GnnParams p, int64_t* __restrict__ actions, float* __restrict__ q_taken) {
+__global__ void __launch_bounds__(GNN_WARPS * 32, 3) sy_gnn_act_kernel(const GnnParams p, int64_t* __restrict__ actions, float* __restrict__ q_taken) {
   __shared__ __align__(16) GnnSmem<KP> sm;
-  gnn_load_models<KP>(p, sm);
+  extern __shared__ __align__(16) unsigned feat_all[];
+  const int N = p.g.num_nodes, A = p.st.num_agents, NF = (N + 7) & ~7;
+  gnn_load_models<KP>(p, sm, feat_all, GNN_WARPS * NF);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = blockIdx.x * GNN_WARPS + w;
-  if (b >= p.st.num_envs) return;
-  const int N = p.g.num_nodes, A = p.st.num_agents;
-  gnn_feature_columns<KP>(p, b, lane, sm.colnode[w]);
-  const int g = p.st.graph_id[b];
-  const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
-  const int32_t* col = p.g.col + (size_t)g * p.g.nnz_stride;
-  const int32_t* wt = p.g.w + (size_t)g * p.g.nnz_stride;
-  const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
-                     p.g.self_coef + (size_t)g * N};
-  // lane a < A owns agent a: its node, budget, neighbour range, number of valid moves, explore decision
-  int my_pos = 0, my_money = 0, r0 = 0, deg = 0, n_valid = 0;
-  if (lane < A) {
-    my_pos = p.st.pos[(size_t)b * A + lane];
-    my_money = p.st.money[(size_t)b * A + lane];
-    r0 = __ldg(rp + my_pos);
-    deg = __ldg(rp + my_pos + 1) - r0;
-    for (int k = 0; k < deg; ++k) n_valid += (__ldg(wt + r0 + k) + p.st.toll <= my_money);
-    sm.apos[w][lane] = r0;
-    sm.amoney[w][lane] = my_money;
-  }
-  int incl = deg;  // inclusive prefix of the degrees over lanes -> candidate ranges
+  unsigned* feat = feat_all + w * NF;
+  // persistent: the models are loaded once per CTA, every warp walks its share of the envs
+  for (int b = blockIdx.x * GNN_WARPS + w; b < p.st.num_envs; b += gridDim.x * GNN_WARPS) {
+    const int my_node = lane < KP ? gnn_feature_node(p, b, lane) : -2;
+    gnn_mark_features<KP>(feat, my_node, lane, true);
+    const int g = p.st.graph_id[b];
+    const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
+    const int32_t* col = p.g.col + (size_t)g * p.g.nnz_stride;
+    const int32_t* wt = p.g.w + (size_t)g * p.g.nnz_stride;
+    const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
+                       p.g.self_coef + (size_t)g * N};
+    // lane a < A owns agent a: its node, budget, neighbour range, number of valid moves, explore decision
+    int my_money = 0, r0 = 0, deg = 0, n_valid = 0;
+    if (lane < A) {
+      const int my_pos = p.st.pos[(size_t)b * A + lane];
+      my_money = p.st.money[(size_t)b * A + lane];
+      r0 = __ldg(rp + my_pos);
+      deg = __ldg(rp + my_pos + 1) - r0;
+      for (int k = 0; k < deg; ++k) n_valid += (__ldg(wt + r0 + k) + p.st.toll <= my_money);
+      sm.apos[w][lane] = r0;
+      sm.amoney[w][lane] = my_money;
+    }
+    int incl = deg;  // inclusive prefix of the degrees over lanes -> candidate ranges
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(FULL, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane < A) sm.cstart[w][lane + 1] = incl;
-  if (lane == 0) sm.cstart[w][0] = 0;
-  const int C = __shfl_sync(FULL, incl, A - 1);
-  bool explore = false;
-  int target = 0;
-  if (lane < A) {
-    const uint4 r = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_GNN_POLICY, (unsigned)lane), make_uint2(p.seed_lo, p.seed_hi));
-    explore = u01(r.x) < (lane == 0 ? p.eps_mrx : p.eps_police);  // np.random.rand() <= epsilon (gnn_agent.py:69)
-    target = (int)__umulhi(r.y, (unsigned)n_valid);                // np.random.choice(valid_actions)
-  }
-  __syncwarp();
-  int seen = 0;             // lane a: valid candidates of agent a in earlier chunks
-  int best_node = -1;       // lane a: running choice
-  unsigned best_key = 0;
-  float best_q = CUDART_NAN_F;
-  const ModelView<KP> mv0(sm.model[0], sm.c1[0]), mv1(sm.model[1], sm.c1[1]);
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    const int c = c0 + lane;
-    int a = -1, node = -1;
-    bool valid = false;
-    if (c < C) {
-      a = 0;
-      while (c >= sm.cstart[w][a + 1]) ++a;
-      const int k = sm.apos[w][a] + (c - sm.cstart[w][a]);
-      node = __ldg(col + k);
-      valid = __ldg(wt + k) + p.st.toll <= sm.amoney[w][a];
+    for (int o = 1; o < SY_POLICY_MAX_FEATURES; o <<= 1) {
+      const int v = __shfl_up_sync(FULL, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane < A) sm.cstart[w][lane + 1] = incl;
+    if (lane == 0) sm.cstart[w][0] = 0;
+    const int C = __shfl_sync(FULL, incl, A - 1);
+    bool explore = false;
+    int target = 0;
+    if (lane < A) {
+      const uint4 r = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_GNN_POLICY, (unsigned)lane), make_uint2(p.seed_lo, p.seed_hi));
+      explore = u01(r.x) < (lane == 0 ? p.eps_mrx : p.eps_police);  // np.random.rand() <= epsilon (gnn_agent.py:69)
+      target = (int)__umulhi(r.y, (unsigned)n_valid);                // np.random.choice(valid_actions)
     }
     const unsigned explore_mask = __ballot_sync(FULL, explore);
-    float qv = 0.0f;
-    if (valid && !((explore_mask >> a) & 1u)) qv = q_at_node<KP>(a == 0 ? mv0 : mv1, gv, sm.colnode[w], node, p.conv_eps);
-    const unsigned key = valid ? ordered_key(qv) : 0u;
     __syncwarp();
-    const int a_lo = __shfl_sync(FULL, a, 0), a_hi = __shfl_sync(FULL, a, min(31, C - c0 - 1));
-    for (int aa = a_lo; aa <= a_hi; ++aa) {  // agents with candidates in this chunk (warp-uniform)
-      const unsigned vm = __ballot_sync(FULL, valid && a == aa);
-      const bool ex = (explore_mask >> aa) & 1u;
-      const int seen_a = __shfl_sync(FULL, seen, aa), target_a = __shfl_sync(FULL, target, aa);
-      int pick_lane = -1;
-      unsigned kmax = 0;
-      if (ex) {  // the target-th valid candidate
-        const int rank = seen_a + __popc(vm & ((1u << lane) - 1u));
-        const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && rank == target_a);
-        if (hit) pick_lane = __ffs(hit) - 1;
-      } else if (vm) {
-        kmax = __reduce_max_sync(FULL, ((vm >> lane) & 1u) ? key : 0u);
-        const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && key == kmax);
-        pick_lane = __ffs(hit) - 1;  // first maximum (np.argmax, gnn_agent.py:75)
+    int seen = 0;        // lane a: valid candidates of agent a in earlier chunks
+    int best_node = -1;  // lane a: running choice
+    unsigned best_key = 0;
+    float best_q = CUDART_NAN_F;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      int a = -1, node = -1;
+      bool valid = false;
+      if (c < C) {
+        a = 0;
+        while (c >= sm.cstart[w][a + 1]) ++a;
+        const int k = sm.apos[w][a] + (c - sm.cstart[w][a]);
+        node = __ldg(col + k);
+        valid = __ldg(wt + k) + p.st.toll <= sm.amoney[w][a];
       }
-      const int pn = __shfl_sync(FULL, node, max(pick_lane, 0));
-      const float pq = __shfl_sync(FULL, qv, max(pick_lane, 0));
-      if (lane == aa) {
-        if (pick_lane >= 0 && (ex || best_node < 0 || kmax > best_key)) {
-          best_node = pn;
-          best_key = kmax;
-          best_q = ex ? CUDART_NAN_F : pq;
+      float qv = 0.0f;
+      if (valid && !((explore_mask >> a) & 1u)) {
+        const int mi = a == 0 ? 0 : 1;  // MrX's agent / the police agent
+        qv = q_at_node<KP>(&sm.model[0][0] + mi * Lay<KP>::MF, &sm.c1[0][0] + mi * KP, gv, feat, node, p.conv_eps);
+      }
+      const unsigned key = valid ? ordered_key(qv) : 0u;
+      __syncwarp();
+      const int a_lo = __shfl_sync(FULL, a, 0), a_hi = __shfl_sync(FULL, a, min(31, C - c0 - 1));
+      for (int aa = a_lo; aa <= a_hi; ++aa) {  // agents with candidates in this chunk (warp-uniform)
+        const unsigned vm = __ballot_sync(FULL, valid && a == aa);
+        if (!vm) continue;
+        const bool ex = (explore_mask >> aa) & 1u;
+        int pick_lane = -1;
+        unsigned kmax = 0;
+        if (ex) {  // the target-th valid candidate
+          const int seen_a = __shfl_sync(FULL, seen, aa), target_a = __shfl_sync(FULL, target, aa);
+          const int rank = seen_a + __popc(vm & ((1u << lane) - 1u));
+          const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && rank == target_a);
+          if (hit) pick_lane = __ffs(hit) - 1;
+        } else {
+          kmax = __reduce_max_sync(FULL, ((vm >> lane) & 1u) ? key : 0u);
+          const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && key == kmax);
+          pick_lane = __ffs(hit) - 1;  // first maximum (np.argmax, gnn_agent.py:75)
         }
-        seen += __popc(vm);
+        const int pn = __shfl_sync(FULL, node, max(pick_lane, 0));
+        const float pq = __shfl_sync(FULL, qv, max(pick_lane, 0));
+        if (lane == aa) {
+          if (pick_lane >= 0 && (ex || best_node < 0 || kmax > best_key)) {
+            best_node = pn;
+            best_key = kmax;
+            best_q = ex ? CUDART_NAN_F : pq;
+          }
+          seen += __popc(vm);
+        }
       }
     }
-  }
-  if (lane < A) {
-    actions[(size_t)b * A + lane] = best_node;  // -1: no valid move (DEFAULT_ACTION)
-    if (q_taken) q_taken[(size_t)b * A + lane] = best_q;
+    if (lane < A) {
+      actions[(size_t)b * A + lane] = best_node;  // -1: no valid move (DEFAULT_ACTION)
+      if (q_taken) q_taken[(size_t)b * A + lane] = best_q;
+    }
+    gnn_mark_features<KP>(feat, my_node, lane, false);
   }
 }
 
@@ -570,6 +586,17 @@ int fill_gnn(const SyPolicyGraphs* g, const SyPolicyState* st, const float* para
   return SY_POLICY_OK;
 }
 
+// persistent grid (a few CTAs per SM, each warp walks its share of the envs) + the per-warp feature bitmasks
+int gnn_launch_shape(const SyPolicyGraphs* g, const SyPolicyState* st, unsigned& grid, size_t& dyn) {
+  dyn = (size_t)GNN_WARPS * ((g->num_nodes + 7) & ~7) * sizeof(unsigned);
+  if (dyn > 160 * 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "num_nodes too large for the GNN kernels' shared memory");
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned need = (unsigned)((st->num_envs + GNN_WARPS - 1) / GNN_WARPS);
+  grid = need < (unsigned)(sms * 6) ? need : (unsigned)(sms * 6);
+  return SY_POLICY_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -585,12 +612,17 @@ int sy_gnn_q_values(const SyPolicyGraphs* graphs, const SyPolicyState* state, co
   GnnParams p;
   if (int rc = fill_gnn(graphs, state, params, K, conv_epsilon, feature_mode, p)) return rc;
   if (!q) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL q");
-  const unsigned grid = (unsigned)((state->num_envs + GNN_WARPS - 1) / GNN_WARPS);
   cudaStream_t s = (cudaStream_t)stream;
+  unsigned grid = 0;
+  size_t dyn = 0;
+  if (int rc = gnn_launch_shape(graphs, state, grid, dyn)) return rc;
   switch (gnn_kp(K)) {
-    case 4: sy_gnn_q_dense_kernel<4><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
-    case 8: sy_gnn_q_dense_kernel<8><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
-    default: sy_gnn_q_dense_kernel<16><<<grid, GNN_WARPS * 32, 0, s>>>(p, q); break;
+    case 4: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sy_gnn_q_dense_kernel<4><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
+    case 8: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sy_gnn_q_dense_kernel<8><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
+    default: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+             sy_gnn_q_dense_kernel<16><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -608,12 +640,17 @@ int sy_gnn_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const f
   p.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
   p.seed_hi = (unsigned)(seed >> 32);
   p.step = step_counter;
-  const unsigned grid = (unsigned)((state->num_envs + GNN_WARPS - 1) / GNN_WARPS);
   cudaStream_t s = (cudaStream_t)stream;
+  unsigned grid = 0;
+  size_t dyn = 0;
+  if (int rc = gnn_launch_shape(graphs, state, grid, dyn)) return rc;
   switch (gnn_kp(K)) {
-    case 4: sy_gnn_act_kernel<4><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
-    case 8: sy_gnn_act_kernel<8><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
-    default: sy_gnn_act_kernel<16><<<grid, GNN_WARPS * 32, 0, s>>>(p, actions, q_taken); break;
+    case 4: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_act_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sy_gnn_act_kernel<4><<<grid, GNN_WARPS * 32, dyn, s>>>(p, actions, q_taken); break;
+    case 8: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_act_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            sy_gnn_act_kernel<8><<<grid, GNN_WARPS * 32, dyn, s>>>(p, actions, q_taken); break;
+    default: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_act_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+             sy_gnn_act_kernel<16><<<grid, GNN_WARPS * 32, dyn, s>>>(p, actions, q_taken); break;
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
