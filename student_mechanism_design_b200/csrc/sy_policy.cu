@@ -378,9 +378,10 @@ __global__ void __launch_bounds__(GNN_WARPS * 32, 3) sy_gnn_act_kernel(const Gnn
 // ---------------------------------------------------------------------------------------------
 // MAPPO
 // ---------------------------------------------------------------------------------------------
-constexpr int MP_ROWS = 128;     // envs per CTA
+constexpr int MP_ROWS = 64;      // envs per CTA (69 KB of shared memory at N = 200, H = 64: three CTAs per SM)
 constexpr int MP_THREADS = 256;
 constexpr int MP_HC = 32;        // hidden units per register chunk
+constexpr int MP_RU = 4;         // rows in flight per thread in the logits loop
 
 struct MappoParams {
   SyPolicyGraphs g;
@@ -392,12 +393,13 @@ struct MappoParams {
   unsigned seed_lo, seed_hi, step;
 };
 
-__global__ void __launch_bounds__(MP_THREADS) sy_mappo_act_kernel(const MappoParams p, int64_t* __restrict__ actions,
-                                                                   float* __restrict__ log_probs, float* __restrict__ probs_out) {
+__global__ void __launch_bounds__(MP_THREADS, 3) sy_mappo_act_kernel(const MappoParams p, int64_t* __restrict__ actions,
+                                                                      float* __restrict__ log_probs, float* __restrict__ probs_out) {
   extern __shared__ __align__(16) float mp_smem[];
   const int N = p.g.num_nodes, A = p.st.num_agents, H = p.H, HP = p.HP, D = p.obs_size;
   float* hid = mp_smem;                    // [MP_ROWS][HP]
-  float* logits = mp_smem + MP_ROWS * HP;  // [MP_ROWS][N]
+  float* logits = hid + MP_ROWS * HP;      // [MP_ROWS][N]
+  float* obs_s = logits + MP_ROWS * N;     // [MP_ROWS][D]
   const int a = blockIdx.y, row0 = blockIdx.x * MP_ROWS;
   const int nrows = min(MP_ROWS, p.st.num_envs - row0);
   const float* pol = p.params + (size_t)p.policy_of_agent[a] * p.policy_floats;
@@ -406,44 +408,63 @@ __global__ void __launch_bounds__(MP_THREADS) sy_mappo_act_kernel(const MappoPar
   const float* W2 = b1 + H;                  // [N, H]
   const float* b2 = W2 + (size_t)N * H;      // [N]
   const int tid = threadIdx.x;
-  // hidden layer: relu(W1 obs + b1)
-  for (int i = tid; i < MP_ROWS * HP; i += MP_THREADS) {
-    const int r = i / HP, h = i - r * HP;
-    float v = 0.0f;
-    if (r < nrows && h < H) {
-      const float* x = p.obs + ((size_t)(row0 + r) * A + a) * D;
-      v = __ldg(b1 + h);
-      for (int o = 0; o < D; ++o) v = fmaf(__ldg(W1 + (size_t)h * D + o), __ldg(x + o), v);
-      v = fmaxf(v, 0.0f);
-    }
-    hid[i] = v;
+  for (int i = tid; i < MP_ROWS * D; i += MP_THREADS) {
+    const int r = i / D, o = i - r * D;
+    obs_s[i] = r < nrows ? __ldg(p.obs + ((size_t)(row0 + r) * A + a) * D + o) : 0.0f;
   }
   __syncthreads();
-  // logits: thread = action node, W2 row chunk in registers, walk the rows
+  // hidden layer: relu(W1 obs + b1); with HP dividing the block every thread keeps one hidden unit
+  if (MP_THREADS % HP == 0) {
+    const int h = tid % HP;
+    const float bias = h < H ? __ldg(b1 + h) : 0.0f;
+    for (int r = tid / HP; r < MP_ROWS; r += MP_THREADS / HP) {
+      float v = bias;
+      if (h < H)
+        for (int o = 0; o < D; ++o) v = fmaf(__ldg(W1 + (size_t)h * D + o), obs_s[r * D + o], v);
+      hid[r * HP + h] = h < H ? fmaxf(v, 0.0f) : 0.0f;
+    }
+  } else {
+    for (int i = tid; i < MP_ROWS * HP; i += MP_THREADS) {
+      const int r = i / HP, h = i - r * HP;
+      float v = 0.0f;
+      if (h < H) {
+        v = __ldg(b1 + h);
+        for (int o = 0; o < D; ++o) v = fmaf(__ldg(W1 + (size_t)h * D + o), obs_s[r * D + o], v);
+        v = fmaxf(v, 0.0f);
+      }
+      hid[i] = v;
+    }
+  }
+  __syncthreads();
+  // logits: thread = action node, W2 row chunk in registers, MP_RU rows of the tile in flight
   for (int n = tid; n < N; n += MP_THREADS) {
     const float bias = __ldg(b2 + n);
     for (int hc = 0; hc < HP; hc += MP_HC) {
       float wreg[MP_HC];
 #pragma unroll
       for (int j = 0; j < MP_HC; ++j) wreg[j] = (hc + j < H) ? __ldg(W2 + (size_t)n * H + hc + j) : 0.0f;
-#pragma unroll 2
-      for (int r = 0; r < nrows; ++r) {
-        const float4* hv = reinterpret_cast<const float4*>(hid + r * HP + hc);
-        float acc = hc == 0 ? bias : logits[r * N + n];
+      for (int r = 0; r < MP_ROWS; r += MP_RU) {
+        float acc[MP_RU];
+#pragma unroll
+        for (int u = 0; u < MP_RU; ++u) acc[u] = hc == 0 ? bias : logits[(r + u) * N + n];
 #pragma unroll
         for (int j4 = 0; j4 < MP_HC / 4; ++j4) {
-          const float4 h4 = hv[j4];
-          acc = fmaf(wreg[4 * j4 + 0], h4.x, acc);
-          acc = fmaf(wreg[4 * j4 + 1], h4.y, acc);
-          acc = fmaf(wreg[4 * j4 + 2], h4.z, acc);
-          acc = fmaf(wreg[4 * j4 + 3], h4.w, acc);
+#pragma unroll
+          for (int u = 0; u < MP_RU; ++u) {
+            const float4 h4 = reinterpret_cast<const float4*>(hid + (r + u) * HP + hc)[j4];
+            acc[u] = fmaf(wreg[4 * j4 + 0], h4.x, acc[u]);
+            acc[u] = fmaf(wreg[4 * j4 + 1], h4.y, acc[u]);
+            acc[u] = fmaf(wreg[4 * j4 + 2], h4.z, acc[u]);
+            acc[u] = fmaf(wreg[4 * j4 + 3], h4.w, acc[u]);
+          }
         }
-        logits[r * N + n] = acc;
+#pragma unroll
+        for (int u = 0; u < MP_RU; ++u) logits[(r + u) * N + n] = acc[u];
       }
     }
   }
   __syncthreads();
-  // softmax, mask, renormalise, sample, log-prob: warp per row (mappo_agent.py:102-142)
+  // softmax, mask, renormalise, sample, log-prob: warp per row, lane = neighbour slot (mappo_agent.py:102-142)
   const int lane = tid & 31, w = tid >> 5;
   for (int r = w; r < nrows; r += MP_THREADS / 32) {
     const int b = row0 + r;
@@ -485,50 +506,58 @@ __global__ void __launch_bounds__(MP_THREADS) sy_mappo_act_kernel(const MappoPar
     const int mode = Sv > 1e-8f ? 0 : (nv > 0 ? 1 : 2);
     const uint4 rnd = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_MAPPO_POLICY, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
     const float u = u01(rnd.x);
-    int action;
-    float pa, total;
+    int action = -1;
+    float pa = 0.0f, total = 1.0f;
     if (mode == 2) {
       action = min((int)(u * (float)N), N - 1);
-      pa = 1.0f / (float)N;
-      total = 1.0f;  // N * (1/N) up to rounding; Categorical renormalises
+      pa = 1.0f / (float)N;  // total: N * (1/N) up to rounding; Categorical renormalises
       if (probs_out)
         for (int n = lane; n < N; n += 32) probs_out[((size_t)b * A + a) * N + n] = pa;
     } else {
-      // current_probs over the valid moves (ascending), Categorical's own normalisation, inverse CDF
-      if (probs_out)
+      if (probs_out) {
         for (int n = lane; n < N; n += 32) probs_out[((size_t)b * A + a) * N + n] = 0.0f;
-      __syncwarp();
+        __syncwarp();
+      }
+      // current_probs over the valid moves (ascending); Categorical's own normalisation
+      const float inv_nv = 1.0f / (float)max(nv, 1), den = Sv + 1e-8f;
       total = 0.0f;
       for (int k = lane; k < deg; k += 32) {
         if (__ldg(wt + k) + p.st.toll <= money) {
-          const float pk = mode == 0 ? (lr[__ldg(col + k)] / Z) / (Sv + 1e-8f) : 1.0f / (float)nv;
+          const int node = __ldg(col + k);
+          const float pk = mode == 0 ? (lr[node] / Z) / den : inv_nv;
           total += pk;
-          if (probs_out) probs_out[((size_t)b * A + a) * N + __ldg(col + k)] = pk;
+          if (probs_out) probs_out[((size_t)b * A + a) * N + node] = pk;
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(FULL, total, o);
-      // sequential inverse CDF in ascending node order (uniform across lanes)
+      // inverse CDF in ascending node order: each lane holds one slot's probability, the walk is a shuffle loop
       const float thr = u * total;
-      float cum = 0.0f;
-      action = -1;
-      pa = 0.0f;
+      float cum = 0.0f, plast = 0.0f;
       int last = -1;
-      float plast = 0.0f;
-      for (int k = 0; k < deg; ++k) {
-        if (__ldg(wt + k) + p.st.toll <= money) {
-          const float pk = mode == 0 ? (lr[__ldg(col + k)] / Z) / (Sv + 1e-8f) : 1.0f / (float)nv;
-          cum += pk;
-          last = __ldg(col + k);
-          plast = pk;
+      for (int c0 = 0; c0 < deg; c0 += 32) {
+        const int k = c0 + lane;
+        int node = -1;
+        float pk = 0.0f;
+        if (k < deg && __ldg(wt + k) + p.st.toll <= money) {
+          node = __ldg(col + k);
+          pk = mode == 0 ? (lr[node] / Z) / den : inv_nv;
+        }
+        const unsigned vm = __ballot_sync(FULL, node >= 0);
+        for (unsigned bits = vm; bits; bits &= bits - 1) {
+          const int j = __ffs(bits) - 1;
+          const float pj = __shfl_sync(FULL, pk, j);
+          cum += pj;
+          last = j + c0;
+          plast = pj;
           if (action < 0 && thr < cum) {
-            action = last;
-            pa = pk;
+            action = __shfl_sync(FULL, node, j);
+            pa = pj;
           }
         }
       }
       if (action < 0) {  // rounding at the top of the CDF
-        action = last;
+        action = __ldg(col + last);
         pa = plast;
       }
     }
@@ -685,7 +714,7 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
   p.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
   p.seed_hi = (unsigned)(seed >> 32);
   p.step = step_counter;
-  const size_t smem = (size_t)MP_ROWS * (p.HP + graphs->num_nodes) * sizeof(float);
+  const size_t smem = (size_t)MP_ROWS * (p.HP + graphs->num_nodes + obs_size) * sizeof(float);
   if (smem > 220 * 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "hidden + num_nodes too large for the MAPPO kernel's shared memory");
   CUDA_TRY(cudaFuncSetAttribute(sy_mappo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((unsigned)((state->num_envs + MP_ROWS - 1) / MP_ROWS), (unsigned)state->num_agents);
