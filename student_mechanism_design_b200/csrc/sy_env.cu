@@ -1262,22 +1262,20 @@ __global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
 // ---------------------------------------------------------------------------------------------
 template <typename ActT>
 __global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, unsigned step_counter, ActT* actions) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)p.B * p.A) return;
-  const int b = (int)(i / p.A), a = (int)(i - (size_t)b * p.A);
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // B * A < 2^31 (checked at sy_create)
+  if (i >= (unsigned)p.B * (unsigned)p.A) return;
+  const unsigned b = i / (unsigned)p.A, a = i - b * (unsigned)p.A;
   const Tables& tb = p.tb;
   const int N = p.N;
   const int g = p.st.graph_id[b], u = p.st.pos[i], m = p.st.money[i];
-  const int r0 = __ldg(tb.row_ptr + (size_t)g * (N + 1) + u), r1 = __ldg(tb.row_ptr + (size_t)g * (N + 1) + u + 1);
-  const uint8_t* wg = tb.wgt + (size_t)g * tb.nnz_stride;
-  int nvalid = 0;
-  for (int k = r0; k < r1; ++k) nvalid += (__ldg(wg + k) + p.toll <= m);
+  const int nvalid = move_count(tb, N, g, u, m, p.toll);  // one table lookup instead of a pass over the row
   long long act = -1;
   if (nvalid > 0) {
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
-    const uint4 r = philox4x32(make_uint4(env_id, step_counter, RNG_ACTION, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
+    const uint4 r = philox4x32(make_uint4(env_id, step_counter, RNG_ACTION, a), make_uint2(p.seed_lo, p.seed_hi));
     int pick = (int)__umulhi(r.x, (unsigned)nvalid);
-    for (int k = r0; k < r1; ++k) {
+    const uint8_t* wg = tb.wgt + (size_t)g * tb.nnz_stride;
+    for (int k = __ldg(tb.row_ptr + (size_t)g * (N + 1) + u);; ++k) {  // the pick-th affordable neighbour exists
       if (__ldg(wg + k) + p.toll <= m) {
         if (pick == 0) {
           act = __ldg(tb.col + (size_t)g * tb.nnz_stride + k);
@@ -1759,6 +1757,7 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
   if (c->struct_bytes != (int32_t)sizeof(SyConfig))
     return fail(SY_ERR_INVALID_ARGUMENT, "SyConfig size mismatch: got %d, library expects %zu", c->struct_bytes, sizeof(SyConfig));
   if (c->num_envs <= 0) return fail(SY_ERR_INVALID_ARGUMENT, "num_envs must be positive");
+  if ((long long)c->num_envs * (c->num_police + 1) >= (1LL << 31)) return fail(SY_ERR_INVALID_ARGUMENT, "num_envs x agents must stay below 2^31 per handle");
   if (c->num_police < 1 || c->num_police + 1 > SY_MAX_AGENTS)
     return fail(SY_ERR_INVALID_ARGUMENT, "num_police must be in [1, %d]", SY_MAX_AGENTS - 1);
   if (c->num_nodes < c->num_police + 1 || c->num_nodes > 65534)

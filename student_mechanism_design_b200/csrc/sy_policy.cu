@@ -264,6 +264,10 @@ __global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_q_dense_kernel(const Gn
   }
 }
 
+__device__ __forceinline__ unsigned lane_range_mask(int lo, int hi) {  // bits [lo, hi), 0 <= lo < 32, hi <= 32
+  return hi <= lo ? 0u : ((hi >= 32 ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u));
+}
+
 __device__ __forceinline__ unsigned ordered_key(float f) {  // monotone float -> unsigned
   const unsigned u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -336,35 +340,54 @@ __global__ void __launch_bounds__(GNN_WARPS * 32, 3) sy_gnn_act_kernel(const Gnn
         const int mi = a == 0 ? 0 : 1;  // MrX's agent / the police agent
         qv = q_at_node<KP>(&sm.model[0][0] + mi * Lay<KP>::MF, &sm.c1[0][0] + mi * KP, gv, feat, node, p.conv_eps);
       }
-      const unsigned key = valid ? ordered_key(qv) : 0u;
+      const unsigned key = valid ? ordered_key(qv) : 0u;  // every valid key is > 0
       __syncwarp();
-      const int a_lo = __shfl_sync(FULL, a, 0), a_hi = __shfl_sync(FULL, a, min(31, C - c0 - 1));
-      for (int aa = a_lo; aa <= a_hi; ++aa) {  // agents with candidates in this chunk (warp-uniform)
-        const unsigned vm = __ballot_sync(FULL, valid && a == aa);
-        if (!vm) continue;
-        const bool ex = (explore_mask >> aa) & 1u;
-        int pick_lane = -1;
-        unsigned kmax = 0;
-        if (ex) {  // the target-th valid candidate
-          const int seen_a = __shfl_sync(FULL, seen, aa), target_a = __shfl_sync(FULL, target, aa);
-          const int rank = seen_a + __popc(vm & ((1u << lane) - 1u));
-          const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && rank == target_a);
-          if (hit) pick_lane = __ffs(hit) - 1;
-        } else {
-          kmax = __reduce_max_sync(FULL, ((vm >> lane) & 1u) ? key : 0u);
-          const unsigned hit = __ballot_sync(FULL, ((vm >> lane) & 1u) && key == kmax);
-          pick_lane = __ffs(hit) - 1;  // first maximum (np.argmax, gnn_agent.py:75)
+      // per-agent choice without a loop over the agents: the candidates of one agent are contiguous lanes, so a
+      // segmented shuffle reduction leaves each segment's first maximum (np.argmax, gnn_agent.py:75) in its first lane,
+      // and one ballot marks every exploring agent's target-th valid candidate; lane a (< A) then collects its own.
+      const unsigned vb = __ballot_sync(FULL, valid);
+      const int seg_hi = a >= 0 ? min(sm.cstart[w][a + 1] - c0, 32) : 0;
+      const int seg_lo = a >= 0 ? max(sm.cstart[w][a] - c0, 0) : 0;
+      unsigned mykey = key;
+      int mybest = lane;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned k2 = __shfl_down_sync(FULL, mykey, o);
+        const int b2 = __shfl_down_sync(FULL, mybest, o);
+        if (lane + o < seg_hi && k2 > mykey) {
+          mykey = k2;
+          mybest = b2;
         }
-        const int pn = __shfl_sync(FULL, node, max(pick_lane, 0));
-        const float pq = __shfl_sync(FULL, qv, max(pick_lane, 0));
-        if (lane == aa) {
-          if (pick_lane >= 0 && (ex || best_node < 0 || kmax > best_key)) {
-            best_node = pn;
-            best_key = kmax;
-            best_q = ex ? CUDART_NAN_F : pq;
-          }
-          seen += __popc(vm);
+      }
+      const int seen_a = __shfl_sync(FULL, seen, max(a, 0)), target_a = __shfl_sync(FULL, target, max(a, 0));
+      const unsigned seg_mask = lane_range_mask(seg_lo, seg_hi);
+      const int rank = seen_a + __popc(vb & seg_mask & ((1u << lane) - 1u));
+      const unsigned hb = __ballot_sync(FULL, valid && ((explore_mask >> a) & 1u) && rank == target_a);
+      int s0 = 32, s1 = 0;
+      if (lane < A) {
+        s0 = sm.cstart[w][lane] - c0;
+        s1 = sm.cstart[w][lane + 1] - c0;
+      }
+      const bool mine = s0 < 32 && s1 > 0 && s1 > s0;  // agent `lane` has candidates in this chunk
+      const unsigned own = mine ? lane_range_mask(max(s0, 0), min(s1, 32)) : 0u;
+      const int head = mine ? max(s0, 0) : 0;
+      const unsigned kmax = __shfl_sync(FULL, mykey, head);
+      const int exploit_lane = __shfl_sync(FULL, mybest, head);
+      int pick_lane = -1;
+      if (explore) {
+        if (hb & own) pick_lane = __ffs(hb & own) - 1;
+      } else if (vb & own) {
+        pick_lane = exploit_lane;
+      }
+      const int pn = __shfl_sync(FULL, node, max(pick_lane, 0));
+      const float pq = __shfl_sync(FULL, qv, max(pick_lane, 0));
+      if (mine) {
+        if (pick_lane >= 0 && (explore || best_node < 0 || kmax > best_key)) {
+          best_node = pn;
+          best_key = kmax;
+          best_q = explore ? CUDART_NAN_F : pq;
         }
+        seen += __popc(vb & own);
       }
     }
     if (lane < A) {
