@@ -96,8 +96,15 @@ int sy_gnn_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const f
  * actions int64 [B, A], log_probs float32 [B, A], probs (may be NULL) float32 [B, A, N] the detached distribution. */
 int32_t sy_mappo_param_count(int32_t obs_size, int32_t hidden, int32_t num_nodes);
 int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const float* obs, int32_t obs_size,
-                 int32_t hidden, const float* params, const int32_t* policy_of_agent, uint64_t seed,
-                 uint32_t step_counter, int64_t* actions, float* log_probs, float* probs, sy_policy_stream_t stream);
+                 int32_t hidden, const float* params, const int32_t* policy_of_agent, int32_t max_degree,
+                 uint64_t seed, uint32_t step_counter, int64_t* actions, float* log_probs, float* probs,
+                 sy_policy_stream_t stream);
+/* max_degree: largest neighbour count in the pool (0 = unknown).  With num_nodes <= 256, max_degree <= 32 and the
+ * operands fitting one SM's shared memory the logits GEMM runs on the tensor cores (tcgen05, 3xTF32, accumulators in
+ * tensor memory); otherwise on the CUDA cores.  sy_policy_set_option("mappo_tensor_cores", 0) forces the latter.
+ * sy_policy_check synchronises the stream and reports a (never expected) failure of the tensor-core kernel. */
+int sy_policy_set_option(const char* name, int32_t value);
+int sy_policy_check(sy_policy_stream_t stream);
 
 /* CentralCritic.forward (mappo_agent.py:32-44): values [M] = W2 relu(W1 x + b1) + b2 for global_obs [M, D];
  * params: W1 [H, D], b1 [H], W2 [H], b2 [1]. */

@@ -32,8 +32,10 @@ SIGNATURES = {
     "sy_gnn_act": (C.c_int, [_G, _S, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_float, C.c_float, C.c_uint64,
                              C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sy_mappo_param_count": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
-    "sy_mappo_act": (C.c_int, [_G, _S, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32,
-                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_mappo_act": (C.c_int, [_G, _S, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint64,
+                               C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_policy_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "sy_policy_check": (C.c_int, [C.c_void_p]),
     "sy_mappo_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -43,6 +43,8 @@ enum { RNG_GNN_POLICY = 3, RNG_MAPPO_POLICY = 4 };
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+int g_mappo_tc = 1;        // sy_policy_set_option("mappo_tensor_cores", 0 | 1)
+int* g_tc_flag = nullptr;  // device flag the tensor-core kernel raises instead of hanging (barrier timeout / degree overflow)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -594,6 +596,296 @@ __global__ void __launch_bounds__(MP_THREADS, 3) sy_mappo_act_kernel(const Mappo
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// MAPPO on the tensor cores (tcgen05 + TMEM): the logits GEMM [128 envs x H] x [H x N] of one agent's policy as
+// 3xTF32 (A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32-level accuracy) with the accumulator tile in tensor memory.
+// One persistent CTA per SM slice of (agent, row tiles): W2 is split and laid out once, every tile then costs 24 MMA
+// instructions issued by one thread; the epilogue reads TMEM with thread = row (lane = TMEM lane), so the softmax
+// statistics, the masked mass, the inverse-CDF sample and the log-prob need no cross-lane traffic at all.
+// Operands sit in shared memory in the canonical K-major no-swizzle layout of the UMMA descriptors: 16-byte chunks of
+// 4 consecutive k for one row, rows contiguous (8 rows = one 128-byte core matrix), K-chunk panels LBO apart.
+// ---------------------------------------------------------------------------------------------
+constexpr int TC_ROWS = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_MAXV = 32;  // valid moves per agent the epilogue keeps (host checks the pool's max degree)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ uint64_t umma_desc_k_major(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell); base offset 0, SWIZZLE_NONE
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcShape {
+  int Kp, Np;                       // hidden padded to 8, nodes padded to 16
+  int off_alo, off_bhi, off_blo;    // float offsets inside the dynamic shared memory (A_hi at 0)
+  int off_obs, off_b2, off_vals, off_nodes, off_mask, total_bytes;
+};
+
+__host__ __device__ inline TcShape tc_shape(int H, int N, int D) {
+  TcShape t;
+  t.Kp = (H + 7) & ~7;
+  t.Np = (N + 15) & ~15;
+  int o = TC_ROWS * t.Kp;
+  t.off_alo = o; o += TC_ROWS * t.Kp;
+  t.off_bhi = o; o += t.Np * t.Kp;
+  t.off_blo = o; o += t.Np * t.Kp;
+  t.off_obs = o; o += TC_ROWS * D;
+  t.off_b2 = o; o += t.Np;
+  t.off_vals = o; o += TC_ROWS * TC_MAXV;
+  t.off_nodes = o; o += TC_ROWS * TC_MAXV / 2;  // u16
+  t.off_mask = o; o += TC_ROWS * 8;             // 256-bit valid-move mask per row
+  t.total_bytes = o * 4 + 64;
+  return t;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const MappoParams p, int64_t* __restrict__ actions,
+                                                                         float* __restrict__ log_probs, float* __restrict__ probs_out,
+                                                                         int* __restrict__ error_flag) {
+  extern __shared__ __align__(1024) float tc_smem[];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(8) unsigned long long mbar;
+  const int N = p.g.num_nodes, A = p.st.num_agents, H = p.H, D = p.obs_size;
+  const TcShape ts = tc_shape(H, N, D);
+  const int Kp = ts.Kp, Np = ts.Np;
+  float* a_hi = tc_smem;
+  float* a_lo = tc_smem + ts.off_alo;
+  float* b_hi = tc_smem + ts.off_bhi;
+  float* b_lo = tc_smem + ts.off_blo;
+  float* obs_s = tc_smem + ts.off_obs;
+  float* b2_s = tc_smem + ts.off_b2;
+  float* vals = tc_smem + ts.off_vals;
+  uint16_t* vnodes = reinterpret_cast<uint16_t*>(tc_smem + ts.off_nodes);
+  unsigned* vmask = reinterpret_cast<unsigned*>(tc_smem + ts.off_mask);
+  const int tid = threadIdx.x, warp = tid >> 5, a = blockIdx.y;
+  const float* pol = p.params + (size_t)p.policy_of_agent[a] * p.policy_floats;
+  const float* W1 = pol;
+  const float* b1 = W1 + (size_t)H * D;
+  const float* W2 = b1 + H;
+  const float* b2 = W2 + (size_t)N * H;
+
+  // ---- one-time setup: TMEM columns, the MMA-completion barrier, W2 split into tf32 hi / lo in the UMMA layout
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  for (int i = tid; i < Np * (Kp / 4); i += TC_THREADS) {
+    const int kc = i / Np, n = i - kc * Np;
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kc * 4 + j;
+      w[j] = (n < N && k < H) ? __ldg(W2 + (size_t)n * H + k) : 0.0f;
+    }
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(w[0]) & 0xFFFFE000u); lo.x = w[0] - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(w[1]) & 0xFFFFE000u); lo.y = w[1] - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(w[2]) & 0xFFFFE000u); lo.z = w[2] - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(w[3]) & 0xFFFFE000u); lo.w = w[3] - hi.w;
+    reinterpret_cast<float4*>(b_hi)[i] = hi;  // float4 index (k / 4) * Np + n
+    reinterpret_cast<float4*>(b_lo)[i] = lo;
+  }
+  for (int n = tid; n < Np; n += TC_THREADS) b2_s[n] = n < N ? __ldg(b2 + n) : 0.0f;
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
+  const uint32_t lbo_a = TC_ROWS * 16, lbo_b = (uint32_t)Np * 16, sbo = 128;
+
+  const int ntiles = (p.st.num_envs + TC_ROWS - 1) / TC_ROWS;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * TC_ROWS;
+    const int nrows = min(TC_ROWS, p.st.num_envs - row0);
+    // ---- (1) obs tile; per-row bit mask of the valid moves (affordable neighbours)
+    for (int i = tid; i < TC_ROWS * D; i += TC_THREADS) {
+      const int r = i / D, o = i - r * D;
+      obs_s[i] = r < nrows ? __ldg(p.obs + ((size_t)(row0 + r) * A + a) * D + o) : 0.0f;
+    }
+    for (int i = tid; i < TC_ROWS * 8; i += TC_THREADS) vmask[i] = 0u;
+    __syncthreads();
+    if (tid < nrows) {
+      const int b = row0 + tid;
+      const int g = p.st.graph_id[b];
+      const int pos = p.st.pos[(size_t)b * A + a], money = p.st.money[(size_t)b * A + a];
+      const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
+      const int r0 = __ldg(rp + pos), deg = __ldg(rp + pos + 1) - r0;
+      const int32_t* col = p.g.col + (size_t)g * p.g.nnz_stride + r0;
+      const int32_t* wt = p.g.w + (size_t)g * p.g.nnz_stride + r0;
+      for (int k = 0; k < deg; ++k)
+        if (__ldg(wt + k) + p.st.toll <= money) {
+          const int n = __ldg(col + k);
+          vmask[tid * 8 + (n >> 5)] |= 1u << (n & 31);
+        }
+    }
+    // ---- (2) hidden layer relu(W1 obs + b1), 4 hidden units per item, split into tf32 hi / lo in the UMMA layout
+    for (int i = tid; i < TC_ROWS * (Kp / 4); i += TC_THREADS) {
+      const int kc = i / TC_ROWS, r = i - kc * TC_ROWS;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int h = kc * 4 + j;
+        float acc = 0.0f;
+        if (h < H) {
+          acc = __ldg(b1 + h);
+          for (int o = 0; o < D; ++o) acc = fmaf(__ldg(W1 + (size_t)h * D + o), obs_s[r * D + o], acc);
+          acc = fmaxf(acc, 0.0f);
+        }
+        v[j] = acc;
+      }
+      float4 hi, lo;
+      hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
+      hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
+      hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
+      hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
+      reinterpret_cast<float4*>(a_hi)[i] = hi;  // float4 index (k / 4) * 128 + row
+      reinterpret_cast<float4*>(a_lo)[i] = lo;
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    // ---- (3) one thread issues the tile's MMAs; completion arrives on the mbarrier
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      for (int ks = 0; ks < Kp / 8; ++ks) {  // one MMA covers K = 8 = two 16-byte chunks, LBO apart
+        const uint64_t dah = umma_desc_k_major(ah + ks * 2 * lbo_a, lbo_a, sbo), dal = umma_desc_k_major(al + ks * 2 * lbo_a, lbo_a, sbo);
+        const uint64_t dbh = umma_desc_k_major(bh + ks * 2 * lbo_b, lbo_b, sbo), dbl = umma_desc_k_major(bl + ks * 2 * lbo_b, lbo_b, sbo);
+        umma_tf32(tmem_base, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(tmem_base, dal, dbh, idesc, 1u);
+        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar)) : "memory");
+    }
+    // ---- (4) epilogue: warps 0-3, thread = row = TMEM lane
+    if (warp < 4) {
+      uint32_t done = 0;
+      for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(&mbar)), "r"(phase)
+            : "memory");
+      if (!done && error_flag) atomicExch(error_flag, 1);  // never expected; bounded so a mistake cannot hang the GPU
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      const int r = tid, b = row0 + r;
+      float mx = -CUDART_INF_F;
+      for (int c0 = 0; c0 < Np; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < N) mx = fmaxf(mx, v[j] + b2_s[c0 + j]);
+      }
+      float Z = 0.0f;
+      int nv = 0;
+      for (int c0 = 0; c0 < Np; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        const unsigned bits = (vmask[r * 8 + (c0 >> 5)] >> (c0 & 31)) & 0xFFFFu;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j < N) {
+            const float e = __expf(v[j] + b2_s[c0 + j] - mx);
+            Z += e;
+            if ((bits >> j) & 1u) {
+              if (nv < TC_MAXV) {
+                vals[r * TC_MAXV + nv] = e;
+                vnodes[r * TC_MAXV + nv] = (uint16_t)(c0 + j);
+              }
+              ++nv;
+            }
+          }
+        }
+      }
+      if (r < nrows) {
+        if (nv > TC_MAXV && error_flag) atomicExch(error_flag, 2);
+        nv = min(nv, TC_MAXV);
+        float Sv = 0.0f;
+        for (int k = 0; k < nv; ++k) Sv += vals[r * TC_MAXV + k] / Z;
+        const int mode = Sv > 1e-8f ? 0 : (nv > 0 ? 1 : 2);  // mappo_agent.py:121-133
+        const uint4 rnd = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_MAPPO_POLICY, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
+        const float u = u01(rnd.x);
+        int action = -1;
+        float pa = 0.0f, total = 1.0f;
+        float* po = probs_out ? probs_out + ((size_t)b * A + a) * N : nullptr;
+        if (mode == 2) {
+          action = min((int)(u * (float)N), N - 1);
+          pa = 1.0f / (float)N;
+          if (po)
+            for (int n = 0; n < N; ++n) po[n] = pa;
+        } else {
+          if (po)
+            for (int n = 0; n < N; ++n) po[n] = 0.0f;
+          const float inv_nv = 1.0f / (float)max(nv, 1), den = Sv + 1e-8f;
+          total = 0.0f;
+          for (int k = 0; k < nv; ++k) {
+            const float pk = mode == 0 ? (vals[r * TC_MAXV + k] / Z) / den : inv_nv;
+            vals[r * TC_MAXV + k] = pk;
+            total += pk;
+            if (po) po[vnodes[r * TC_MAXV + k]] = pk;
+          }
+          const float thr = u * total;
+          float cum = 0.0f;
+          for (int k = 0; k < nv; ++k) {
+            const float pk = vals[r * TC_MAXV + k];
+            cum += pk;
+            if (thr < cum) {
+              action = vnodes[r * TC_MAXV + k];
+              pa = pk;
+              break;
+            }
+          }
+          if (action < 0) {  // rounding at the top of the CDF
+            action = vnodes[r * TC_MAXV + nv - 1];
+            pa = vals[r * TC_MAXV + nv - 1];
+          }
+        }
+        actions[(size_t)b * A + a] = action;
+        const float eps = 1.1920928955078125e-07f;  // Categorical: log(clamp(p / sum p, eps, 1 - eps))
+        log_probs[(size_t)b * A + a] = logf(fminf(fmaxf(pa / total, eps), 1.0f - eps));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    }
+    phase ^= 1u;
+    __syncthreads();  // TMEM tile and the A / mask / vals buffers are free again
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256));
+}
+
 // CentralCritic: thread per row
 __global__ void sy_mappo_values_kernel(const float* __restrict__ x, int M, int D, int H, const float* __restrict__ params, float* __restrict__ out) {
   extern __shared__ float cw[];  // W1 [H, D], b1 [H], W2 [H], b2
@@ -709,14 +1001,32 @@ int sy_gnn_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const f
   return SY_POLICY_OK;
 }
 
+int sy_policy_set_option(const char* name, int32_t value) {
+  if (name && std::strcmp(name, "mappo_tensor_cores") == 0) {
+    g_mappo_tc = value;
+    return SY_POLICY_OK;
+  }
+  return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "unknown option");
+}
+
+int sy_policy_check(sy_policy_stream_t stream) {
+  if (!g_tc_flag) return SY_POLICY_OK;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, g_tc_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag == 1) return fail(SY_POLICY_ERR_CUDA, "tensor-core MAPPO kernel: MMA completion barrier timed out");
+  if (flag == 2) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "tensor-core MAPPO kernel: a node has more valid moves than max_degree promised");
+  return SY_POLICY_OK;
+}
+
 int32_t sy_mappo_param_count(int32_t obs_size, int32_t hidden, int32_t num_nodes) {
   if (obs_size < 1 || hidden < 1 || num_nodes < 1) return 0;
   return hidden * obs_size + hidden + num_nodes * hidden + num_nodes;
 }
 
 int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const float* obs, int32_t obs_size, int32_t hidden,
-                 const float* params, const int32_t* policy_of_agent, uint64_t seed, uint32_t step_counter, int64_t* actions,
-                 float* log_probs, float* probs, sy_policy_stream_t stream) {
+                 const float* params, const int32_t* policy_of_agent, int32_t max_degree, uint64_t seed, uint32_t step_counter,
+                 int64_t* actions, float* log_probs, float* probs, sy_policy_stream_t stream) {
   if (int rc = check_common(graphs, state)) return rc;
   if (!obs || !params || !policy_of_agent || !actions || !log_probs) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL MAPPO arguments");
   if (obs_size < 1 || hidden < 1 || hidden > 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad MAPPO layer sizes");
@@ -737,6 +1047,27 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
   p.seed_lo = (unsigned)(seed & 0xFFFFFFFFu);
   p.seed_hi = (unsigned)(seed >> 32);
   p.step = step_counter;
+  // tensor-core path (tcgen05): N <= 256 nodes, operands + epilogue scratch within one SM's shared memory, and at most
+  // TC_MAXV neighbours per node (max_degree from the host; 0 = unknown -> CUDA-core kernel)
+  const TcShape ts = tc_shape(hidden, graphs->num_nodes, obs_size);
+  const bool want_tc = g_mappo_tc != 0 && max_degree > 0 && max_degree <= TC_MAXV && graphs->num_nodes <= 256 &&
+                       graphs->num_nodes >= 16 && ts.total_bytes <= 220 * 1024;
+  if (want_tc) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!g_tc_flag) CUDA_TRY(cudaMalloc(&g_tc_flag, sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(g_tc_flag, 0, sizeof(int), (cudaStream_t)stream));
+    CUDA_TRY(cudaFuncSetAttribute(sy_mappo_act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ts.total_bytes));
+    const int ntiles = (state->num_envs + TC_ROWS - 1) / TC_ROWS;
+    int gx = sms / state->num_agents;
+    if (gx < 1) gx = 1;
+    if (gx > ntiles) gx = ntiles;
+    sy_mappo_act_tc_kernel<<<dim3((unsigned)gx, (unsigned)state->num_agents), TC_THREADS, ts.total_bytes, (cudaStream_t)stream>>>(
+        p, actions, log_probs, probs, g_tc_flag);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SY_POLICY_OK;
+  }
   const size_t smem = (size_t)MP_ROWS * (p.HP + graphs->num_nodes + obs_size) * sizeof(float);
   if (smem > 220 * 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "hidden + num_nodes too large for the MAPPO kernel's shared memory");
   CUDA_TRY(cudaFuncSetAttribute(sy_mappo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -64,6 +64,7 @@ class _GraphTables:
         s.num_graphs, s.num_nodes, s.nnz_stride, s.in_stride = env.num_graphs, env.graph_nodes, col.shape[1], in_stride
         (s.row_ptr, s.col, s.w, s.in_ptr, s.in_src, s.in_coef, s.self_coef) = [x.data_ptr() for x in self.tensors]
         self.struct = s
+        self.max_degree = int(np.diff(row_ptr, axis=1).max())
         self.generation = env._gen["generation"]
         self.graphs_id = id(env.graphs)
 
@@ -220,6 +221,12 @@ class MappoPolicy(_PolicyBase):
                                    for k in ("critic.0.weight", "critic.0.bias", "critic.2.weight", "critic.2.bias")])
             self.critic_params = torch.from_numpy(flat.astype(np.float32)).to(env.device)
         self.step_counter = 0
+        self.tensor_cores = True  # let the library use the tcgen05 path when the shapes allow (include/sy_policy.h)
+
+    def check(self):
+        """synchronise and surface a (never expected) failure flag of the tensor-core kernel"""
+        with torch.cuda.device(self.env.device):
+            pc.check(self._lib.sy_policy_check(self.env._stream()))
 
     @staticmethod
     def _linear(out_f, in_f, gen):
@@ -251,8 +258,10 @@ class MappoPolicy(_PolicyBase):
         lp = torch.empty(e.num_envs, e.num_agents, dtype=torch.float32, device=e.device)
         pr = torch.empty(e.num_envs, e.num_agents, self.N, dtype=torch.float32, device=e.device) if return_probs else None
         with torch.cuda.device(e.device):
-            pc.check(self._lib.sy_mappo_act(C.byref(self._graphs()), C.byref(self._state()), obs.data_ptr(), self.obs_size,
+            graphs = self._graphs()
+            pc.check(self._lib.sy_mappo_act(C.byref(graphs), C.byref(self._state()), obs.data_ptr(), self.obs_size,
                                             self.hidden, self.params.data_ptr(), self.policy_of_agent.ctypes.data,
+                                            self._tables.max_degree if self.tensor_cores else 0,
                                             e.seed & 0xFFFFFFFFFFFFFFFF, int(step_counter) & 0xFFFFFFFF, acts.data_ptr(),
                                             lp.data_ptr(), _ptr(pr), e._stream()))
         return (acts, lp, pr) if return_probs else (acts, lp)

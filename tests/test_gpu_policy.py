@@ -118,19 +118,20 @@ def test_mappo_matches_oracle_and_reference_goldens(torch_cuda):
         mp2 = pkg.MappoPolicy(env, obs_size=D, hidden_size=H, policies=mp.policies, policy_of_agent=list(range(A)),
                               critic=mp.critic, global_obs_size=D * A)
         obs = torch.randn(B, A, D, generator=torch.Generator().manual_seed(7)).cuda()
-        acts, lp, probs = mp2.act(obs, step_counter=11, return_probs=True)
-        acts, lp, probs = acts.cpu().numpy(), lp.cpu().numpy(), probs.cpu().numpy()
         mask = env.action_mask.cpu().numpy()
         obs_h = obs.cpu().numpy()
-        modes = set()
-        for b in range(B):
-            for a in range(A):
-                sd = {k: v.numpy() for k, v in mp.policies[a].items()}
-                want = po.mappo_probs(obs_h[b, a], sd, mask[b, a].astype(np.float64))
-                np.testing.assert_allclose(probs[b, a], want, rtol=3e-5, atol=1e-9)
-                assert acts[b, a] == po.mappo_sample(probs[b, a], seed, b, 11, a), (b, a)
-                np.testing.assert_allclose(lp[b, a], po.categorical_log_prob(probs[b, a], acts[b, a]), rtol=1e-5, atol=2e-6)
-                modes.add("none" if mask[b, a].sum() == 0 else "mask")
+        for tensor_cores in (True, False):  # tcgen05 3xTF32 path and the CUDA-core path
+            mp2.tensor_cores = tensor_cores
+            acts, lp, probs = mp2.act(obs, step_counter=11, return_probs=True)
+            mp2.check()
+            acts, lp, probs = acts.cpu().numpy(), lp.cpu().numpy(), probs.cpu().numpy()
+            for b in range(B):
+                for a in range(A):
+                    sd = {k: v.numpy() for k, v in mp.policies[a].items()}
+                    want = po.mappo_probs(obs_h[b, a], sd, mask[b, a].astype(np.float64))
+                    np.testing.assert_allclose(probs[b, a], want, rtol=3e-5, atol=1e-9, err_msg=f"tc={tensor_cores} {b} {a}")
+                    assert acts[b, a] == po.mappo_sample(probs[b, a], seed, b, 11, a), (tensor_cores, b, a)
+                    np.testing.assert_allclose(lp[b, a], po.categorical_log_prob(probs[b, a], acts[b, a]), rtol=1e-5, atol=2e-6)
         gobs = torch.randn(37, D * A, generator=torch.Generator().manual_seed(8)).cuda()
         v = mp2.values(gobs).cpu().numpy()
         want_v = [po.critic_value(x, {k: t.numpy() for k, t in mp.critic.items()}) for x in gobs.cpu().numpy()]
@@ -146,7 +147,8 @@ def test_mappo_matches_oracle_and_reference_goldens(torch_cuda):
             if mask[0] == 1 or mask.sum() == 0:
                 continue  # cannot be expressed as neighbours of node 0 / covered by the live test
             nbrs = np.nonzero(mask)[0]
-            links = [(0, int(n)) for n in nbrs] + [(int(nbrs[0]), int(n)) for n in range(1, N) if mask[n] == 0]
+            rest = [int(n) for n in range(1, N) if mask[n] == 0]  # hang the other nodes off as a chain (small degrees)
+            links = [(0, int(n)) for n in nbrs] + list(zip([int(nbrs[0])] + rest[:-1], rest))
             g = pkg.GraphSpec(N, np.asarray(links), np.ones(len(links), dtype=np.int64))
             env = pkg.BatchedScotlandYardEnv(1, 1, 50, graphs=[g], seed=1)
             env.reset(init_pos=np.asarray([[int(nbrs[0]), 0]], dtype=np.int32))  # MrX on a neighbour, the officer on node 0
@@ -155,6 +157,7 @@ def test_mappo_matches_oracle_and_reference_goldens(torch_cuda):
             mp = pkg.MappoPolicy(env, obs_size=D, hidden_size=H, policies=[sd], policy_of_agent=[0, 0])
             obs = torch.from_numpy(np.stack([obs_all[t], obs_all[t]])[None]).cuda()
             _, lp, probs = mp.act(obs, return_probs=True)
+            mp.check()
             got = probs[0, 1].cpu().numpy()
             # the officer may not move onto MrX's node?  the mask rule only looks at budgets (yard.py:420-472), so it can
             np.testing.assert_allclose(got, gold[f"c{ci}_probs"][t], rtol=3e-5, atol=1e-9)

@@ -38,4 +38,8 @@ if which in ("gnn", "both"):
 if which in ("mappo", "both"):
     mp = pkg.MappoPolicy(env, obs_size=A, hidden_size=64, seed=0)
     obs = (env.pos.float() / N).unsqueeze(1).expand(B, A, A).contiguous()
-    print(f"mappo act: {timed(lambda: mp.act(obs), 5) * 1e3:.1f} us", flush=True)
+    for tc in (True, False):
+        mp.tensor_cores = tc
+        print(f"mappo act (tensor cores {tc}, max degree {mp._graphs() and mp._tables.max_degree}): "
+              f"{timed(lambda: mp.act(obs), 5) * 1e3:.1f} us", flush=True)
+        mp.check()
