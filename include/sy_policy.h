@@ -99,8 +99,8 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
                  int32_t hidden, const float* params, const int32_t* policy_of_agent, int32_t max_degree,
                  uint64_t seed, uint32_t step_counter, int64_t* actions, float* log_probs, float* probs,
                  sy_policy_stream_t stream);
-/* max_degree: largest neighbour count in the pool (0 = unknown).  With num_nodes <= 256, max_degree <= 32 and the
- * operands fitting one SM's shared memory the logits GEMM runs on the tensor cores (tcgen05, 3xTF32, accumulators in
+/* max_degree: largest neighbour count in the pool (0 = unknown).  With num_nodes <= 256, hidden <= 64, obs_size <= 16,
+ * max_degree <= 16 and the operands fitting one SM's shared memory the logits GEMM runs on the tensor cores (tcgen05, 3xTF32, accumulators in
  * tensor memory); otherwise on the CUDA cores.  sy_policy_set_option("mappo_tensor_cores", 0) forces the latter.
  * sy_policy_check synchronises the stream and reports a (never expected) failure of the tensor-core kernel. */
 int sy_policy_set_option(const char* name, int32_t value);

@@ -607,7 +607,8 @@ __global__ void __launch_bounds__(MP_THREADS, 3) sy_mappo_act_kernel(const Mappo
 // ---------------------------------------------------------------------------------------------
 constexpr int TC_ROWS = 128;
 constexpr int TC_THREADS = 256;
-constexpr int TC_MAXV = 32;  // valid moves per agent the epilogue keeps (host checks the pool's max degree)
+constexpr int TC_MAXV = 16;  // valid moves per agent the epilogue keeps per column half (host checks the pool's max degree)
+constexpr int TC_DMAX = 16;  // observation size the hidden-layer registers hold
 
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
@@ -645,7 +646,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 struct TcShape {
   int Kp, Np;                       // hidden padded to 8, nodes padded to 16
   int off_alo, off_bhi, off_blo;    // float offsets inside the dynamic shared memory (A_hi at 0)
-  int off_obs, off_b2, off_vals, off_nodes, off_mask, total_bytes;
+  int off_obs, off_b2, off_vals, off_nodes, off_mask, off_red, off_w1, total_bytes;
 };
 
 __host__ __device__ inline TcShape tc_shape(int H, int N, int D) {
@@ -658,9 +659,11 @@ __host__ __device__ inline TcShape tc_shape(int H, int N, int D) {
   t.off_blo = o; o += t.Np * t.Kp;
   t.off_obs = o; o += TC_ROWS * D;
   t.off_b2 = o; o += t.Np;
-  t.off_vals = o; o += TC_ROWS * TC_MAXV;
-  t.off_nodes = o; o += TC_ROWS * TC_MAXV / 2;  // u16
-  t.off_mask = o; o += TC_ROWS * 8;             // 256-bit valid-move mask per row
+  t.off_vals = o; o += TC_ROWS * 2 * TC_MAXV;
+  t.off_nodes = o; o += TC_ROWS * 2 * TC_MAXV / 2;  // u16
+  t.off_mask = o; o += TC_ROWS * 8;                 // 256-bit valid-move mask per row
+  t.off_red = o; o += 2 * TC_ROWS * 4;              // per (column half, row): max, Z, #valid, spare
+  t.off_w1 = o; o += t.Kp * (D + 1);                // W1 rows + b1, padded hidden units zero
   t.total_bytes = o * 4 + 64;
   return t;
 }
@@ -683,6 +686,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
   float* vals = tc_smem + ts.off_vals;
   uint16_t* vnodes = reinterpret_cast<uint16_t*>(tc_smem + ts.off_nodes);
   unsigned* vmask = reinterpret_cast<unsigned*>(tc_smem + ts.off_mask);
+  float* red = tc_smem + ts.off_red;
+  float* w1_s = tc_smem + ts.off_w1;  // [Kp][D + 1]: W1 row then b1
   const int tid = threadIdx.x, warp = tid >> 5, a = blockIdx.y;
   const float* pol = p.params + (size_t)p.policy_of_agent[a] * p.policy_floats;
   const float* W1 = pol;
@@ -716,12 +721,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
     reinterpret_cast<float4*>(b_lo)[i] = lo;
   }
   for (int n = tid; n < Np; n += TC_THREADS) b2_s[n] = n < N ? __ldg(b2 + n) : 0.0f;
+  for (int i = tid; i < Kp * (D + 1); i += TC_THREADS) {
+    const int h = i / (D + 1), o = i - h * (D + 1);
+    w1_s[i] = h < H ? (o < D ? __ldg(W1 + (size_t)h * D + o) : __ldg(b1 + h)) : 0.0f;
+  }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);
   const uint32_t lbo_a = TC_ROWS * 16, lbo_b = (uint32_t)Np * 16, sbo = 128;
+  // hidden layer: this thread's four hidden units (one 16-byte K chunk) stay in registers for the whole kernel
+  const int my_kc = tid >> 4;  // Kp / 4 <= 16 chunks; threads 16 apart in a chunk take rows 16 apart
+  float w1r[4][TC_DMAX], b1r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int h = min(my_kc * 4 + j, Kp - 1);
+    const bool live = my_kc * 4 + j < Kp;
+    b1r[j] = live ? w1_s[h * (D + 1) + D] : 0.0f;
+#pragma unroll
+    for (int o = 0; o < TC_DMAX; ++o) w1r[j][o] = (live && o < D) ? w1_s[h * (D + 1) + o] : 0.0f;
+  }
+  // epilogue split: warps w and w + 4 read the same TMEM lanes (rows), each one half of the columns
+  const int half = warp >> 2, erow = tid & 127;
+  const int ncb = Np / 16, cb0 = half ? (ncb + 1) / 2 : 0, cb1 = half ? ncb : (ncb + 1) / 2;
 
   const int ntiles = (p.st.num_envs + TC_ROWS - 1) / TC_ROWS;
   uint32_t phase = 0;
@@ -735,8 +758,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
     }
     for (int i = tid; i < TC_ROWS * 8; i += TC_THREADS) vmask[i] = 0u;
     __syncthreads();
-    if (tid < nrows) {
-      const int b = row0 + tid;
+    if (tid >= 128 && tid - 128 < nrows) {  // the upper warps build the masks while the lower ones start on the hidden layer
+      const int r = tid - 128, b = row0 + r;
       const int g = p.st.graph_id[b];
       const int pos = p.st.pos[(size_t)b * A + a], money = p.st.money[(size_t)b * A + a];
       const int32_t* rp = p.g.row_ptr + (size_t)g * (N + 1);
@@ -746,31 +769,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
       for (int k = 0; k < deg; ++k)
         if (__ldg(wt + k) + p.st.toll <= money) {
           const int n = __ldg(col + k);
-          vmask[tid * 8 + (n >> 5)] |= 1u << (n & 31);
+          vmask[r * 8 + (n >> 5)] |= 1u << (n & 31);
         }
     }
-    // ---- (2) hidden layer relu(W1 obs + b1), 4 hidden units per item, split into tf32 hi / lo in the UMMA layout
-    for (int i = tid; i < TC_ROWS * (Kp / 4); i += TC_THREADS) {
-      const int kc = i / TC_ROWS, r = i - kc * TC_ROWS;
-      float v[4];
+    // ---- (2) hidden layer relu(W1 obs + b1) split into tf32 hi / lo, written in the UMMA layout
+    if (my_kc < Kp / 4) {
+      for (int r = tid & 15; r < TC_ROWS; r += 16) {
+        float v[4] = {b1r[0], b1r[1], b1r[2], b1r[3]};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int h = kc * 4 + j;
-        float acc = 0.0f;
-        if (h < H) {
-          acc = __ldg(b1 + h);
-          for (int o = 0; o < D; ++o) acc = fmaf(__ldg(W1 + (size_t)h * D + o), obs_s[r * D + o], acc);
-          acc = fmaxf(acc, 0.0f);
+        for (int o = 0; o < TC_DMAX; ++o) {
+          if (o < D) {
+            const float x = obs_s[r * D + o];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = fmaf(w1r[j][o], x, v[j]);
+          }
         }
-        v[j] = acc;
+        float4 hi, lo;
+        v[0] = fmaxf(v[0], 0.0f); v[1] = fmaxf(v[1], 0.0f); v[2] = fmaxf(v[2], 0.0f); v[3] = fmaxf(v[3], 0.0f);
+        hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
+        hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
+        hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
+        hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
+        reinterpret_cast<float4*>(a_hi)[my_kc * TC_ROWS + r] = hi;  // float4 index (k / 4) * 128 + row
+        reinterpret_cast<float4*>(a_lo)[my_kc * TC_ROWS + r] = lo;
       }
-      float4 hi, lo;
-      hi.x = __uint_as_float(__float_as_uint(v[0]) & 0xFFFFE000u); lo.x = v[0] - hi.x;
-      hi.y = __uint_as_float(__float_as_uint(v[1]) & 0xFFFFE000u); lo.y = v[1] - hi.y;
-      hi.z = __uint_as_float(__float_as_uint(v[2]) & 0xFFFFE000u); lo.z = v[2] - hi.z;
-      hi.w = __uint_as_float(__float_as_uint(v[3]) & 0xFFFFE000u); lo.w = v[3] - hi.w;
-      reinterpret_cast<float4*>(a_hi)[i] = hi;  // float4 index (k / 4) * 128 + row
-      reinterpret_cast<float4*>(a_lo)[i] = lo;
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
     __syncthreads();
@@ -787,8 +809,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar)) : "memory");
     }
-    // ---- (4) epilogue: warps 0-3, thread = row = TMEM lane
-    if (warp < 4) {
+    // ---- (4) epilogue: thread = (row = TMEM lane, column half)
+    {
       uint32_t done = 0;
       for (int spin = 0; spin < (1 << 24) && !done; ++spin)
         asm volatile(
@@ -800,21 +822,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
             : "memory");
       if (!done && error_flag) atomicExch(error_flag, 1);  // never expected; bounded so a mistake cannot hang the GPU
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-      const int r = tid, b = row0 + r;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const int r = erow;
       float mx = -CUDART_INF_F;
-      for (int c0 = 0; c0 < Np; c0 += 16) {
+      for (int cb = cb0; cb < cb1; ++cb) {
         float v[16];
-        tmem_ld16(taddr + c0, v);
+        tmem_ld16(taddr + cb * 16, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c0 + j < N) mx = fmaxf(mx, v[j] + b2_s[c0 + j]);
+          if (cb * 16 + j < N) mx = fmaxf(mx, v[j] + b2_s[cb * 16 + j]);
       }
+      red[(half * TC_ROWS + r) * 4] = mx;
+      __syncthreads();
+      mx = fmaxf(red[r * 4], red[(TC_ROWS + r) * 4]);
       float Z = 0.0f;
       int nv = 0;
-      for (int c0 = 0; c0 < Np; c0 += 16) {
+      float* myvals = vals + (r * 2 + half) * TC_MAXV;
+      uint16_t* mynodes = vnodes + (r * 2 + half) * TC_MAXV;
+      for (int cb = cb0; cb < cb1; ++cb) {
         float v[16];
-        tmem_ld16(taddr + c0, v);
+        tmem_ld16(taddr + cb * 16, v);
+        const int c0 = cb * 16;
         const unsigned bits = (vmask[r * 8 + (c0 >> 5)] >> (c0 & 31)) & 0xFFFFu;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -823,20 +851,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
             Z += e;
             if ((bits >> j) & 1u) {
               if (nv < TC_MAXV) {
-                vals[r * TC_MAXV + nv] = e;
-                vnodes[r * TC_MAXV + nv] = (uint16_t)(c0 + j);
+                myvals[nv] = e;
+                mynodes[nv] = (uint16_t)(c0 + j);
               }
               ++nv;
             }
           }
         }
       }
-      if (r < nrows) {
-        if (nv > TC_MAXV && error_flag) atomicExch(error_flag, 2);
-        nv = min(nv, TC_MAXV);
+      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+      red[(half * TC_ROWS + r) * 4 + 1] = Z;
+      red[(half * TC_ROWS + r) * 4 + 2] = __int_as_float(nv);
+      __syncthreads();
+      if (half == 0 && r < nrows) {  // the lower half's thread finishes the row: valid moves of both halves, ascending
+        const int b = row0 + r;
+        const int nv0 = nv, nv1 = __float_as_int(red[(TC_ROWS + r) * 4 + 2]);
+        if ((nv0 > TC_MAXV || nv1 > TC_MAXV) && error_flag) atomicExch(error_flag, 2);
+        const int n0 = min(nv0, TC_MAXV), n1 = min(nv1, TC_MAXV), nvt = n0 + n1;
+        Z += red[(TC_ROWS + r) * 4 + 1];
+        // entry k of the row's list: first the lower half's, then the upper half's (two adjacent TC_MAXV blocks)
+        float* lv = vals + r * 2 * TC_MAXV;
+        uint16_t* ln = vnodes + r * 2 * TC_MAXV;
+#define ROW_SLOT(k) ((k) < n0 ? (k) : TC_MAXV + (k) - n0)
         float Sv = 0.0f;
-        for (int k = 0; k < nv; ++k) Sv += vals[r * TC_MAXV + k] / Z;
-        const int mode = Sv > 1e-8f ? 0 : (nv > 0 ? 1 : 2);  // mappo_agent.py:121-133
+        for (int k = 0; k < nvt; ++k) Sv += lv[ROW_SLOT(k)] / Z;
+        const int mode = Sv > 1e-8f ? 0 : (nvt > 0 ? 1 : 2);  // mappo_agent.py:121-133
         const uint4 rnd = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_MAPPO_POLICY, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
         const float u = u01(rnd.x);
         int action = -1;
@@ -850,35 +889,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         } else {
           if (po)
             for (int n = 0; n < N; ++n) po[n] = 0.0f;
-          const float inv_nv = 1.0f / (float)max(nv, 1), den = Sv + 1e-8f;
+          const float inv_nv = 1.0f / (float)max(nvt, 1), den = Sv + 1e-8f;
           total = 0.0f;
-          for (int k = 0; k < nv; ++k) {
-            const float pk = mode == 0 ? (vals[r * TC_MAXV + k] / Z) / den : inv_nv;
-            vals[r * TC_MAXV + k] = pk;
+          for (int k = 0; k < nvt; ++k) {
+            const float pk = mode == 0 ? (lv[ROW_SLOT(k)] / Z) / den : inv_nv;
+            lv[ROW_SLOT(k)] = pk;
             total += pk;
-            if (po) po[vnodes[r * TC_MAXV + k]] = pk;
+            if (po) po[ln[ROW_SLOT(k)]] = pk;
           }
           const float thr = u * total;
           float cum = 0.0f;
-          for (int k = 0; k < nv; ++k) {
-            const float pk = vals[r * TC_MAXV + k];
+          for (int k = 0; k < nvt; ++k) {
+            const float pk = lv[ROW_SLOT(k)];
             cum += pk;
             if (thr < cum) {
-              action = vnodes[r * TC_MAXV + k];
+              action = ln[ROW_SLOT(k)];
               pa = pk;
               break;
             }
           }
           if (action < 0) {  // rounding at the top of the CDF
-            action = vnodes[r * TC_MAXV + nv - 1];
-            pa = vals[r * TC_MAXV + nv - 1];
+            action = ln[ROW_SLOT(nvt - 1)];
+            pa = lv[ROW_SLOT(nvt - 1)];
           }
         }
+#undef ROW_SLOT
         actions[(size_t)b * A + a] = action;
         const float eps = 1.1920928955078125e-07f;  // Categorical: log(clamp(p / sum p, eps, 1 - eps))
         log_probs[(size_t)b * A + a] = logf(fminf(fmaxf(pa / total, eps), 1.0f - eps));
       }
-      asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     }
     phase ^= 1u;
     __syncthreads();  // TMEM tile and the A / mask / vals buffers are free again
@@ -1051,7 +1090,7 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
   // TC_MAXV neighbours per node (max_degree from the host; 0 = unknown -> CUDA-core kernel)
   const TcShape ts = tc_shape(hidden, graphs->num_nodes, obs_size);
   const bool want_tc = g_mappo_tc != 0 && max_degree > 0 && max_degree <= TC_MAXV && graphs->num_nodes <= 256 &&
-                       graphs->num_nodes >= 16 && ts.total_bytes <= 220 * 1024;
+                       graphs->num_nodes >= 16 && hidden <= 64 && obs_size <= TC_DMAX && ts.total_bytes <= 220 * 1024;
   if (want_tc) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
