@@ -720,7 +720,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
     reinterpret_cast<float4*>(b_hi)[i] = hi;  // float4 index (k / 4) * Np + n
     reinterpret_cast<float4*>(b_lo)[i] = lo;
   }
-  for (int n = tid; n < Np; n += TC_THREADS) b2_s[n] = n < N ? __ldg(b2 + n) : 0.0f;
+  // bias pre-scaled for the exp2 of the epilogue; the padded columns get -inf-like so they drop out of max and sum
+  for (int n = tid; n < Np; n += TC_THREADS) b2_s[n] = n < N ? __ldg(b2 + n) : -1e30f;
   for (int i = tid; i < Kp * (D + 1); i += TC_THREADS) {
     const int h = i / (D + 1), o = i - h * (D + 1);
     w1_s[i] = h < H ? (o < D ? __ldg(W1 + (size_t)h * D + o) : __ldg(b1 + h)) : 0.0f;
@@ -829,13 +830,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         float v[16];
         tmem_ld16(taddr + cb * 16, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (cb * 16 + j < N) mx = fmaxf(mx, v[j] + b2_s[cb * 16 + j]);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bb = reinterpret_cast<const float4*>(b2_s + cb * 16)[j4];
+          mx = fmaxf(mx, fmaxf(fmaxf(v[4 * j4] + bb.x, v[4 * j4 + 1] + bb.y), fmaxf(v[4 * j4 + 2] + bb.z, v[4 * j4 + 3] + bb.w)));
+        }
       }
       red[(half * TC_ROWS + r) * 4] = mx;
       __syncthreads();
       mx = fmaxf(red[r * 4], red[(TC_ROWS + r) * 4]);
-      float Z = 0.0f;
+      float Zp[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       int nv = 0;
       float* myvals = vals + (r * 2 + half) * TC_MAXV;
       uint16_t* mynodes = vnodes + (r * 2 + half) * TC_MAXV;
@@ -843,15 +846,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         float v[16];
         tmem_ld16(taddr + cb * 16, v);
         const int c0 = cb * 16;
-        const unsigned bits = (vmask[r * 8 + (c0 >> 5)] >> (c0 & 31)) & 0xFFFFu;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j < N) {
-            const float e = __expf(v[j] + b2_s[c0 + j] - mx);
-            Z += e;
+        for (int j4 = 0; j4 < 4; ++j4) {  // e = exp(logit - max), logit = accumulator + bias
+          const float4 bb = reinterpret_cast<const float4*>(b2_s + c0)[j4];
+          v[4 * j4 + 0] = __expf(v[4 * j4 + 0] + bb.x - mx);
+          v[4 * j4 + 1] = __expf(v[4 * j4 + 1] + bb.y - mx);
+          v[4 * j4 + 2] = __expf(v[4 * j4 + 2] + bb.z - mx);
+          v[4 * j4 + 3] = __expf(v[4 * j4 + 3] + bb.w - mx);
+          Zp[0] += v[4 * j4 + 0];
+          Zp[1] += v[4 * j4 + 1];
+          Zp[2] += v[4 * j4 + 2];
+          Zp[3] += v[4 * j4 + 3];
+        }
+        const unsigned bits = (vmask[r * 8 + (c0 >> 5)] >> (c0 & 31)) & 0xFFFFu;
+        if (bits) {  // a valid move among these 16 columns (the uncommon case): keep its e and node, ascending
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
             if ((bits >> j) & 1u) {
               if (nv < TC_MAXV) {
-                myvals[nv] = e;
+                myvals[nv] = v[j];
                 mynodes[nv] = (uint16_t)(c0 + j);
               }
               ++nv;
@@ -859,6 +872,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
           }
         }
       }
+      float Z = (Zp[0] + Zp[1]) + (Zp[2] + Zp[3]);
       asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
       red[(half * TC_ROWS + r) * 4 + 1] = Z;
       red[(half * TC_ROWS + r) * 4 + 2] = __int_as_float(nv);
