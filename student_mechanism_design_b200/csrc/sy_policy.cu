@@ -657,11 +657,11 @@ __host__ __device__ inline TcShape tc_shape(int H, int N, int D) {
   t.off_alo = o; o += TC_ROWS * t.Kp;
   t.off_bhi = o; o += t.Np * t.Kp;
   t.off_blo = o; o += t.Np * t.Kp;
-  t.off_obs = o; o += TC_ROWS * D;
+  t.off_obs = o; o += 2 * TC_ROWS * D;              // two tiles in flight
   t.off_b2 = o; o += t.Np;
   t.off_vals = o; o += TC_ROWS * 2 * TC_MAXV;
   t.off_nodes = o; o += TC_ROWS * 2 * TC_MAXV / 2;  // u16
-  t.off_mask = o; o += TC_ROWS * 8;                 // 256-bit valid-move mask per row
+  t.off_mask = o; o += 2 * TC_ROWS * 8;             // 256-bit valid-move mask per row, two tiles in flight
   t.off_red = o; o += 2 * TC_ROWS * 4;              // per (column half, row): max, Z, #valid, spare
   t.off_w1 = o; o += t.Kp * (D + 1);                // W1 rows + b1, padded hidden units zero
   t.total_bytes = o * 4 + 64;
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
                                                                          int* __restrict__ error_flag) {
   extern __shared__ __align__(1024) float tc_smem[];
   __shared__ uint32_t tmem_base_s;
-  __shared__ __align__(8) unsigned long long mbar;
+  __shared__ __align__(8) unsigned long long mbar[2];  // MMA completion, one per accumulator buffer
   const int N = p.g.num_nodes, A = p.st.num_agents, H = p.H, D = p.obs_size;
   const TcShape ts = tc_shape(H, N, D);
   const int Kp = ts.Kp, Np = ts.Np;
@@ -681,11 +681,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
   float* a_lo = tc_smem + ts.off_alo;
   float* b_hi = tc_smem + ts.off_bhi;
   float* b_lo = tc_smem + ts.off_blo;
-  float* obs_s = tc_smem + ts.off_obs;
+  float* obs_all = tc_smem + ts.off_obs;
   float* b2_s = tc_smem + ts.off_b2;
   float* vals = tc_smem + ts.off_vals;
   uint16_t* vnodes = reinterpret_cast<uint16_t*>(tc_smem + ts.off_nodes);
-  unsigned* vmask = reinterpret_cast<unsigned*>(tc_smem + ts.off_mask);
+  unsigned* vmask_all = reinterpret_cast<unsigned*>(tc_smem + ts.off_mask);
   float* red = tc_smem + ts.off_red;
   float* w1_s = tc_smem + ts.off_w1;  // [Kp][D + 1]: W1 row then b1
   const int tid = threadIdx.x, warp = tid >> 5, a = blockIdx.y;
@@ -697,11 +697,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
 
   // ---- one-time setup: TMEM columns, the MMA-completion barrier, W2 split into tf32 hi / lo in the UMMA layout
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   if (tid == 32) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&mbar[1])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   for (int i = tid; i < Np * (Kp / 4); i += TC_THREADS) {
@@ -748,11 +749,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
   const int ncb = Np / 16, cb0 = half ? (ncb + 1) / 2 : 0, cb1 = half ? ncb : (ncb + 1) / 2;
 
   const int ntiles = (p.st.num_envs + TC_ROWS - 1) / TC_ROWS;
-  uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+
+  // wait for the MMAs of accumulator buffer `buf` (bounded: a mistake must not hang the GPU)
+  auto wait_mma = [&](int buf, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 24) && !done; ++spin)
+      asm volatile(
+          "{\n\t.reg .pred P1;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, P1;\n\t}\n"
+          : "=r"(done)
+          : "r"(smem_u32(&mbar[buf])), "r"(parity)
+          : "memory");
+    if (!done && error_flag) atomicExch(error_flag, 1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  };
+
+  // front half of a tile: obs + valid-move masks + hidden layer into the A operand, then its MMAs are issued into
+  // accumulator buffer `buf` (256 TMEM columns each); they run while the previous tile's epilogue executes
+  auto front = [&](int tile, int buf) {
     const int row0 = tile * TC_ROWS;
     const int nrows = min(TC_ROWS, p.st.num_envs - row0);
-    // ---- (1) obs tile; per-row bit mask of the valid moves (affordable neighbours)
+    float* obs_s = obs_all + buf * TC_ROWS * D;
+    unsigned* vmask = vmask_all + buf * TC_ROWS * 8;
     for (int i = tid; i < TC_ROWS * D; i += TC_THREADS) {
       const int r = i / D, o = i - r * D;
       obs_s[i] = r < nrows ? __ldg(p.obs + ((size_t)(row0 + r) * A + a) * D + o) : 0.0f;
@@ -773,8 +792,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
           vmask[r * 8 + (n >> 5)] |= 1u << (n & 31);
         }
     }
-    // ---- (2) hidden layer relu(W1 obs + b1) split into tf32 hi / lo, written in the UMMA layout
-    if (my_kc < Kp / 4) {
+    if (my_kc < Kp / 4) {  // hidden layer relu(W1 obs + b1) split into tf32 hi / lo, written in the UMMA layout
       for (int r = tid & 15; r < TC_ROWS; r += 16) {
         float v[4] = {b1r[0], b1r[1], b1r[2], b1r[3]};
 #pragma unroll
@@ -796,34 +814,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
       }
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    // ---- (3) one thread issues the tile's MMAs; completion arrives on the mbarrier
-    if (tid == 0) {
+    if (tid == 0) {  // one thread issues the tile's MMAs; completion arrives on the buffer's mbarrier
       asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
+      const uint32_t td = tmem_base + (uint32_t)buf * 256u;
       for (int ks = 0; ks < Kp / 8; ++ks) {  // one MMA covers K = 8 = two 16-byte chunks, LBO apart
         const uint64_t dah = umma_desc_k_major(ah + ks * 2 * lbo_a, lbo_a, sbo), dal = umma_desc_k_major(al + ks * 2 * lbo_a, lbo_a, sbo);
         const uint64_t dbh = umma_desc_k_major(bh + ks * 2 * lbo_b, lbo_b, sbo), dbl = umma_desc_k_major(bl + ks * 2 * lbo_b, lbo_b, sbo);
-        umma_tf32(tmem_base, dah, dbh, idesc, ks > 0 ? 1u : 0u);
-        umma_tf32(tmem_base, dal, dbh, idesc, 1u);
-        umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        umma_tf32(td, dah, dbh, idesc, ks > 0 ? 1u : 0u);
+        umma_tf32(td, dal, dbh, idesc, 1u);
+        umma_tf32(td, dah, dbl, idesc, 1u);
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar)) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar[buf])) : "memory");
     }
+  };
+
+  if ((int)blockIdx.x < ntiles) front(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int row0 = tile * TC_ROWS;
+    const int nrows = min(TC_ROWS, p.st.num_envs - row0);
+    const unsigned* vmask = vmask_all + buf * TC_ROWS * 8;
+    wait_mma(buf, (uint32_t)(it >> 1) & 1u);  // this tile's accumulators are complete, the A operand is free again
+    if (tile + (int)gridDim.x < ntiles) front(tile + gridDim.x, buf ^ 1);  // next tile's MMAs overlap this epilogue
     // ---- (4) epilogue: thread = (row = TMEM lane, column half)
     {
-      uint32_t done = 0;
-      for (int spin = 0; spin < (1 << 24) && !done; ++spin)
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t}\n"
-            : "=r"(done)
-            : "r"(smem_u32(&mbar)), "r"(phase)
-            : "memory");
-      if (!done && error_flag) atomicExch(error_flag, 1);  // never expected; bounded so a mistake cannot hang the GPU
-      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)buf * 256u;
       const int r = erow;
       float mx = -CUDART_INF_F;
       for (int cb = cb0; cb < cb1; ++cb) {
@@ -933,10 +952,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         log_probs[(size_t)b * A + a] = logf(fminf(fmaxf(pa / total, eps), 1.0f - eps));
       }
     }
-    phase ^= 1u;
-    __syncthreads();  // TMEM tile and the A / mask / vals buffers are free again
+    __syncthreads();  // this accumulator buffer and the vals / red scratch are free again
   }
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(256));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(512));
 }
 
 // CentralCritic: thread per row
