@@ -878,17 +878,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
           Zp[3] += v[4 * j4 + 3];
         }
         const unsigned bits = (vmask[r * 8 + (c0 >> 5)] >> (c0 & 31)) & 0xFFFFu;
-        if (bits) {  // a valid move among these 16 columns (the uncommon case): keep its e and node, ascending
+        // valid moves among these 16 columns (uncommon): keep their e and node, ascending.  One pass per set bit with
+        // a select chain over the register tile instead of sixteen predicated tests per chunk.
+        for (unsigned bb = bits; bb; bb &= bb - 1u) {
+          const int j = __ffs(bb) - 1;
+          float e = v[0];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if ((bits >> j) & 1u) {
-              if (nv < TC_MAXV) {
-                myvals[nv] = v[j];
-                mynodes[nv] = (uint16_t)(c0 + j);
-              }
-              ++nv;
-            }
+          for (int q = 1; q < 16; ++q) e = (j == q) ? v[q] : e;
+          if (nv < TC_MAXV) {
+            myvals[nv] = e;
+            mynodes[nv] = (uint16_t)(c0 + j);
           }
+          ++nv;
         }
       }
       float Z = (Zp[0] + Zp[1]) + (Zp[2] + Zp[3]);
@@ -906,8 +907,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         float* lv = vals + r * 2 * TC_MAXV;
         uint16_t* ln = vnodes + r * 2 * TC_MAXV;
 #define ROW_SLOT(k) ((k) < n0 ? (k) : TC_MAXV + (k) - n0)
+        const float rZ = 1.0f / Z;  // softmax = e / Z as e * (1 / Z): well inside the parity tolerance, a third of the divides
         float Sv = 0.0f;
-        for (int k = 0; k < nvt; ++k) Sv += lv[ROW_SLOT(k)] / Z;
+        for (int k = 0; k < nvt; ++k) Sv += lv[ROW_SLOT(k)] * rZ;
         const int mode = Sv > 1e-8f ? 0 : (nvt > 0 ? 1 : 2);  // mappo_agent.py:121-133
         const uint4 rnd = philox4x32(make_uint4((unsigned)(p.st.env_offset + b), p.step, RNG_MAPPO_POLICY, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
         const float u = u01(rnd.x);
@@ -922,10 +924,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
         } else {
           if (po)
             for (int n = 0; n < N; ++n) po[n] = 0.0f;
-          const float inv_nv = 1.0f / (float)max(nvt, 1), den = Sv + 1e-8f;
+          const float inv_nv = 1.0f / (float)max(nvt, 1), scale = rZ / (Sv + 1e-8f);
           total = 0.0f;
           for (int k = 0; k < nvt; ++k) {
-            const float pk = mode == 0 ? (lv[ROW_SLOT(k)] / Z) / den : inv_nv;
+            const float pk = mode == 0 ? lv[ROW_SLOT(k)] * scale : inv_nv;
             lv[ROW_SLOT(k)] = pk;
             total += pk;
             if (po) po[ln[ROW_SLOT(k)]] = pk;
