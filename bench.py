@@ -315,10 +315,12 @@ def run_cuda_arm(args, wl):
 
     # ---- end to end through the host-buffer API
     Ke = max(3, min(K, args.e2e_steps))
-    wire = torch.int64 if args.e2e_int64 else torch.int32  # host actions travel as int32 unless asked otherwise
-    wb = 8 if args.e2e_int64 else 4
+    # wire format of the host actions: node ids fit 16 bits at every BASELINE config; --e2e-int64 = the reference's dtype
+    wname = "int64" if args.e2e_int64 else (args.e2e_wire if N <= 32767 or args.e2e_wire != "int16" else "int32")
+    wire, wb = {"int64": (torch.int64, 8), "int32": (torch.int32, 4), "int16": (torch.int16, 2)}[wname]
+    fl = args.e2e_flags
     for _ in range(3):
-        env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire))
+        env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire), flags=fl)
         counter += 1
     barrier()
     sampler.active = True
@@ -326,7 +328,7 @@ def run_cuda_arm(args, wl):
     ev0.record()
     for _ in range(Ke):
         host_actions = env.sample_actions_host(step_counter=counter, dtype=wire)  # the "policy" hands over HOST actions
-        res = env.step_host(host_actions)  # H2D actions, kernel, D2H reward/flags, synchronised
+        res = env.step_host(host_actions, flags=fl)  # H2D actions, kernel, D2H reward/flags, synchronised
         counter += 1
     ev1.record()
     barrier()
@@ -334,10 +336,12 @@ def run_cuda_arm(args, wl):
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
     assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
     e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb),
-           "steps": Ke, "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 + terminated/truncated/done "
-           "u8 [B,A] + winner out to pinned host memory; observations stay on the device for the GPU policy; the D2H "
-           "count includes the random policy's actions coming back to the host"}
+           "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb, fl),
+           "steps": Ke, "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 [B,A] + winner + "
+           + ("one status byte per env (terminated/truncated/frozen bits; every agent of an env shares them)" if fl == "compact"
+              else "terminated/truncated/done u8 [B,A] + status") +
+           " out to pinned host memory; observations stay on the device for the GPU policy; the D2H count includes the "
+           "random policy's actions coming back to the host"}
 
     clocks = sampler.summary()
     if rank == 0:
@@ -385,7 +389,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype) instead of int32")
+    ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype)")
+    ap.add_argument("--e2e-wire", default="int16", choices=["int16", "int32", "int64"], help="wire format of the host actions")
+    ap.add_argument("--e2e-flags", default="compact", choices=["compact", "per_agent"],
+                    help="host results: one status byte per env, or the reference-shaped [B, A] flag arrays")
     ap.add_argument("--policy", default=None, choices=["random", "gnn", "mappo"],
                     help="who picks the actions (default: the workload's; c5 = gnn)")
     ap.add_argument("--epsilon", type=float, default=0.05, help="exploration rate of the GNN agents")

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SY_LIB_PATH: profiling experiments only (kernel variants built side by side); the product loads the in-tree library
 LIB_PATH = os.environ.get("SY_LIB_PATH") or os.path.join(_HERE, "libsy_env.so")
 
-SY_ABI_VERSION = 1
+SY_ABI_VERSION = 2
 SY_NUM_REWARD_WEIGHTS = 11
 SY_MAX_AGENTS = 16
 SY_NUM_STATS = 16
@@ -42,11 +42,11 @@ class SyObs(C.Structure):
 
 
 class SyOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("reward", "reward64", "terminated", "truncated", "done", "winner", "stats")]
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "reward64", "terminated", "truncated", "done", "winner", "stats", "status")]
 
 
 class SyHostOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "truncated", "done", "winner")]
+    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "truncated", "done", "winner", "status")]
 
 
 # name -> (restype, argtypes); must list every function include/sy_env.h declares
@@ -68,6 +68,10 @@ SIGNATURES = {
     "sy_step": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
     "sy_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut),
                                C.POINTER(SyHostOut), C.c_void_p]),
+    "sy_step_i16": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
+    "sy_step_host_i16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
+                                   C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),
+    "sy_sample_actions_i16": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_step_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
     "sy_step_host_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                    C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),

@@ -116,6 +116,7 @@ struct Params {
   SyOut out;
   const long long* actions;  // int64 [B, A] ...
   const int* actions32;      // ... or int32 [B, A] (narrow wire format of the host-buffer path), exactly one is set
+  const short* actions16;    // ... or int16 [B, A]
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr;  // writer warps: smem staging layout (bytes) and path flag
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
@@ -478,7 +479,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
-    const long long a64 = p.actions ? p.actions[o] : (long long)p.actions32[o];
+    const long long a64 = p.actions ? p.actions[o] : (p.actions32 ? (long long)p.actions32[o] : (long long)p.actions16[o]);
     const int ps = p.st.pos[o];
     sm.act[e * AS + a] = (a64 >= 0 && a64 < N) ? (int)a64 : (a64 == -1 ? -1 : -2);
     sm.pos[e * HS + a] = (u16)ps;
@@ -633,6 +634,8 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
       p.out.terminated[o] = term;
       p.out.truncated[o] = trunc;
       p.out.done[o] = term || trunc || sm.frozen[e];
+      if (p.out.status && i - e * A == 0)  // one byte per env for host loops (SY_STATUS_*)
+        p.out.status[b0 + e] = (uint8_t)((term ? SY_STATUS_TERMINATED : 0) | (trunc ? SY_STATUS_TRUNCATED : 0) | (sm.frozen[e] ? SY_STATUS_FROZEN : 0));
     }
   } else {
     // timestep, reveal schedule, same-step auto-reset, statistics
@@ -2103,8 +2106,9 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
 namespace {
 // after_logic (optional): recorded between the two kernels -- rewards / flags are final once the logic kernel is done
 int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
-              sy_stream_t stream, cudaEvent_t after_logic = nullptr) {
-  if (!e || (!actions && !actions32)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
+              sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr) {
+  if (!e || (!actions && !actions32 && !actions16)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
+  if (actions16 && e->cfg.num_nodes > 32767) return fail(SY_ERR_INVALID_ARGUMENT, "int16 actions need num_nodes <= 32767");
   if (!out || !out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
   Params p;
@@ -2113,6 +2117,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   if ((rc = check_obs(ob))) return rc;
   p.actions = reinterpret_cast<const long long*>(actions);
   p.actions32 = actions32;
+  p.actions16 = actions16;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
@@ -2154,7 +2159,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
 int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaStream_t s) {
   const size_t n = (size_t)e->cfg.num_envs * e->A;
   struct Seg { char* dst; const char* src; size_t bytes; };
-  Seg segs[5] = {};
+  Seg segs[6] = {};
   int m = 0;
   auto add = [&](void* dst, const void* src, size_t bytes) {
     if (!dst) return;
@@ -2168,6 +2173,8 @@ int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaS
   add(ho->truncated, out->truncated, n);
   add(ho->done, out->done, n);
   add(ho->winner, out->winner, (size_t)e->cfg.num_envs);
+  if (ho->status && !out->status) return fail(SY_ERR_INVALID_ARGUMENT, "SyHostOut.status needs SyOut.status");
+  add(ho->status, out->status, (size_t)e->cfg.num_envs);
   CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_logic, 0));
   for (int i = 0; i < m; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDeviceToHost, e->aux_stream));
   CUDA_TRY(cudaEventRecord(e->ev_copied, e->aux_stream));
@@ -2223,6 +2230,27 @@ int sy_step_host_i32(SyEnv* e, const int32_t* actions_host, int32_t* actions_dev
   const int rc = step_impl(e, nullptr, actions_dev, st, ob, out, stream, e->ev_logic);
   if (rc) return rc;
   return copy_results_and_sync(e, out, ho, s);
+}
+
+int sy_step_i16(SyEnv* e, const int16_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
+  return step_impl(e, nullptr, nullptr, st, ob, out, stream, nullptr, actions);
+}
+
+int sy_step_host_i16(SyEnv* e, const int16_t* actions_host, int16_t* actions_dev, const SyState* st, const SyObs* ob,
+                     const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
+  if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)e->cfg.num_envs * e->A;
+  CUDA_TRY(cudaMemcpyAsync(actions_dev, actions_host, n * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+  const int rc = step_impl(e, nullptr, nullptr, st, ob, out, stream, e->ev_logic, actions_dev);
+  if (rc) return rc;
+  return copy_results_and_sync(e, out, ho, s);
+}
+
+int sy_sample_actions_i16(SyEnv* e, const SyState* st, uint32_t step_counter, int16_t* actions, sy_stream_t stream) {
+  if (e && e->cfg.num_nodes > 32767) return fail(SY_ERR_INVALID_ARGUMENT, "int16 actions need num_nodes <= 32767");
+  return sample_impl<short>(e, st, step_counter, reinterpret_cast<short*>(actions), stream);
 }
 
 int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_t* actions, sy_stream_t stream) {

@@ -167,7 +167,8 @@ class BatchedScotlandYardEnv:
             # step results live in ONE block (reward | terminated | truncated | done | winner) so that the host-buffer
             # path moves them with a single D2H copy
             self._result_block = z(self._result_bytes(), dtype=torch.uint8)
-            (self.reward, self.terminated, self.truncated, self.done_flags, self.winner) = self._result_views(self._result_block)
+            (self.reward, self.terminated, self.truncated, self.done_flags, self.winner,
+             self.status) = self._result_views(self._result_block)
             self.reward64 = z(B, A, dtype=torch.float64) if keep_reward64 else None
             self.stats_vec = z(_cabi.SY_NUM_STATS, dtype=torch.int64) if collect_stats else None
         self._state = _cabi.SyState(_ptr(self.pos), _ptr(self.money), _ptr(self.timestep), _ptr(self.graph_id),
@@ -175,7 +176,7 @@ class BatchedScotlandYardEnv:
         self._obs = _cabi.SyObs(_ptr(self.action_mask), _ptr(self.node_features), _ptr(self.agent_budget),
                                 _ptr(self.mrx_revealed))
         self._out = _cabi.SyOut(_ptr(self.reward), _ptr(self.reward64), _ptr(self.terminated), _ptr(self.truncated),
-                                _ptr(self.done_flags), _ptr(self.winner), _ptr(self.stats_vec))
+                                _ptr(self.done_flags), _ptr(self.winner), _ptr(self.stats_vec), _ptr(self.status))
         self._static = None
         self._sample_counter = 0
         self._is_reset = False
@@ -183,7 +184,7 @@ class BatchedScotlandYardEnv:
     # ------------------------------------------------------------------ plumbing
     def _result_bytes(self) -> int:
         n = self.num_envs * self.num_agents
-        return 4 * n + 3 * n + self.num_envs
+        return 4 * n + 3 * n + 2 * self.num_envs
 
     def _result_views(self, block: torch.Tensor):
         B, A = self.num_envs, self.num_agents
@@ -191,7 +192,8 @@ class BatchedScotlandYardEnv:
         reward = block[: 4 * n].view(torch.float32).view(B, A)
         flags = [block[4 * n + k * n: 4 * n + (k + 1) * n].view(torch.bool).view(B, A) for k in range(3)]
         winner = block[7 * n: 7 * n + B].view(torch.int8)
-        return reward, flags[0], flags[1], flags[2], winner
+        status = block[7 * n + B: 7 * n + 2 * B]  # uint8 [B]: bit 0 terminated, 1 truncated, 2 frozen (done = any)
+        return reward, flags[0], flags[1], flags[2], winner, status
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -255,10 +257,11 @@ class BatchedScotlandYardEnv:
         if not self._is_reset:
             raise _cabi.SyError("step() before reset()")
         a = actions
-        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype in (torch.int64, torch.int32)
+        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype in (torch.int64, torch.int32, torch.int16)
                 and a.is_contiguous() and tuple(a.shape) == (self.num_envs, self.num_agents)):
             a = self._dev(actions, torch.int64, (self.num_envs, self.num_agents))
-        fn = self._lib.sy_step if a.dtype == torch.int64 else self._lib.sy_step_i32  # int32: narrow wire format
+        fn = {torch.int64: self._lib.sy_step, torch.int32: self._lib.sy_step_i32,
+              torch.int16: self._lib.sy_step_i16}[a.dtype]  # int32 / int16: narrow wire formats
         with torch.cuda.device(self.device):
             _cabi.check(fn(self._handle, a.data_ptr(), C.byref(self._state), C.byref(self._obs), C.byref(self._out),
                            self._stream()))
@@ -273,7 +276,8 @@ class BatchedScotlandYardEnv:
         if step_counter is None:
             step_counter = self._sample_counter
             self._sample_counter += 1
-        fn = self._lib.sy_sample_actions if out.dtype == torch.int64 else self._lib.sy_sample_actions_i32
+        fn = {torch.int64: self._lib.sy_sample_actions, torch.int32: self._lib.sy_sample_actions_i32,
+              torch.int16: self._lib.sy_sample_actions_i16}[out.dtype]
         with torch.cuda.device(self.device):
             _cabi.check(fn(self._handle, C.byref(self._state), int(step_counter) & 0xFFFFFFFF, out.data_ptr(), self._stream()))
         return out
@@ -302,48 +306,68 @@ class BatchedScotlandYardEnv:
             B, A = self.num_envs, self.num_agents
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, pin_memory=True)  # noqa: E731
             self._host_block = pin(self._result_bytes(), dtype=torch.uint8)  # same layout as the device result block
-            r, te, tr, dn, wn = self._result_views(self._host_block)
-            self._host = dict(reward=r, terminated=te, truncated=tr, done=dn, winner=wn,
-                              actions=pin(B, A, dtype=torch.int64), actions32=pin(B, A, dtype=torch.int32))
+            r, te, tr, dn, wn, st = self._result_views(self._host_block)
+            self._host = dict(reward=r, terminated=te, truncated=tr, done=dn, winner=wn, status=st,
+                              actions=pin(B, A, dtype=torch.int64), actions32=pin(B, A, dtype=torch.int32),
+                              actions16=pin(B, A, dtype=torch.int16))
             self._actions_dev = torch.empty(B, A, dtype=torch.int64, device=self.device)
             self._actions_dev32 = torch.empty(B, A, dtype=torch.int32, device=self.device)
+            self._actions_dev16 = torch.empty(B, A, dtype=torch.int16, device=self.device)
             self._host_out = _cabi.SyHostOut(*[self._host[k].data_ptr() for k in
-                                               ("reward", "terminated", "truncated", "done", "winner")])
+                                               ("reward", "terminated", "truncated", "done", "winner", "status")])
+            # compact form: the three [B, A] flag arrays stay on the device, one status byte per env travels instead
+            self._host_out_compact = _cabi.SyHostOut(r.data_ptr(), None, None, None, wn.data_ptr(), st.data_ptr())
         return self._host
 
     def host_h2d_bytes_per_step(self, action_bytes: int = 8) -> int:
         return self.num_envs * self.num_agents * action_bytes
 
-    def host_d2h_bytes_per_step(self, action_bytes: int = 8) -> int:
+    def host_d2h_bytes_per_step(self, action_bytes: int = 8, flags: str = "per_agent") -> int:
         """step_host results (+ the sampled actions when sample_actions_host feeds it)"""
         B, A = self.num_envs, self.num_agents
-        return B * A * (4 + 3) + B + B * A * action_bytes
+        return B * A * 4 + (2 * B if flags == "compact" else 3 * B * A + 2 * B) + B * A * action_bytes
 
-    def step_host(self, actions) -> Dict[str, torch.Tensor]:
+    def step_host(self, actions, flags: str = "per_agent") -> Dict[str, torch.Tensor]:
         """`step` with HOST buffers on both sides, as the reference's env is called (python ints in,
-        numpy/python values out, yard.py:144,269): actions int64 [B, A] in host memory (pinned is
-        fastest) -> H2D -> kernel -> D2H of reward / terminated / truncated / done / winner into
-        pinned host tensors; synchronous.  Observations stay on the device (`observation()`)."""
+        numpy/python values out, yard.py:144,269): actions int64 / int32 / int16 [B, A] in host memory
+        (pinned is fastest; the dtype is the wire format) -> H2D -> kernel -> D2H of reward / terminated /
+        truncated / done / winner / status into pinned host tensors; synchronous.  Observations stay on the
+        device (`observation()`).  flags="compact": only reward, winner and the status byte per env travel
+        (bit 0 terminated, bit 1 truncated, bit 2 frozen; all agents of an env share them) -- 3A - 1 fewer
+        bytes per env over PCIe; `expand_status` rebuilds the per-agent arrays on the host when needed."""
         if not self._is_reset:
             raise _cabi.SyError("step() before reset()")
         host = self._host_buffers()
         a = torch.as_tensor(actions)
-        if a.is_cuda or a.dtype not in (torch.int64, torch.int32) or not a.is_contiguous() or \
+        if a.is_cuda or a.dtype not in (torch.int64, torch.int32, torch.int16) or not a.is_contiguous() or \
                 tuple(a.shape) != (self.num_envs, self.num_agents):
             a = torch.as_tensor(np.asarray(a.cpu() if a.is_cuda else a), dtype=torch.int64).contiguous()
             if tuple(a.shape) != (self.num_envs, self.num_agents):
                 raise ValueError(f"expected shape {(self.num_envs, self.num_agents)}, got {tuple(a.shape)}")
-        narrow = a.dtype == torch.int32  # int32 host actions travel as int32 (half the PCIe bytes)
-        fn, stage = (self._lib.sy_step_host_i32, self._actions_dev32) if narrow else (self._lib.sy_step_host, self._actions_dev)
+        fn, stage = {torch.int64: (self._lib.sy_step_host, self._actions_dev),
+                     torch.int32: (self._lib.sy_step_host_i32, self._actions_dev32),
+                     torch.int16: (self._lib.sy_step_host_i16, self._actions_dev16)}[a.dtype]
+        if flags not in ("per_agent", "compact"):
+            raise ValueError("flags must be 'per_agent' or 'compact'")
+        compact = flags == "compact"
         with torch.cuda.device(self.device):
             _cabi.check(fn(self._handle, a.data_ptr(), stage.data_ptr(), C.byref(self._state), C.byref(self._obs),
-                           C.byref(self._out), C.byref(self._host_out), self._stream()))
-        return {k: host[k] for k in ("reward", "terminated", "truncated", "done", "winner")}
+                           C.byref(self._out), C.byref(self._host_out_compact if compact else self._host_out), self._stream()))
+        keys = ("reward", "winner", "status") if compact else ("reward", "terminated", "truncated", "done", "winner", "status")
+        return {k: host[k] for k in keys}
+
+    def expand_status(self, status: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """per-agent bool [B, A] views of a status byte vector (what the reference's per-agent dicts hold)"""
+        A = self.num_agents
+        te, tr = (status & 1).bool(), (status & 2).bool()
+        dn = status != 0
+        return {"terminated": te[:, None].expand(-1, A), "truncated": tr[:, None].expand(-1, A), "done": dn[:, None].expand(-1, A)}
 
     def sample_actions_host(self, step_counter: Optional[int] = None, dtype=torch.int64) -> torch.Tensor:
         """random valid actions delivered in pinned HOST memory (stands in for a host-side policy)"""
         host = self._host_buffers()
-        key, stage = ("actions", self._actions_dev) if dtype == torch.int64 else ("actions32", self._actions_dev32)
+        key, stage = {torch.int64: ("actions", self._actions_dev), torch.int32: ("actions32", self._actions_dev32),
+                      torch.int16: ("actions16", self._actions_dev16)}[dtype]
         dev_actions = self.sample_actions(out=stage, step_counter=step_counter)
         host[key].copy_(dev_actions, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

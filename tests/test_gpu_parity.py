@@ -56,7 +56,7 @@ def test_library_loaded_is_in_tree(torch_cuda):
     pkg = _pkg()
     lib = pkg.load_library()
     assert os.path.dirname(pkg.LIB_PATH).endswith("student_mechanism_design_b200")
-    assert lib.sy_abi_version() == 1
+    assert lib.sy_abi_version() == pkg._cabi.SY_ABI_VERSION == 2
 
 
 def test_graph_tables_match_oracle(torch_cuda, golden_traces):
@@ -638,6 +638,45 @@ def test_int32_wire_format_equals_int64(torch_cuda, tables):
             assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), (k, s)
             assert getattr(a, k).cpu().numpy().tobytes() == getattr(h, k).cpu().numpy().tobytes(), (k, s)
         assert res["reward"].numpy().tobytes() == a.reward.cpu().numpy().tobytes()
+    for e in (a, b, h):
+        e.close()
+
+
+def test_int16_wire_and_compact_status(torch_cuda, tables):
+    """sy_step_i16 / sy_step_host_i16 / sy_sample_actions_i16 and the one-byte-per-env status output: identical
+    dynamics, and the status bits expand to exactly the three per-agent flag arrays (also for frozen envs)."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=6, G=2, B=70, kw=dict(belief=True, reveal_interval=4), mode="fp64")
+    a, _ = _make_pair(pkg, c, tables, auto_reset=False, max_timestep=12)  # no auto-reset: finished envs freeze
+    b, _ = _make_pair(pkg, c, tables, auto_reset=False, max_timestep=12)
+    h, _ = _make_pair(pkg, c, tables, auto_reset=False, max_timestep=12)
+    for e in (a, b, h):
+        e.reset()
+    a16 = torch.empty(c["B"], c["P"] + 1, dtype=torch.int16, device="cuda")
+    seen = set()
+    for s in range(20):
+        acts = a.sample_actions(step_counter=s)
+        b.sample_actions(out=a16, step_counter=s)
+        assert torch.equal(acts.to(torch.int16), a16)
+        junk = acts.clone()
+        junk[::5] = 20_000 + s  # out of range, representable in int16
+        a.step(junk)
+        b.step(junk.to(torch.int16))
+        hacts = h.sample_actions_host(step_counter=s, dtype=torch.int16).clone()
+        hacts[::5] = 20_000 + s
+        res = h.step_host(hacts, flags="compact")
+        assert set(res) == {"reward", "winner", "status"}
+        for k in ("pos", "money", "reward64", "terminated", "truncated", "done_flags", "action_mask", "belief_map", "status"):
+            assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), (k, s)
+            assert getattr(a, k).cpu().numpy().tobytes() == getattr(h, k).cpu().numpy().tobytes(), (k, s)
+        assert res["reward"].numpy().tobytes() == a.reward.cpu().numpy().tobytes()
+        assert torch.equal(res["status"], a.status.cpu()) and torch.equal(res["winner"], a.winner.cpu())
+        ex = h.expand_status(res["status"])
+        assert torch.equal(ex["terminated"], a.terminated.cpu()) and torch.equal(ex["truncated"], a.truncated.cpu())
+        assert torch.equal(ex["done"], a.done_flags.cpu())
+        seen |= set(res["status"].tolist())
+    assert {0, 1, 2, 4} <= seen  # running, terminated, truncated and frozen envs all occurred
     for e in (a, b, h):
         e.close()
 
