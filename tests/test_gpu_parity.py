@@ -866,3 +866,29 @@ def test_device_graph_sampler_matches_oracle(torch_cuda, tables, N, E, G, P):
                                           seed=seed, graph_offset=G // 2)
         check_pool(half, 0, offset=G // 2)
         half.close()
+
+
+@pytest.mark.gpu
+def test_device_graph_sampler_large_graphs(torch_cuda):
+    """BASELINE config 4 sized graphs (1000 nodes / 2000 edges) sampled on the device: edge lists equal the oracle's
+    counter-based sampler draw for draw, the all-pairs table equals scipy's Dijkstra on the sampled graph."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import dijkstra
+
+    pkg = _pkg()
+    N, E, G, seed = 1000, 2000, 3, 77
+    env = pkg.BatchedScotlandYardEnv(64, 6, 20, graph_nodes=N, graph_edges=E, graphs="device", num_graphs=G, seed=seed,
+                                     belief=True)
+    want_pool = so.philox_graph_pool(seed, G, N, E)
+    for g in range(G):
+        assert np.array_equal(env.graphs[g].edge_links, want_pool[g].edge_links), g
+        assert np.array_equal(env.graphs[g].edges, want_pool[g].edges), g
+        W, D = env.graph_tables(g)
+        assert np.array_equal(W.astype(np.int64), want_pool[g].weight_matrix()), g
+        ref = dijkstra(csr_matrix(W.astype(np.float64)), directed=False)
+        assert np.isfinite(ref).all() and np.array_equal(D.astype(np.float64), ref), g
+    env.reset()
+    for s in range(5):  # the generic (large-N) belief path runs on the device-built neighbour lists
+        env.step(env.sample_actions(step_counter=s))
+    assert float((env.belief_map.sum(dim=1) - 1).abs().max()) < 1e-5
+    env.close()
