@@ -181,8 +181,11 @@ class GNNPolicy(_PolicyBase):
                                           e._stream()))
         return (acts, qt) if return_q else acts
 
-    def __call__(self, obs=None):  # RolloutCollector-style callable is `act`; kept explicit to avoid dense logits
-        return self.act()
+    returns_actions = True  # RolloutCollector: the kernel already does the masked epsilon-greedy selection
+    epsilon = (0.0, 0.0)    # (MrX, police) exploration rates used by __call__
+
+    def __call__(self, obs=None):
+        return self.act(self.epsilon[0], self.epsilon[1])
 
 
 class MappoPolicy(_PolicyBase):

@@ -40,7 +40,9 @@ def masked_sample(logits: torch.Tensor, mask: torch.Tensor, generator: Optional[
 
 
 class RolloutCollector:
-    """Collect `horizon` steps of all envs with a policy `policy(obs) -> logits [B, A, N]` (obs = env.observation()).
+    """Collect `horizon` steps of all envs with a policy `policy(obs) -> logits [B, A, N]` (obs = env.observation());
+    a policy object with `returns_actions = True` (e.g. `GNNPolicy`, whose kernel does the masked selection itself)
+    is called as `policy(obs) -> actions int64 [B, A]` instead.
 
     Stored per step (leading dim T): `actions` int64 [T,B,A], `reward` f32 [T,B,A], `terminated` / `truncated`
     bool [T,B], `pos` / `money` int32 [T,B,A] (state BEFORE the step) and `mrx_revealed` int32 [T,B]."""
@@ -67,8 +69,10 @@ class RolloutCollector:
             buf["pos"][t].copy_(env.pos)
             buf["money"][t].copy_(env.money)
             buf["mrx_revealed"][t].copy_(env.mrx_revealed)
-            logits = self.policy(obs)
-            actions = masked_sample(logits, env.action_mask, self.gen, self.greedy, env.DEFAULT_ACTION)
+            if getattr(self.policy, "returns_actions", False):
+                actions = self.policy(obs)
+            else:
+                actions = masked_sample(self.policy(obs), env.action_mask, self.gen, self.greedy, env.DEFAULT_ACTION)
             obs, reward, terminated, truncated, _ = env.step(actions)
             buf["actions"][t].copy_(actions)
             buf["reward"][t].copy_(reward)

@@ -102,6 +102,23 @@ def test_gnn_policy_rollout_and_state_dict(torch_cuda):
     env.close()
 
 
+def test_gnn_policy_in_the_rollout_collector(torch_cuda):
+    """row f1 + f2 together: RolloutCollector drives the env with the GNN agents' own kernel (no dense logits)."""
+    torch = torch_cuda
+    pkg = _pkg()
+    env = pkg.BatchedScotlandYardEnv(512, 3, 12, graph_nodes=40, graph_edges=75, seed=4, auto_reset=True)
+    env.reset()
+    pol = pkg.GNNPolicy(env, seed=1)
+    pol.epsilon = (0.2, 0.1)
+    traj = pkg.RolloutCollector(env, pol, 30).collect()
+    acts, pos0, money0 = traj["actions"], traj["pos"], traj["money"]
+    W = torch.from_numpy(env.graph_tables(0)[0].astype(np.int64)).cuda()
+    w = W[pos0.long(), acts.clamp_min(0)]
+    assert bool((((w > 0) & (w <= money0)) | (acts == -1)).all())
+    assert bool((acts >= 0).any()) and env.stats()["episodes"] > 0
+    env.close()
+
+
 def test_mappo_matches_oracle_and_reference_goldens(torch_cuda):
     torch = torch_cuda
     pkg = _pkg()
