@@ -119,6 +119,7 @@ struct Params {
   const short* actions16;    // ... or int16 [B, A]
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr;  // writer warps: smem staging layout (bytes) and path flag
+  int bel_share_csr;  // generic belief path gathers over the writers' staged CSR (+ 1/deg) instead of the global lists
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
@@ -921,9 +922,15 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
       s_col[k] = __ldg(tb.col + (size_t)g0 * tb.nnz_stride + k);
       s_wgt[k] = __ldg(tb.wgt + (size_t)g0 * tb.nnz_stride + k);
     }
+    if (p.bel_share_csr) {
+      float* s_inv = reinterpret_cast<float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + tb.nnz_stride * 3 + 3) & ~3));
+      for (int i = tw; i < N; i += WR_WARPS * 32) s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
+    }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
   named_barrier(2, WR_WARPS * 32);
+  // the staged CSR is complete: release the belief warps that gather over it (arrive only: the writers do not wait)
+  if (p.bel_share_csr) asm volatile("bar.arrive 3, %0;\n" ::"r"(THREADS) : "memory");
   int* fpos = s_fpos + w * SY_MAX_AGENTS;
   const int lpa = 32 / A;
   for (int e = w; e < nEnv; e += WR_WARPS) {
@@ -1001,7 +1008,13 @@ __device__ __forceinline__ void ce_flush(const Params& p, const CeAcc& acc, int 
   }
 }
 
-__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane, CeAcc& ce) {
+struct SharedCsr {  // the writer warps' staged copy of the tile's graph (null rp: not available)
+  const int* rp;
+  const uint16_t* col;
+  const float* inv;
+};
+
+__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane, CeAcc& ce, const SharedCsr sc) {
   const int N = p.N;
   const Tables& tb = p.tb;
   float* bel = p.st.belief + (size_t)b * N;
@@ -1031,6 +1044,27 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
         vx = ce_clip(unif);
       } else {
         _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+      }
+    } else if (sc.rp) {
+      // gather over the staged CSR: same neighbour order and the same 1/deg values as the padded global lists, so the
+      // result is bit-identical; every operand comes from shared memory
+      const float inv = 1.0f / tot;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
+        const int r0 = sc.rp[j], r1 = sc.rp[j + 1];
+        float a = 0.0f;
+        _Pragma("unroll 2") for (int k = r0; k < r1; ++k) {
+          const int i = sc.col[k];
+          a = fmaf(sb[i], sc.inv[i], a);
+        }
+        if (r0 == r1) a = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
+        const float v = a * inv;
+        if (!score) {
+          bel[j] = v;
+        } else {
+          const float c = ce_clip(v);
+          S += c;
+          if (j == x) vx = c;
+        }
       }
     } else {
       const float inv = 1.0f / tot;
@@ -1110,13 +1144,22 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   const bool score = p.belief_score && p.out.stats != nullptr;
   const unsigned prop = __ballot_sync(FULL, op == BEL_PROPAGATE || (score && op == BEL_DELTA));
   const unsigned any = __ballot_sync(FULL, op != BEL_KEEP);
+  // the writers stage the tile's CSR (+ 1/deg) for the large-N path; every belief warp waits for it exactly once
+  if (p.bel_share_csr) asm volatile("bar.sync 3, %0;\n" ::"r"(THREADS) : "memory");
   if (!any) return;
   CeAcc ce;
   const int g0 = __shfl_sync(FULL, g, prop ? __ffs(prop) - 1 : 0);
+  const int gfirst = __shfl_sync(FULL, g, 0);
   const bool fast = p.bel_fast && prop && __all_sync(FULL, !((prop >> lane) & 1u) || g == g0);
   if (!fast) {
     float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * N;
-    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce);
+    SharedCsr sc{nullptr, nullptr, nullptr};
+    if (p.bel_share_csr && __all_sync(FULL, lane >= nEnv || g == gfirst)) {  // the writers' `staged` condition
+      sc.rp = reinterpret_cast<const int*>(dyn + p.wr_off_csr);
+      sc.col = reinterpret_cast<const uint16_t*>(sc.rp + N + 1);
+      sc.inv = reinterpret_cast<const float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + p.tb.nnz_stride * 3 + 3) & ~3));
+    }
+    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
     ce_flush(p, ce, lane);
     return;
   }
@@ -1636,7 +1679,7 @@ struct SyEnv {
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
-  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0;
+  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0;
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
 
@@ -1724,6 +1767,7 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.wr_off_csr = env->wr_off_csr;
   p.wr_img_stride = env->wr_img_stride;
   p.wr_stage_csr = env->wr_stage_csr;
+  p.bel_share_csr = (p.dbg_skip & 5) ? 0 : env->bel_share_csr;  // the hand-over barrier needs both roles
   p.st = *st;
   if (ob) p.ob = *ob;
   if (out) p.out = *out;
@@ -1940,11 +1984,15 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
      // action_mask images, then (optionally) the graph's CSR
     const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
     const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + WR_WARPS * SY_MAX_AGENTS) * sizeof(int) + WR_WARPS * img_stride;
-    const size_t csr = (size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3 + 16;
+    // generic (large-N) belief path: it gathers over the same staged CSR, plus the 1/deg row, instead of walking the
+    // neighbour lists in global memory (at N = 1000 they no longer fit the L1 left over by the shared-memory carve-out)
+    const bool share = e->cfg.belief && !e->bel_fast;
+    const size_t csr = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + (share ? (size_t)N * sizeof(float) : 0) + 16;
     e->wr_off = (int)((e->bel_smem + 15) & ~(size_t)15);
     e->wr_img_stride = (int)img_stride;
     e->wr_off_csr = (int)(((size_t)e->wr_off + base + 15) & ~(size_t)15);
     e->wr_stage_csr = (csr <= 32 * 1024 && (size_t)e->wr_off_csr + csr <= 200 * 1024) ? 1 : 0;
+    e->bel_share_csr = (share && e->wr_stage_csr) ? 1 : 0;
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
     CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
