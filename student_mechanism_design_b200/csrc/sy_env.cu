@@ -97,6 +97,7 @@ struct Tables {
   const int2* nbr_pack;  // [G, pack_stride] belief fast path: per neighbour {byte offset of its tile row, bits of 1/deg(nbr)};
                          //  every node's list is padded to a multiple of 4 entries with {0, 0.0f}
   const int32_t* pack_ptr;  // [G, N+1] start of each node's list in nbr_pack (entries)
+  const uint16_t* deg_perm; // [G, N] nodes ordered by degree: lanes of a warp that walk neighbour lists get equal lengths
   const double* exp_neg; // [n_exp]
   const double* coverage;  // [n_cov]
   int n_exp, n_cov, G, Ns, nnz_stride, wcap, pack_stride;
@@ -924,7 +925,11 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
     }
     if (p.bel_share_csr) {
       float* s_inv = reinterpret_cast<float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + tb.nnz_stride * 3 + 3) & ~3));
-      for (int i = tw; i < N; i += WR_WARPS * 32) s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
+      uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_inv + N);
+      for (int i = tw; i < N; i += WR_WARPS * 32) {
+        s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
+        s_perm[i] = __ldg(tb.deg_perm + (size_t)g0 * N + i);
+      }
     }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
@@ -1012,6 +1017,7 @@ struct SharedCsr {  // the writer warps' staged copy of the tile's graph (null r
   const int* rp;
   const uint16_t* col;
   const float* inv;
+  const uint16_t* perm;  // nodes by degree: the 32 lanes of a gather step walk lists of (nearly) equal length
 };
 
 __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane, CeAcc& ce, const SharedCsr sc) {
@@ -1049,7 +1055,8 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
       // gather over the staged CSR: same neighbour order and the same 1/deg values as the padded global lists, so the
       // result is bit-identical; every operand comes from shared memory
       const float inv = 1.0f / tot;
-      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) {
+      _Pragma("unroll 1") for (int jj = lane; jj < N; jj += 32) {
+        const int j = sc.perm[jj];
         const int r0 = sc.rp[j], r1 = sc.rp[j + 1];
         float a = 0.0f;
         _Pragma("unroll 2") for (int k = r0; k < r1; ++k) {
@@ -1153,11 +1160,12 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   const bool fast = p.bel_fast && prop && __all_sync(FULL, !((prop >> lane) & 1u) || g == g0);
   if (!fast) {
     float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * N;
-    SharedCsr sc{nullptr, nullptr, nullptr};
+    SharedCsr sc{nullptr, nullptr, nullptr, nullptr};
     if (p.bel_share_csr && __all_sync(FULL, lane >= nEnv || g == gfirst)) {  // the writers' `staged` condition
       sc.rp = reinterpret_cast<const int*>(dyn + p.wr_off_csr);
       sc.col = reinterpret_cast<const uint16_t*>(sc.rp + N + 1);
       sc.inv = reinterpret_cast<const float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + p.tb.nnz_stride * 3 + 3) & ~3));
+      sc.perm = reinterpret_cast<const uint16_t*>(sc.inv + N);
     }
     for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
     ce_flush(p, ce, lane);
@@ -1353,6 +1361,18 @@ __global__ void sy_build_rows_kernel(int N, int Ns, int nnz_stride, int wcap, co
     cnt[((size_t)g * N + u) * (wcap + 1) + c] = (uint8_t)min(n, 255);
   }
   if (threadIdx.x == 0) inv_deg[(size_t)g * N + u] = (r1 > r0) ? 1.0f / (float)(r1 - r0) : 0.0f;
+}
+
+// nodes of every graph ordered by degree (stable counting sort, one thread per graph: setup path, N <= 65535)
+__global__ void sy_degree_perm_kernel(int N, const int32_t* row_ptr, uint16_t* perm, int* scratch /*[G, 257]*/) {
+  const int g = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  const int32_t* rp = row_ptr + (size_t)g * (N + 1);
+  int* cnt = scratch + (size_t)g * 257;
+  for (int d = 0; d <= 256; ++d) cnt[d] = 0;
+  for (int u = 0; u < N; ++u) cnt[min(rp[u + 1] - rp[u], 255) + 1] += 1;
+  for (int d = 1; d <= 256; ++d) cnt[d] += cnt[d - 1];
+  for (int u = 0; u < N; ++u) perm[(size_t)g * N + cnt[min(rp[u + 1] - rp[u], 255)]++] = (uint16_t)u;
 }
 
 // all-pairs shortest paths, one warp per (graph, source): in-place Bellman-Ford relaxation to a fixed point
@@ -1663,6 +1683,7 @@ struct SyEnv {
   void* d_inv_deg = nullptr;
   void* d_pack = nullptr;
   void* d_pack_ptr = nullptr;
+  void* d_deg_perm = nullptr;
   // device graph sampler (sy_generate_graphs): edge lists in the reference's order, per-slot edge count / status
   void* d_edges = nullptr;
   void* d_edge_w = nullptr;
@@ -1686,7 +1707,7 @@ struct SyEnv {
 namespace {
 
 void free_graph_tables(SyEnv* e) {
-  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack, &e->d_pack_ptr,
+  for (void** ptr : {&e->d_W, &e->d_D, &e->d_row_ptr, &e->d_col, &e->d_wgt, &e->d_cnt, &e->d_inv_deg, &e->d_pack, &e->d_pack_ptr, &e->d_deg_perm,
                      &e->d_edges, &e->d_edge_w, &e->d_edge_count, &e->d_gen_status, &e->d_gen_want}) {
     if (*ptr) cudaFree(*ptr);
     *ptr = nullptr;
@@ -1714,6 +1735,7 @@ int alloc_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_strid
   CUDA_TRY(cudaMalloc(&e->d_inv_deg, (size_t)G * N * sizeof(float)));
   CUDA_TRY(cudaMalloc(&e->d_pack, (size_t)G * pack_stride * sizeof(int2)));
   CUDA_TRY(cudaMalloc(&e->d_pack_ptr, (size_t)G * (N + 1) * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&e->d_deg_perm, (size_t)G * N * sizeof(uint16_t)));
   e->alloc_G = G;
   e->alloc_nnz = nnz_stride;
   e->alloc_wcap = wcap;
@@ -1958,6 +1980,16 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   e->tb.nbr_pack = (const int2*)e->d_pack;
   e->tb.pack_ptr = (const int32_t*)e->d_pack_ptr;
   e->tb.pack_stride = pack_stride;
+  {
+    int* scratch = nullptr;
+    CUDA_TRY(cudaMalloc(&scratch, (size_t)G * 257 * sizeof(int)));
+    sy_degree_perm_kernel<<<G, 32, 0, s>>>(N, (const int32_t*)e->d_row_ptr, (uint16_t*)e->d_deg_perm, scratch);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(s));
+    cudaFree(scratch);
+    e->tb.deg_perm = (const uint16_t*)e->d_deg_perm;
+  }
   // dynamic shared memory of the observe kernel's belief warps (generic: BEL_WARPS x N floats; fast path: two
   // transposed tiles [N][BSTRIDE] + per-warp partial sums)
   e->bel_smem = 0;
@@ -1987,7 +2019,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     // generic (large-N) belief path: it gathers over the same staged CSR, plus the 1/deg row, instead of walking the
     // neighbour lists in global memory (at N = 1000 they no longer fit the L1 left over by the shared-memory carve-out)
     const bool share = e->cfg.belief && !e->bel_fast;
-    const size_t csr = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + (share ? (size_t)N * sizeof(float) : 0) + 16;
+    const size_t csr = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + (share ? (size_t)N * (sizeof(float) + sizeof(uint16_t)) : 0) + 16;
     e->wr_off = (int)((e->bel_smem + 15) & ~(size_t)15);
     e->wr_img_stride = (int)img_stride;
     e->wr_off_csr = (int)(((size_t)e->wr_off + base + 15) & ~(size_t)15);
