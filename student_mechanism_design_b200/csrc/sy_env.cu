@@ -891,6 +891,7 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
 // on one graph and its CSR fits -- the graph's row pointers / neighbours / weights.  Each env's action_mask rows are
 // assembled in a per-warp shared-memory image and copied out, node_features are zero-filled and the (at most A) chunks
 // with a one rewritten whole: no byte-sized stores anywhere (they cost 60 % extra time when tried).
+template <int WRW>
 __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
   const Tables& tb = p.tb;
   const int N = p.N, A = p.A;
@@ -898,8 +899,8 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   int* s_money = s_pos + TILE * A;                      // [TILE * A]
   int* s_rev = s_money + TILE * A;                      // [TILE]
   int* s_gid = s_rev + TILE;                            // [TILE]
-  int* s_fpos = s_gid + TILE;                           // [WR_WARPS * SY_MAX_AGENTS] flat node_features index per agent
-  uint8_t* s_img = reinterpret_cast<uint8_t*>(s_fpos + WR_WARPS * SY_MAX_AGENTS) + (size_t)w * p.wr_img_stride;  // mask image
+  int* s_fpos = s_gid + TILE;                           // [WRW * SY_MAX_AGENTS] flat node_features index per agent
+  uint8_t* s_img = reinterpret_cast<uint8_t*>(s_fpos + WRW * SY_MAX_AGENTS) + (size_t)w * p.wr_img_stride;  // mask image
   int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);  // [N + 1]
   uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
   uint8_t* s_wgt = reinterpret_cast<uint8_t*>(s_col + tb.nnz_stride);
@@ -907,7 +908,7 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   const int gl = (lane < nEnv) ? p.st.graph_id[tile0 + lane] : -1;
   const int g0 = __shfl_sync(FULL, gl, 0);
   const bool staged = p.wr_stage_csr && __all_sync(FULL, gl == g0 || gl < 0);
-  for (int i = tw; i < nEnv * A; i += WR_WARPS * 32) {
+  for (int i = tw; i < nEnv * A; i += WRW * 32) {
     s_pos[i] = p.st.pos[(size_t)tile0 * A + i];
     s_money[i] = p.st.money[(size_t)tile0 * A + i];
   }
@@ -918,27 +919,27 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   if (staged) {
     const int32_t* grp = tb.row_ptr + (size_t)g0 * (N + 1);
     const int nnz = __ldg(grp + N);
-    for (int i = tw; i <= N; i += WR_WARPS * 32) s_rp[i] = __ldg(grp + i);
-    for (int k = tw; k < nnz; k += WR_WARPS * 32) {
+    for (int i = tw; i <= N; i += WRW * 32) s_rp[i] = __ldg(grp + i);
+    for (int k = tw; k < nnz; k += WRW * 32) {
       s_col[k] = __ldg(tb.col + (size_t)g0 * tb.nnz_stride + k);
       s_wgt[k] = __ldg(tb.wgt + (size_t)g0 * tb.nnz_stride + k);
     }
     if (p.bel_share_csr) {
       float* s_inv = reinterpret_cast<float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + tb.nnz_stride * 3 + 3) & ~3));
       uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_inv + N);
-      for (int i = tw; i < N; i += WR_WARPS * 32) {
+      for (int i = tw; i < N; i += WRW * 32) {
         s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
         s_perm[i] = __ldg(tb.deg_perm + (size_t)g0 * N + i);
       }
     }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
-  named_barrier(2, WR_WARPS * 32);
+  named_barrier(2, WRW * 32);
   // the staged CSR is complete: release the belief warps that gather over it (arrive only: the writers do not wait)
   if (p.bel_share_csr) asm volatile("bar.arrive 3, %0;\n" ::"r"(THREADS) : "memory");
   int* fpos = s_fpos + w * SY_MAX_AGENTS;
   const int lpa = 32 / A;
-  for (int e = w; e < nEnv; e += WR_WARPS) {
+  for (int e = w; e < nEnv; e += WRW) {
     const int b = tile0 + e;
     uint8_t* mask = p.ob.action_mask + (size_t)b * A * N;
     float* nf = p.ob.node_features + (size_t)b * N * A;
@@ -1139,6 +1140,7 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
   }
 }
 
+template <int BW>
 __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
   const int N = p.N;
   // every belief warp reads the same 32 flags / graph ids, so the branches below are uniform across the role
@@ -1167,7 +1169,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       sc.inv = reinterpret_cast<const float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + p.tb.nnz_stride * 3 + 3) & ~3));
       sc.perm = reinterpret_cast<const uint16_t*>(sc.inv + N);
     }
-    for (int e = w; e < nEnv; e += BEL_WARPS) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
+    for (int e = w; e < nEnv; e += BW) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
     ce_flush(p, ce, lane);
     return;
   }
@@ -1180,10 +1182,10 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   int* __restrict__ sptr = reinterpret_cast<int*>(dyn + p.bel_off_ptr);
   const int32_t* gptr = p.tb.pack_ptr + (size_t)g0 * (N + 1);
   const int2* gpack = p.tb.nbr_pack + (size_t)g0 * p.tb.pack_stride;
-  const int jpw = (N + BEL_WARPS - 1) / BEL_WARPS;  // warp w owns nodes [j0, j1) = list entries [q0, q1)
+  const int jpw = (N + BW - 1) / BW;  // warp w owns nodes [j0, j1) = list entries [q0, q1)
   const int j0 = min(N, w * jpw), j1 = min(N, j0 + jpw);
   const int q0 = __ldg(gptr + j0), q1 = __ldg(gptr + j1);
-  for (int e = w; e < TILE; e += BEL_WARPS) {
+  for (int e = w; e < TILE; e += BW) {
     if ((prop >> e) & 1u) {
       const float* bel = p.st.belief + (size_t)(tile0 + e) * N;
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) cp_async4(tin + j * BSTRIDE + e, bel + j);
@@ -1206,7 +1208,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
     iso[r] = __ballot_sync(FULL, qa == qb);
   }
   cp_async_wait_all();
-  named_barrier(1, BEL_WARPS * 32);
+  named_barrier(1, BW * 32);
   float sum = 0.0f;
   const unsigned char* tin_lane = reinterpret_cast<const unsigned char*>(tin + lane);
   float* tout_row = tout + j0 * BSTRIDE + lane;
@@ -1241,17 +1243,17 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
     }
   }
   part[w * 32 + lane] = sum;
-  named_barrier(1, BEL_WARPS * 32);
+  named_barrier(1, BW * 32);
   // normalise + per-env operation, coalesced copy-out: warp per env, lane = node
   const float unif = 1.0f / (float)N;
-  for (int e = w; e < nEnv; e += BEL_WARPS) {
+  for (int e = w; e < nEnv; e += BW) {
     const int ope = __shfl_sync(FULL, op, e);
     if (ope == BEL_KEEP) continue;
     float* bel = p.st.belief + (size_t)(tile0 + e) * N;
     if (ope == BEL_PROPAGATE) {
       float tot = 0.0f;
 #pragma unroll
-      for (int ww = 0; ww < BEL_WARPS; ++ww) tot += part[ww * 32 + e];
+      for (int ww = 0; ww < BW; ++ww) tot += part[ww * 32 + e];
       if (tot == 0.0f) {  // belief_module.py:29-38
         _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
       } else {
@@ -1265,7 +1267,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       if (score) {
         float tot = 0.0f, vx = 0.0f, S = 0.0f;
 #pragma unroll
-        for (int ww = 0; ww < BEL_WARPS; ++ww) tot += part[ww * 32 + e];
+        for (int ww = 0; ww < BW; ++ww) tot += part[ww * 32 + e];
         if (tot == 0.0f) {
           S = lane == 0 ? (float)N * ce_clip(unif) : 0.0f;
           vx = ce_clip(unif);
@@ -1285,19 +1287,25 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   ce_flush(p, ce, lane);
 }
 
+// BW belief warps + WRW writer warps.  <8, 8> everywhere the belief hides under the write stream (fast path); the
+// large-N generic belief path is the critical role, there the split is <12, 4> (c4: 82 -> 91 M env-steps/s).
+template <int BW, int WRW>
 __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
+  static_assert((BW + WRW) * 32 == THREADS, "the role hand-over barrier counts THREADS");
   extern __shared__ __align__(16) unsigned char dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile0 = blockIdx.x * TILE;
   const int nEnv = min(TILE, p.B - tile0);
-  const int nbw = BEL_WARPS;  // without a belief map the belief warps simply exit
+  const int nbw = BW;  // without a belief map the belief warps simply exit
   if (warp < nbw && !p.belief_on) return;
   if (warp < nbw) {
-    if (!(p.dbg_skip & 4)) belief_role(p, dyn, tile0, nEnv, warp, lane);
+    if (!(p.dbg_skip & 4)) belief_role<BW>(p, dyn, tile0, nEnv, warp, lane);
   } else if (!(p.dbg_skip & 1)) {
-    writer_role(p, dyn, tile0, nEnv, warp - nbw, lane);
+    writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
   }
 }
+
+constexpr int GEN_BEL_WARPS = 12, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
 
 // statistics: fold the replicated accumulators into the caller's vector and clear them
 __global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
@@ -1701,6 +1709,7 @@ struct SyEnv {
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
   int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0;
+  int bel_warps = BEL_WARPS, wr_warps = WR_WARPS;  // role split of the observe kernel for this pool
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
 
@@ -1741,6 +1750,13 @@ int alloc_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_strid
   e->alloc_wcap = wcap;
   e->alloc_pack = pack_stride;
   return SY_OK;
+}
+
+void launch_observe(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t s) {
+  if (e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS)
+    sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
+  else
+    sy_observe_kernel<BEL_WARPS, WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
 }
 
 int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOut* out, Params& p) {
@@ -1995,7 +2011,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   e->bel_smem = 0;
   e->bel_fast = 0;
   if (e->cfg.belief) {
-    const size_t generic = (size_t)BEL_WARPS * N * sizeof(float);
+    size_t generic = (size_t)BEL_WARPS * N * sizeof(float);
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_out = up16((size_t)N * BSTRIDE * sizeof(float));
     const size_t off_part = up16(2 * off_out);
@@ -2009,13 +2025,20 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
       e->bel_off_pack = (int)off_pack;
       e->bel_off_ptr = (int)off_ptr;
     }
+    e->bel_warps = BEL_WARPS;
+    e->wr_warps = WR_WARPS;
+    if (!e->bel_fast && THREADS / 32 > GEN_BEL_WARPS) {  // the generic path is the critical role: give it more warps
+      e->bel_warps = GEN_BEL_WARPS;
+      e->wr_warps = GEN_WR_WARPS;
+      generic = (size_t)e->bel_warps * N * sizeof(float);
+    }
     e->bel_smem = e->bel_fast && fast > generic ? fast : generic;
     if (e->bel_smem > 180 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes too large for the belief kernel's shared memory");
   }
   {  // writer staging area: pos, money [TILE, A], revealed, graph id [TILE], per-warp flat one-hot indices and
      // action_mask images, then (optionally) the graph's CSR
     const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
-    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + WR_WARPS * SY_MAX_AGENTS) * sizeof(int) + WR_WARPS * img_stride;
+    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + e->wr_warps * SY_MAX_AGENTS) * sizeof(int) + e->wr_warps * img_stride;
     // generic (large-N) belief path: it gathers over the same staged CSR, plus the 1/deg row, instead of walking the
     // neighbour lists in global memory (at N = 1000 they no longer fit the L1 left over by the shared-memory carve-out)
     const bool share = e->cfg.belief && !e->bel_fast;
@@ -2027,7 +2050,8 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     e->bel_share_csr = (share && e->wr_stage_csr) ? 1 : 0;
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
-    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
+    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
+    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
   }
   e->tb.G = G;
   e->tb.Ns = Ns;
@@ -2175,7 +2199,7 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
   sy_reset_kernel<<<(unsigned)((p.B + LOGIC_THREADS - 1) / LOGIC_THREADS), LOGIC_THREADS, 0, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  sy_observe_kernel<<<(unsigned)((p.B + TILE - 1) / TILE), THREADS, e->obs_smem, s>>>(p);
+  launch_observe(e, p, (unsigned)((p.B + TILE - 1) / TILE), s);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
@@ -2226,7 +2250,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
-  if (!(p.dbg_skip & 16)) sy_observe_kernel<<<grid, THREADS, e->obs_smem, s>>>(p);
+  if (!(p.dbg_skip & 16)) launch_observe(e, p, grid, s);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
