@@ -274,12 +274,25 @@ def run_cuda_arm(args, wl):
         choose(counter)
         env.step(actions)
         counter += 1
+    # --cuda-graph (random policy only): the K steps are replays of one captured sy_rollout_random_dev segment whose
+    # step counter lives on the device (fresh draws on every replay)
+    use_graph = not args.no_cuda_graph and not args.python_loop and policy == "random"
+    seg = 0
+    if use_graph:
+        seg = next(s for s in (50, 25, 20, 10, 5, 4, 2, 1) if K % s == 0)
+        env._sample_counter = counter
+        rollout_graph, _ctr = env.capture_rollout(seg, actions=actions)
+        counter += seg
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler.active = True
     launches0 = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0)
     ev0.record()
-    if py_loop:
+    if use_graph:  # replay the captured segment: launch latency is paid once per segment instead of three times per step
+        for _ in range(K // seg):
+            rollout_graph.replay()
+        counter += K
+    elif py_loop:
         for k in range(K):
             choose(counter)
             env.step(actions)
@@ -292,6 +305,8 @@ def run_cuda_arm(args, wl):
     barrier()
     sampler.active = False
     launches = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0) - launches0
+    if use_graph:  # kernels inside a replayed graph do not pass through the library's host-side counter
+        launches += (K // seg) * (3 * seg + 1)
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     value = world * B * K / (ms_total * 1e-3)
 
@@ -360,7 +375,8 @@ def run_cuda_arm(args, wl):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
-                       "envs_per_gpu": B, "global_envs": world * B, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": "python" if py_loop else "sy_rollout_random (C)",
+                       "envs_per_gpu": B, "global_envs": world * B, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
+                                "python" if py_loop else "sy_rollout_random (C)"),
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
@@ -396,6 +412,9 @@ def main():
     ap.add_argument("--policy", default=None, choices=["random", "gnn", "mappo"],
                     help="who picks the actions (default: the workload's; c5 = gnn)")
     ap.add_argument("--epsilon", type=float, default=0.05, help="exploration rate of the GNN agents")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="issue the timed steps with one sy_rollout_random call instead of replaying a captured CUDA graph of "
+                         "50-step segments (the default for the random policy: no launch gaps between the kernels)")
     ap.add_argument("--python-loop", action="store_true", help="issue every step from Python instead of sy_rollout_random")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -246,6 +246,12 @@ int sy_stats(SyEnv* env, int64_t* stats, sy_stream_t stream);
 int sy_rollout_random(SyEnv* env, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* state,
                       const SyObs* obs, const SyOut* out, sy_stream_t stream);
 
+/* The same with the step counter in DEVICE memory: step k samples with *step_counter_dev + k and the call ends by
+ * adding num_steps to it on the stream, so a CUDA graph captured around this call draws fresh actions on every replay
+ * (small batches are launch-latency bound: BASELINE config 2 runs ~1.8x faster from a replayed graph). */
+int sy_rollout_random_dev(SyEnv* env, int32_t num_steps, uint32_t* step_counter_dev, int64_t* actions,
+                          const SyState* state, const SyObs* obs, const SyOut* out, sy_stream_t stream);
+
 /* replaces compute_action_mask (action_mask.py:30-83) for Q queries on dense float64 inputs
  * (device pointers): adj [N,N]; weights [N,N] or NULL (adjacency as unit costs, :99-113);
  * toll_matrix [N,N] or NULL (then toll_scalar is used everywhere, :86-96); cur [Q]; budget [Q];

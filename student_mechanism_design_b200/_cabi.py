@@ -78,6 +78,8 @@ SIGNATURES = {
     "sy_sample_actions_i32": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_sample_actions": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_rollout_random_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
+                                        C.POINTER(SyOut), C.c_void_p]),
     "sy_rollout_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                     C.POINTER(SyOut), C.c_void_p]),
     "sy_action_mask_dense": (C.c_int, [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,

@@ -1323,7 +1323,9 @@ __global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
 // random valid policy: thread per (env, agent)
 // ---------------------------------------------------------------------------------------------
 template <typename ActT>
-__global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, unsigned step_counter, ActT* actions) {
+__global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, unsigned step_counter, ActT* actions,
+                                                                const unsigned* __restrict__ step_base) {
+  if (step_base) step_counter += *step_base;  // device-resident counter: a captured CUDA graph keeps advancing
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;  // B * A < 2^31 (checked at sy_create)
   if (i >= (unsigned)p.B * (unsigned)p.A) return;
   const unsigned b = i / (unsigned)p.A, a = i - b * (unsigned)p.A;
@@ -1349,6 +1351,8 @@ __global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, 
   }
   actions[i] = (ActT)act;
 }
+
+__global__ void sy_advance_counter_kernel(unsigned* counter, unsigned by) { *counter += by; }
 
 // ---------------------------------------------------------------------------------------------
 // graph table construction
@@ -2288,14 +2292,15 @@ int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaS
 }
 
 template <typename ActT>
-int sample_impl(SyEnv* e, const SyState* st, uint32_t step_counter, ActT* actions, sy_stream_t stream) {
+int sample_impl(SyEnv* e, const SyState* st, uint32_t step_counter, ActT* actions, sy_stream_t stream,
+                const uint32_t* step_base = nullptr) {
   if (!e || !actions) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   Params p;
   int rc = fill_params(e, st, nullptr, nullptr, p);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   const size_t n = (size_t)p.B * p.A;
-  sy_sample_actions_kernel<ActT><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, step_counter, actions);
+  sy_sample_actions_kernel<ActT><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, step_counter, actions, step_base);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
@@ -2382,6 +2387,20 @@ int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64
     if (rc) return rc;
     if ((rc = sy_step(e, actions, st, ob, out, stream))) return rc;
   }
+  return SY_OK;
+}
+
+int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_dev, int64_t* actions, const SyState* st,
+                          const SyObs* ob, const SyOut* out, sy_stream_t stream) {
+  if (!e || !actions || !step_counter_dev || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / counter or negative num_steps");
+  for (int32_t k = 0; k < num_steps; ++k) {
+    int rc = sample_impl<long long>(e, st, (uint32_t)k, reinterpret_cast<long long*>(actions), stream, step_counter_dev);
+    if (rc) return rc;
+    if ((rc = sy_step(e, actions, st, ob, out, stream))) return rc;
+  }
+  sy_advance_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev, (unsigned)num_steps);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
   return SY_OK;
 }
 

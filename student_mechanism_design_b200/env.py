@@ -301,6 +301,31 @@ class BatchedScotlandYardEnv:
         return actions
 
     # ------------------------------------------------------------------ host-buffer API (the reference's call shape)
+    def capture_rollout(self, num_steps: int, actions: Optional[torch.Tensor] = None):
+        """A CUDA graph of `num_steps` random-policy steps whose step counter lives on the device, so every
+        `graph.replay()` continues the rollout with fresh draws (sy_rollout_random_dev).  Small batches are
+        launch-latency bound; replaying a graph removes most of that.  Returns (graph, counter tensor)."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        if actions is None:
+            actions = torch.empty(self.num_envs, self.num_agents, dtype=torch.int64, device=self.device)
+        counter = torch.tensor([self._sample_counter], dtype=torch.int32, device=self.device)  # read as uint32
+
+        def issue():
+            _cabi.check(self._lib.sy_rollout_random_dev(self._handle, int(num_steps), counter.data_ptr(), actions.data_ptr(),
+                                                        C.byref(self._state), C.byref(self._obs), C.byref(self._out),
+                                                        self._stream()))
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device), torch.cuda.stream(side):
+            issue()  # warm-up outside the capture (it advances the rollout like any other call)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.device(self.device), torch.cuda.graph(graph, stream=side):
+            issue()
+        self._rollout_graph_keepalive = (actions, counter)
+        return graph, counter
+
     def _host_buffers(self):
         if getattr(self, "_host", None) is None:
             B, A = self.num_envs, self.num_agents

@@ -601,13 +601,23 @@ def test_rollout_random_and_cuda_graph_replay(torch_cuda, tables):
         graph.replay()
         ref.rollout_random(4, step_counter=1)
     torch.cuda.synchronize()
-    for e in (a, b, g, ref):
+    # device-resident step counter (sy_rollout_random_dev): the replayed graph keeps drawing fresh actions, so
+    # 4 warm-up steps + 5 replays of a 4-step graph are the same 24 steps as the python loop
+    d, _ = _make_pair(pkg, c, tables)
+    d.reset()
+    dgraph, counter = d.capture_rollout(4)
+    for _ in range(5):
+        dgraph.replay()
+    torch.cuda.synchronize()
+    assert int(counter.item()) == T
+    for e in (a, b, g, ref, d):
         e.stats()  # folds the library's accumulators into stats_vec
     for k in ("pos", "money", "timestep", "episode", "visits", "belief_map", "reward64", "terminated", "action_mask",
               "node_features", "stats_vec"):
         assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), k
         assert getattr(g, k).cpu().numpy().tobytes() == getattr(ref, k).cpu().numpy().tobytes(), k
-    for e in (a, b, g, ref):
+        assert getattr(a, k).cpu().numpy().tobytes() == getattr(d, k).cpu().numpy().tobytes(), ("graph + device counter", k)
+    for e in (a, b, g, ref, d):
         e.close()
 
 
