@@ -19,9 +19,11 @@
 // float4 broadcasts, everything is fp32 like the reference.  The dense [B, 2, N] Q tensor (training targets) comes from
 // the same per-node routine with lane = node.
 //
-// MAPPO design: one CTA per (128-env tile, agent): hidden layer into shared memory, then thread = action node keeps its
-// W2 row chunk in registers and walks the tile's rows (fp32 FMA-bound), logits tile in shared memory, one warp per row
-// for softmax / mask / renormalise / inverse-CDF sampling / log-prob.
+// MAPPO design: the logits GEMM [rows x H] x [H x N] runs on the tensor cores (sy_mappo_act_tc_kernel: tcgen05.mma
+// kind::tf32 as 3xTF32, accumulator tiles in TMEM, thread-per-row epilogue from tcgen05.ld; details above that kernel).
+// sy_mappo_act_kernel is the CUDA-core form for shapes the tensor path does not take (N > 256, H > 64, obs > 16,
+// degree > 16): one CTA per (64-env tile, agent), hidden layer in shared memory, thread = action node with its W2 row
+// chunk in registers walking four rows at a time, one warp per row for softmax / mask / renormalise / sampling / log-prob.
 
 #include <cuda_runtime.h>
 #include <math_constants.h>
