@@ -218,7 +218,8 @@ def run_cuda_arm(args, wl):
     lib = _cabi.load_library()
     N, P, B = wl["N"], wl["P"], args.envs or wl["B"]
     A = P + 1
-    env = BatchedScotlandYardEnv(B, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], num_graphs=1, seed=0,
+    pool_kw = dict(num_graphs=1) if args.graphs <= 1 else dict(num_graphs=args.graphs, graphs="device")  # pool sampled on the device
+    env = BatchedScotlandYardEnv(B, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], seed=0, **pool_kw,
                                  tolls=wl["toll"], belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True,
                                  env_offset=rank * B, device=f"cuda:{local}")
     env.reset()
@@ -375,7 +376,7 @@ def run_cuda_arm(args, wl):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
-                       "envs_per_gpu": B, "global_envs": world * B, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
+                       "envs_per_gpu": B, "global_envs": world * B, "graph_pool": env.num_graphs, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
                                 "python" if py_loop else "sy_rollout_random (C)"),
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
@@ -402,6 +403,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--graphs", type=int, default=1, help="graph pool size (> 1: sampled on the device; envs in blocks of 32 per graph)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -378,7 +378,7 @@ void syo_reset_all(const SyoConfig* c, int32_t B, const SyoState* st, const int3
     int32_t start[SYO_MAX_AGENTS];
     const uint32_t env = (uint32_t)(c->env_offset + b);
     st->episode[b] = 0;
-    st->gid[b] = init_gid ? init_gid[b] : (c->resample_graph ? graph_choice(c, env, 0) : (int32_t)((c->env_offset + b) % c->num_graphs));
+    st->gid[b] = init_gid ? init_gid[b] : (c->resample_graph ? graph_choice(c, env, 0) : (int32_t)(((c->env_offset + b) / 32) % c->num_graphs));
     if (init_pos) memcpy(start, init_pos + (size_t)b * A, sizeof(int32_t) * A);
     else start_positions(c, env, 0, start);
     reset_one(c, st, b, start);

@@ -733,7 +733,7 @@ class OracleBatch:
         gid, sp = [], []
         for b in range(num_envs):
             e = env_offset + b
-            g = philox_graph_choice(seed, e, 0, len(graphs)) if resample_graph else e % len(graphs)
+            g = philox_graph_choice(seed, e, 0, len(graphs)) if resample_graph else (e // 32) % len(graphs)  # blocks of 32 envs
             gid.append(g)
             sp.append(philox_start_positions(seed, e, 0, N, cfg.num_police + 1))
         return cls(cfg, graphs, gid, sp, seed, auto_reset, env_offset, resample_graph)

@@ -31,6 +31,7 @@ DEFAULT_REWARD_WEIGHTS = {
     "Mrx_closest": 0.3, "Mrx_average": 0.2, "Mrx_position": 0.1, "Mrx_time": 0.0,
     "Police_coverage": 0.05, "Police_proximity": 0.05, "Police_overlap_penalty": 0.0,
 }
+GRAPH_BLOCK = 32  # default graph assignment: env e plays on graph (e // 32) % G
 MAX_MONEY_LIMIT = 1000  # yard.py:11
 N_EXP_TABLE = 1100  # exp(-d) underflows to 0 beyond d = 745
 
@@ -243,7 +244,10 @@ class BatchedScotlandYardEnv:
         if not self._is_reset and m is not None:
             raise _cabi.SyError("the first reset must cover every env")
         if gi is None and not self._is_reset and not self.config.resample_graph:
-            gi = (torch.arange(B, device=self.device, dtype=torch.int64) + self.env_offset).remainder(self.num_graphs).to(torch.int32)
+            # blocks of 32 consecutive envs share a graph: the kernels' 32-env tiles then stay on the single-graph fast
+            # paths (shared-memory CSR, lane = env belief propagation) for pools of up to B / 32 graphs
+            gi = (torch.arange(B, device=self.device, dtype=torch.int64) + self.env_offset).div(GRAPH_BLOCK, rounding_mode="floor") \
+                .remainder(self.num_graphs).to(torch.int32)
         with torch.cuda.device(self.device):
             _cabi.check(self._lib.sy_reset(self._handle, _ptr(m), _ptr(ip), _ptr(gi), int(bool(restart)),
                                            C.byref(self._state), C.byref(self._obs), self._stream()))

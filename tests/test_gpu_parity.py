@@ -902,3 +902,36 @@ def test_device_graph_sampler_large_graphs(torch_cuda):
         env.step(env.sample_actions(step_counter=s))
     assert float((env.belief_map.sum(dim=1) - 1).abs().max()) < 1e-5
     env.close()
+
+
+@pytest.mark.gpu
+def test_interleaved_graph_pool_matches_oracle(torch_cuda, tables):
+    """Every 32-env tile holds a mix of graphs (explicit graph ids e % G instead of the default blocks of 32 envs):
+    the writers' per-env CSR walk and the generic warp-per-env belief path against the oracle, incl. belief scoring."""
+    pkg = _pkg()
+    c = CASES[2]
+    pool = pkg.generate_graph_pool(c["G"], c["N"], c["E"], seed=3)
+    B, seed = 130, 29
+    env = pkg.BatchedScotlandYardEnv(B, c["P"], c["money"], graphs=pool, seed=seed, auto_reset=True, reward_mode=c["mode"],
+                                     keep_reward64=True, reward_tables=tables, belief_ce=True, **c["kw"])
+    gid = np.arange(B) % c["G"]
+    env.reset(graph_id=gid)
+    ocfg = so.OracleConfig(num_police=c["P"], agent_money=c["money"], reward_mode=c["mode"], reveal_interval=c["kw"]["reveal_interval"],
+                           toll=c["kw"]["tolls"], belief=True, exp_table=tables[0], cov_table=tables[1])
+    ograph = [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in pool]
+    starts = [so.philox_start_positions(seed, e, 0, c["N"], c["P"] + 1) for e in range(B)]
+    ob = so.OracleBatch(ocfg, ograph, gid.tolist(), starts, seed=seed, auto_reset=True)
+    _compare_state(env, ob, c, "reset")
+    for s in range(20):
+        acts = env.sample_actions(step_counter=s)
+        a_h = acts.cpu().numpy()
+        assert np.array_equal(a_h, ob.sample_actions(s))
+        env.step(acts)
+        want = ob.step(a_h)
+        _compare_out(env, want, c, ("out", s))
+        _compare_state(env, ob, c, ("state", s))
+    ces = np.asarray(ob.belief_ces)
+    st = env.stats()
+    assert st["reveals"] == len(ces) > 0
+    np.testing.assert_allclose(env.metrics()["mean_belief_ce"], ces.mean(), rtol=1e-5, atol=1e-6)
+    env.close()
