@@ -248,22 +248,78 @@ __device__ __forceinline__ void gnn_mark_features(unsigned* feat, int my_node, i
   __syncwarp();
 }
 
+// layer 2 + read-out of node n from the layer-1 rows of the whole graph (rows [N][KP] in shared memory)
 template <int KP>
-__global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_q_dense_kernel(const GnnParams p, float* __restrict__ q) {
+__device__ __forceinline__ float q_from_rows(const float* __restrict__ ms, const GraphView& gv, const float* __restrict__ rows, int n,
+                                             float eps) {
+  float x1n[KP], z[KP];
+  const float sc = __ldg(gv.self_coef + n);
+#pragma unroll
+  for (int c4 = 0; c4 < KP / 4; ++c4) {
+    const float4 r = reinterpret_cast<const float4*>(rows + n * KP)[c4];
+    x1n[4 * c4] = r.x; x1n[4 * c4 + 1] = r.y; x1n[4 * c4 + 2] = r.z; x1n[4 * c4 + 3] = r.w;
+  }
+#pragma unroll
+  for (int k = 0; k < KP; ++k) z[k] = sc * x1n[k];
+  const int e0 = __ldg(gv.in_ptr + n), e1 = __ldg(gv.in_ptr + n + 1);
+  for (int e = e0; e < e1; ++e) {
+    const float c = __ldg(gv.in_coef + e);
+    const float* rs = rows + __ldg(gv.in_src + e) * KP;
+#pragma unroll
+    for (int c4 = 0; c4 < KP / 4; ++c4) {
+      const float4 r = reinterpret_cast<const float4*>(rs)[c4];
+      z[4 * c4] = fmaf(c, r.x, z[4 * c4]);
+      z[4 * c4 + 1] = fmaf(c, r.y, z[4 * c4 + 1]);
+      z[4 * c4 + 2] = fmaf(c, r.z, z[4 * c4 + 2]);
+      z[4 * c4 + 3] = fmaf(c, r.w, z[4 * c4 + 3]);
+    }
+  }
+  const float* ms2 = ms + Lay<KP>::CONV;
+  float acc[KP];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) acc[k] = ms2[Lay<KP>::BIAS + k];
+  matvec_acc<KP>(acc, x1n, ms2 + Lay<KP>::WAS);
+  matvec_acc<KP>(acc, z, ms2 + Lay<KP>::TH);
+  float q = ms[Lay<KP>::OUT_B];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) q = fmaf(fmaxf(x1n[k] + eps * tanh_fast(acc[k]), 0.0f), ms[Lay<KP>::OUT_W + k], q);
+  return q;
+}
+
+// Dense Q [B, 2, N] (training targets).  With room for one [N][KP] row block per warp the two layers run as two passes
+// over the nodes (every layer-1 row computed once, same arithmetic and order as q_at_node); otherwise every node
+// recomputes its neighbourhood (rows_per_warp_floats == 0).
+template <int KP>
+__global__ void __launch_bounds__(GNN_WARPS * 32) sy_gnn_q_dense_kernel(const GnnParams p, float* __restrict__ q, int rows_per_warp_floats) {
   __shared__ __align__(16) GnnSmem<KP> sm;
   extern __shared__ __align__(16) unsigned feat_all[];
   const int N = p.g.num_nodes, NF = (N + 7) & ~7;
   gnn_load_models<KP>(p, sm, feat_all, GNN_WARPS * NF);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   unsigned* feat = feat_all + w * NF;
+  float* rows = reinterpret_cast<float*>(feat_all + GNN_WARPS * NF) + (size_t)w * rows_per_warp_floats;
   for (int b = blockIdx.x * GNN_WARPS + w; b < p.st.num_envs; b += gridDim.x * GNN_WARPS) {
     const int my_node = lane < KP ? gnn_feature_node(p, b, lane) : -2;
     gnn_mark_features<KP>(feat, my_node, lane, true);
     const int g = p.st.graph_id[b];
     const GraphView gv{p.g.in_ptr + (size_t)g * (N + 1), p.g.in_src + (size_t)g * p.g.in_stride, p.g.in_coef + (size_t)g * p.g.in_stride,
                        p.g.self_coef + (size_t)g * N};
-    for (int m = 0; m < 2; ++m)
-      for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_at_node<KP>(sm.model[m], sm.c1[m], gv, feat, n, p.conv_eps);
+    for (int m = 0; m < 2; ++m) {
+      if (rows_per_warp_floats) {
+        for (int n = lane; n < N; n += 32) {
+          float x1[KP];
+          x1_at<KP>(sm.model[m], sm.c1[m], gv, feat, n, p.conv_eps, x1);
+#pragma unroll
+          for (int c4 = 0; c4 < KP / 4; ++c4)
+            reinterpret_cast<float4*>(rows + n * KP)[c4] = make_float4(x1[4 * c4], x1[4 * c4 + 1], x1[4 * c4 + 2], x1[4 * c4 + 3]);
+        }
+        __syncwarp();
+        for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_from_rows<KP>(sm.model[m], gv, rows, n, p.conv_eps);
+        __syncwarp();
+      } else {
+        for (int n = lane; n < N; n += 32) q[((size_t)b * 2 + m) * N + n] = q_at_node<KP>(sm.model[m], sm.c1[m], gv, feat, n, p.conv_eps);
+      }
+    }
     gnn_mark_features<KP>(feat, my_node, lane, false);
   }
 }
@@ -1035,13 +1091,17 @@ int sy_gnn_q_values(const SyPolicyGraphs* graphs, const SyPolicyState* state, co
   unsigned grid = 0;
   size_t dyn = 0;
   if (int rc = gnn_launch_shape(graphs, state, grid, dyn)) return rc;
-  switch (gnn_kp(K)) {
+  const int KP = gnn_kp(K);
+  int rows = ((graphs->num_nodes * KP + 3) & ~3);  // floats per warp for the layer-1 rows; 0 = recompute per node
+  if (dyn + (size_t)GNN_WARPS * rows * sizeof(float) > 150 * 1024) rows = 0;
+  dyn += (size_t)GNN_WARPS * rows * sizeof(float);
+  switch (KP) {
     case 4: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            sy_gnn_q_dense_kernel<4><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
+            sy_gnn_q_dense_kernel<4><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q, rows); break;
     case 8: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            sy_gnn_q_dense_kernel<8><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
+            sy_gnn_q_dense_kernel<8><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q, rows); break;
     default: CUDA_TRY(cudaFuncSetAttribute(sy_gnn_q_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-             sy_gnn_q_dense_kernel<16><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q); break;
+             sy_gnn_q_dense_kernel<16><<<grid, GNN_WARPS * 32, dyn, s>>>(p, q, rows); break;
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
