@@ -75,3 +75,29 @@ def test_gnn_restatement_properties():
     np.testing.assert_allclose(po.gnn_forward(x, g.edge_links, sd2), po.gnn_forward(x, g.edge_links, sd3), rtol=1e-12)
     # messages follow the stored edge direction only: reversing every edge changes the result
     assert not np.allclose(q, po.gnn_forward(x, g.edge_links[:, ::-1], sd))
+
+
+def test_host_gcn_lists_reproduce_the_oracle_aggregation():
+    """policy.gcn_in_edges (host logic of the policy kernels): aggregating with its in-edge lists and coefficients is
+    GCNConv's normalised propagation as the oracle restates it (directed edge_links.T, self-loops, deg = 1 + in-degree)."""
+    from student_mechanism_design_b200 import GraphSpec, gcn_in_edges
+
+    rng = np.random.default_rng(3)
+    graphs = [so.philox_sample_graph_once(5, g, 0, 0, 25, 45) for g in range(3)]
+    specs = [GraphSpec(g.num_nodes, g.edge_links, g.edges) for g in graphs]
+    in_ptr, in_src, in_coef, self_coef, stride = gcn_in_edges(specs)
+    assert stride == max(len(g.edges) for g in graphs)
+    for i, g in enumerate(graphs):
+        n = g.num_nodes
+        x = rng.normal(size=(n, 5))
+        got = self_coef[i][:, None].astype(np.float64) * x
+        for v in range(n):
+            for e in range(in_ptr[i, v], in_ptr[i, v + 1]):
+                got[v] += float(in_coef[i, e]) * x[in_src[i, e]]
+        src, dst = g.edge_links[:, 0].astype(np.int64), g.edge_links[:, 1].astype(np.int64)
+        deg = 1.0 + np.bincount(dst, minlength=n)
+        dis = deg ** -0.5
+        want = (dis * dis)[:, None] * x
+        np.add.at(want, dst, (dis[src] * dis[dst])[:, None] * x[src])
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+        assert in_ptr[i, -1] == len(g.edges) and (np.diff(in_ptr[i]) == np.bincount(dst, minlength=n)).all()
