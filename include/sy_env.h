@@ -223,6 +223,10 @@ int sy_step_host_i16(SyEnv* env, const int16_t* actions_host, int16_t* actions_d
                      const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
 int sy_sample_actions_i16(SyEnv* env, const SyState* state, uint32_t step_counter, int16_t* actions,
                           sy_stream_t stream);
+/* sy_sample_actions + device->host copy + synchronise in one call (a host-side policy stand-in for host loops):
+ * bytes_per_action = 8 | 4 | 2 selects the wire format of actions_dev / actions_host. */
+int sy_sample_actions_host(SyEnv* env, const SyState* state, uint32_t step_counter, void* actions_dev, void* actions_host,
+                           int32_t bytes_per_action, sy_stream_t stream);
 int sy_step_host_i32(SyEnv* env, const int32_t* actions_host, int32_t* actions_dev, const SyState* state,
                      const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
 int sy_sample_actions_i32(SyEnv* env, const SyState* state, uint32_t step_counter, int32_t* actions,

@@ -2362,6 +2362,21 @@ int sy_sample_actions_i16(SyEnv* e, const SyState* st, uint32_t step_counter, in
   return sample_impl<short>(e, st, step_counter, reinterpret_cast<short*>(actions), stream);
 }
 
+int sy_sample_actions_host(SyEnv* e, const SyState* st, uint32_t step_counter, void* actions_dev, void* actions_host,
+                           int32_t bytes_per_action, sy_stream_t stream) {
+  if (!e || !actions_dev || !actions_host) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
+  int rc;
+  if (bytes_per_action == 8) rc = sample_impl<long long>(e, st, step_counter, reinterpret_cast<long long*>(actions_dev), stream);
+  else if (bytes_per_action == 4) rc = sample_impl<int>(e, st, step_counter, reinterpret_cast<int*>(actions_dev), stream);
+  else if (bytes_per_action == 2) rc = sy_sample_actions_i16(e, st, step_counter, reinterpret_cast<int16_t*>(actions_dev), stream);
+  else return fail(SY_ERR_INVALID_ARGUMENT, "bytes_per_action must be 8, 4 or 2");
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(actions_host, actions_dev, (size_t)e->cfg.num_envs * e->A * bytes_per_action, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return SY_OK;
+}
+
 int sy_sample_actions(SyEnv* e, const SyState* st, uint32_t step_counter, int64_t* actions, sy_stream_t stream) {
   return sample_impl<long long>(e, st, step_counter, reinterpret_cast<long long*>(actions), stream);
 }

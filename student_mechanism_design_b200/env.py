@@ -397,9 +397,12 @@ class BatchedScotlandYardEnv:
         host = self._host_buffers()
         key, stage = {torch.int64: ("actions", self._actions_dev), torch.int32: ("actions32", self._actions_dev32),
                       torch.int16: ("actions16", self._actions_dev16)}[dtype]
-        dev_actions = self.sample_actions(out=stage, step_counter=step_counter)
-        host[key].copy_(dev_actions, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if step_counter is None:
+            step_counter = self._sample_counter
+            self._sample_counter += 1
+        with torch.cuda.device(self.device):  # kernel + D2H + synchronise in one C call
+            _cabi.check(self._lib.sy_sample_actions_host(self._handle, C.byref(self._state), int(step_counter) & 0xFFFFFFFF,
+                                                         stage.data_ptr(), host[key].data_ptr(), stage.element_size(), self._stream()))
         return host[key]
 
     # ------------------------------------------------------------------ device graph pool
