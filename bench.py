@@ -335,6 +335,7 @@ def run_cuda_arm(args, wl):
     wname = "int64" if args.e2e_int64 else (args.e2e_wire if N <= 32767 or args.e2e_wire != "int16" else "int32")
     wire, wb = {"int64": (torch.int64, 8), "int32": (torch.int32, 4), "int16": (torch.int16, 2)}[wname]
     fl = args.e2e_flags
+    env.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
     for _ in range(3):
         env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire), flags=fl)
         counter += 1
@@ -350,6 +351,7 @@ def run_cuda_arm(args, wl):
     barrier()
     sampler.active = False
     e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
+    env.set_host_overlap(False)
     assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
     e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb, fl),
@@ -409,6 +411,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype)")
     ap.add_argument("--e2e-wire", default="int16", choices=["int16", "int32", "int64"], help="wire format of the host actions")
+    ap.add_argument("--e2e-no-overlap", action="store_true",
+                    help="fully synchronous host calls (default: step_host returns when the results are on the host, the next "
+                         "host actions are produced while the observation kernel of the step still runs)")
     ap.add_argument("--e2e-flags", default="compact", choices=["compact", "per_agent"],
                     help="host results: one status byte per env, or the reference-shaped [B, A] flag arrays")
     ap.add_argument("--policy", default=None, choices=["random", "gnn", "mappo"],

@@ -223,6 +223,12 @@ int sy_step_host_i16(SyEnv* env, const int16_t* actions_host, int16_t* actions_d
                      const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
 int sy_sample_actions_i16(SyEnv* env, const SyState* state, uint32_t step_counter, int16_t* actions,
                           sy_stream_t stream);
+/* Host loops with overlap (off by default): sy_step_host* then return as soon as the step's RESULTS are in host_out --
+ * the observation kernel may still be running on `stream` (everything issued to that stream later is ordered after it)
+ * -- and sy_sample_actions_host runs on a library stream right behind the step's dynamics, next to the observation
+ * kernel.  A host-side policy that only needs rewards / flags / state therefore works while the observations of the
+ * same step are still being written (they never leave the device on this path). */
+int sy_set_host_overlap(SyEnv* env, int32_t on);
 /* sy_sample_actions + device->host copy + synchronise in one call (a host-side policy stand-in for host loops):
  * bytes_per_action = 8 | 4 | 2 selects the wire format of actions_dev / actions_host. */
 int sy_sample_actions_host(SyEnv* env, const SyState* state, uint32_t step_counter, void* actions_dev, void* actions_host,

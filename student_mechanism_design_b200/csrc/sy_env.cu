@@ -1707,6 +1707,9 @@ struct SyEnv {
   void* d_bel_flags = nullptr;  // [B] u8, logic/reset kernel -> observe kernel
   void* d_stats_rep = nullptr;  // [STAT_REPLICAS, SY_NUM_STATS] u64
   cudaStream_t aux_stream = nullptr;  // host-buffer path: result copies overlap the observe kernel
+  int host_overlap = 0;               // sy_set_host_overlap
+  bool aux_after_logic = false;       // the aux stream is ordered behind the last step's dynamics, nothing else touched the state since
+  cudaEvent_t ev_main = nullptr;      // orders the aux stream behind the caller's stream when that is not known
   cudaEvent_t ev_logic = nullptr, ev_copied = nullptr;
   void* d_exp = nullptr;
   void* d_cov = nullptr;
@@ -1887,6 +1890,7 @@ void sy_destroy(SyEnv* e) {
   if (e->d_bel_flags) cudaFree(e->d_bel_flags);
   if (e->d_stats_rep) cudaFree(e->d_stats_rep);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->ev_main) cudaEventDestroy(e->ev_main);
   if (e->ev_logic) cudaEventDestroy(e->ev_logic);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   delete e;
@@ -2190,6 +2194,7 @@ int sy_read_graph_tables(SyEnv* e, int32_t g, uint8_t* weights, uint16_t* apsp, 
 int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const int32_t* init_gid, int32_t restart,
              const SyState* st, const SyObs* ob, sy_stream_t stream) {
   if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
+  e->aux_after_logic = false;
   Params p;
   int rc = fill_params(e, st, ob, nullptr, p);
   if (rc) return rc;
@@ -2217,6 +2222,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
               sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr) {
   if (!e || (!actions && !actions32 && !actions16)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   if (actions16 && e->cfg.num_nodes > 32767) return fail(SY_ERR_INVALID_ARGUMENT, "int16 actions need num_nodes <= 32767");
+  e->aux_after_logic = false;
   if (!out || !out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
   Params p;
@@ -2287,7 +2293,12 @@ int copy_results_and_sync(SyEnv* e, const SyOut* out, const SyHostOut* ho, cudaS
   for (int i = 0; i < m; ++i) CUDA_TRY(cudaMemcpyAsync(segs[i].dst, segs[i].src, segs[i].bytes, cudaMemcpyDeviceToHost, e->aux_stream));
   CUDA_TRY(cudaEventRecord(e->ev_copied, e->aux_stream));
   CUDA_TRY(cudaStreamWaitEvent(s, e->ev_copied, 0));  // later work on the caller's stream is ordered after the copy
-  CUDA_TRY(cudaStreamSynchronize(s));
+  if (e->host_overlap) {  // the results are on the host; the observe kernel keeps running on the caller's stream
+    CUDA_TRY(cudaEventSynchronize(e->ev_copied));
+    e->aux_after_logic = true;
+  } else {
+    CUDA_TRY(cudaStreamSynchronize(s));
+  }
   return SY_OK;
 }
 
@@ -2365,15 +2376,34 @@ int sy_sample_actions_i16(SyEnv* e, const SyState* st, uint32_t step_counter, in
 int sy_sample_actions_host(SyEnv* e, const SyState* st, uint32_t step_counter, void* actions_dev, void* actions_host,
                            int32_t bytes_per_action, sy_stream_t stream) {
   if (!e || !actions_dev || !actions_host) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
+  // overlap mode: sample on the library stream, which sits right behind the last step's dynamics (the observe kernel of
+  // that step only READS the state the sampler reads); otherwise, or when anything else touched the state since, in
+  // order on the caller's stream
+  cudaStream_t s = (cudaStream_t)stream;
+  if (e->host_overlap) {
+    if (!e->aux_after_logic) {
+      CUDA_TRY(cudaEventRecord(e->ev_main, s));
+      CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_main, 0));
+    }
+    s = e->aux_stream;
+    stream = (sy_stream_t)s;
+  }
   int rc;
   if (bytes_per_action == 8) rc = sample_impl<long long>(e, st, step_counter, reinterpret_cast<long long*>(actions_dev), stream);
   else if (bytes_per_action == 4) rc = sample_impl<int>(e, st, step_counter, reinterpret_cast<int*>(actions_dev), stream);
   else if (bytes_per_action == 2) rc = sy_sample_actions_i16(e, st, step_counter, reinterpret_cast<int16_t*>(actions_dev), stream);
   else return fail(SY_ERR_INVALID_ARGUMENT, "bytes_per_action must be 8, 4 or 2");
   if (rc) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaMemcpyAsync(actions_host, actions_dev, (size_t)e->cfg.num_envs * e->A * bytes_per_action, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  return SY_OK;
+}
+
+int sy_set_host_overlap(SyEnv* e, int32_t on) {
+  if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
+  if (on && !e->ev_main) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming));
+  e->host_overlap = on ? 1 : 0;
+  e->aux_after_logic = false;
   return SY_OK;
 }
 

@@ -385,6 +385,13 @@ class BatchedScotlandYardEnv:
         keys = ("reward", "winner", "status") if compact else ("reward", "terminated", "truncated", "done", "winner", "status")
         return {k: host[k] for k in keys}
 
+    def set_host_overlap(self, on: bool = True):
+        """Host loops with overlap: `step_host` then returns as soon as the step's results are in the pinned host
+        tensors -- the observation kernel of that step may still be running on the stream (any later stream work,
+        incl. reading the observation tensors with torch on this stream, is ordered after it) -- and
+        `sample_actions_host` runs on a library stream next to it.  Off by default (fully synchronous calls)."""
+        _cabi.check(self._lib.sy_set_host_overlap(self._handle, int(bool(on))))
+
     def expand_status(self, status: torch.Tensor) -> Dict[str, torch.Tensor]:
         """per-agent bool [B, A] views of a status byte vector (what the reference's per-agent dicts hold)"""
         A = self.num_agents

@@ -935,3 +935,42 @@ def test_interleaved_graph_pool_matches_oracle(torch_cuda, tables):
     assert st["reveals"] == len(ces) > 0
     np.testing.assert_allclose(env.metrics()["mean_belief_ce"], ces.mean(), rtol=1e-5, atol=1e-6)
     env.close()
+
+
+@pytest.mark.gpu
+def test_host_overlap_mode_is_equivalent(torch_cuda, tables):
+    """sy_set_host_overlap: step_host returns when the results are on the host (the observation kernel may still be
+    running) and sample_actions_host runs next to it on the library stream -- same trajectory, results and
+    observations as the fully synchronous calls, also when resets / device steps are mixed in."""
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=8, G=2, B=300, kw=dict(belief=True, reveal_interval=4, tolls=1), mode="fp64")
+    a, _ = _make_pair(pkg, c, tables)
+    b, _ = _make_pair(pkg, c, tables)
+    a.reset()
+    b.reset()
+    b.set_host_overlap(True)
+    for s in range(40):
+        ha = a.sample_actions_host(step_counter=s, dtype=torch.int16)
+        hb = b.sample_actions_host(step_counter=s, dtype=torch.int16)
+        assert torch.equal(ha, hb), s
+        ra = a.step_host(ha, flags="compact")
+        rb = b.step_host(hb, flags="compact")
+        for k in ("reward", "winner", "status"):
+            assert torch.equal(ra[k], rb[k]), (k, s)
+        if s % 7 == 3:  # observations read on the stream are ordered behind the still-running kernel
+            for k in ("pos", "money", "action_mask", "node_features", "belief_map"):
+                assert torch.equal(getattr(a, k), getattr(b, k)), (k, s)
+        if s == 20:  # a device-side step and a partial reset in between: the library re-orders its stream behind them
+            acts = a.sample_actions(step_counter=1000)
+            a.step(acts)
+            b.step(b.sample_actions(step_counter=1000))
+            m = torch.zeros(c["B"], dtype=torch.bool, device="cuda")
+            m[::3] = True
+            a.reset(reset_mask=m)
+            b.reset(reset_mask=m)
+    torch.cuda.synchronize()
+    for k in ("pos", "money", "timestep", "episode", "visits", "action_mask", "node_features", "belief_map", "reward64"):
+        assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), k
+    a.close()
+    b.close()
