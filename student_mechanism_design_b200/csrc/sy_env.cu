@@ -1710,6 +1710,7 @@ struct SyEnv {
   int host_overlap = 0;               // sy_set_host_overlap
   bool aux_after_logic = false;       // the aux stream is ordered behind the last step's dynamics, nothing else touched the state since
   cudaEvent_t ev_main = nullptr;      // orders the aux stream behind the caller's stream when that is not known
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // sy_rollout_random_dev: sampler of the next step next to the observe kernel
   cudaEvent_t ev_logic = nullptr, ev_copied = nullptr;
   void* d_exp = nullptr;
   void* d_cov = nullptr;
@@ -1891,6 +1892,8 @@ void sy_destroy(SyEnv* e) {
   if (e->d_stats_rep) cudaFree(e->d_stats_rep);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
   if (e->ev_main) cudaEventDestroy(e->ev_main);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   if (e->ev_logic) cudaEventDestroy(e->ev_logic);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   delete e;
@@ -2438,12 +2441,26 @@ int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64
 int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_dev, int64_t* actions, const SyState* st,
                           const SyObs* ob, const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || !step_counter_dev || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / counter or negative num_steps");
+  // The sampler of step k + 1 only needs the state the dynamics of step k wrote, not its observations: it is forked
+  // onto the library stream right behind the logic kernel (fork / join with events, capturable), so it runs next to
+  // the observation kernel of step k instead of after it.
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!e->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+  if (!e->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  int rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
+  if (rc) return rc;
   for (int32_t k = 0; k < num_steps; ++k) {
-    int rc = sample_impl<long long>(e, st, (uint32_t)k, reinterpret_cast<long long*>(actions), stream, step_counter_dev);
-    if (rc) return rc;
-    if ((rc = sy_step(e, actions, st, ob, out, stream))) return rc;
+    const bool more = k + 1 < num_steps;
+    if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, more ? e->ev_fork : nullptr))) return rc;
+    if (more) {
+      CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+      if ((rc = sample_impl<long long>(e, st, (uint32_t)(k + 1), reinterpret_cast<long long*>(actions), (sy_stream_t)e->aux_stream, step_counter_dev)))
+        return rc;
+      CUDA_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+      CUDA_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+    }
   }
-  sy_advance_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_counter_dev, (unsigned)num_steps);
+  sy_advance_counter_kernel<<<1, 1, 0, s>>>(step_counter_dev, (unsigned)num_steps);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_OK;
