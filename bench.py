@@ -45,11 +45,11 @@ WORKLOADS = {
 METRIC, UNIT = "batched_env_steps_per_sec", "env-steps/s"
 
 
-def algorithmic_bytes_per_env_step(N, P, belief):
+def algorithmic_bytes_per_env_step(N, P, belief, nf_bytes=4):
     """actions R + pos/money/t R+W + visit RMW + belief R+W + reward/flags W
     + action_mask W + node_features W (static graph tables are L2-resident and excluded)."""
     A = P + 1
-    return 8 * A + 2 * (4 * A + 4 * A + 4) + 2 * 2 * P + (2 * 4 * N if belief else 0) + 4 * A + 3 * A + A * N + 4 * N * A
+    return 8 * A + 2 * (4 * A + 4 * A + 4) + 2 * 2 * P + (2 * 4 * N if belief else 0) + 4 * A + 3 * A + A * N + nf_bytes * N * A
 
 
 def measured_hbm_peak():
@@ -219,6 +219,8 @@ def run_cuda_arm(args, wl):
     N, P, B = wl["N"], wl["P"], args.envs or wl["B"]
     A = P + 1
     pool_kw = dict(num_graphs=1) if args.graphs <= 1 else dict(num_graphs=args.graphs, graphs="device")  # pool sampled on the device
+    if args.nf_u8:
+        pool_kw["node_features_dtype"] = torch.uint8
     env = BatchedScotlandYardEnv(B, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], seed=0, **pool_kw,
                                  tolls=wl["toll"], belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True,
                                  env_offset=rank * B, device=f"cuda:{local}")
@@ -363,12 +365,12 @@ def run_cuda_arm(args, wl):
 
     clocks = sampler.summary()
     if rank == 0:
-        bstep = algorithmic_bytes_per_env_step(N, P, wl["belief"])
+        bstep = algorithmic_bytes_per_env_step(N, P, wl["belief"], 1 if args.nf_u8 else 4)
         peak, peak_src = measured_hbm_peak()
         achieved = bstep * B / (step_kernel_ms * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and not args.nf_u8:  # the ncu capture is of the float32 observation layout
             try:
                 traffic = json.load(open(tp)).get(wl["name"], {}).get("dram_bytes_per_launch")
             except Exception:
@@ -378,7 +380,7 @@ def run_cuda_arm(args, wl):
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f64", "data": "synthetic",
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
-                       "envs_per_gpu": B, "global_envs": world * B, "graph_pool": env.num_graphs, "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
+                       "envs_per_gpu": B, "global_envs": world * B, "graph_pool": env.num_graphs, "node_features_dtype": "uint8 (opt-in)" if args.nf_u8 else "float32", "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
                                 "python" if py_loop else "sy_rollout_random (C)"),
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
@@ -405,6 +407,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--nf-u8", action="store_true",
+                    help="write node_features as uint8 instead of float32 (opt-in observation dtype; the roofline bytes follow)")
     ap.add_argument("--graphs", type=int, default=1, help="graph pool size (> 1: sampled on the device; envs in blocks of 32 per graph)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SY_ABI_VERSION 2
+#define SY_ABI_VERSION 3
 #define SY_NUM_REWARD_WEIGHTS 11 /* order = REWARD_WEIGHT_NAMES, src/reward_net.py:5-17 */
 #define SY_MAX_AGENTS 16
 #define SY_NUM_STATS 16
@@ -120,6 +120,8 @@ typedef struct SyObs {
   float* node_features;  /* [B, N, A] one-hot of positions, column 0 = MrX (blank while hidden) */
   float* agent_budget;   /* [B, A]  yard.py:329-331 */
   int32_t* mrx_revealed; /* [B] MrX node if visible this step else -1 */
+  uint8_t* node_features_u8; /* [B, N, A] or NULL.  Non-NULL: the one-hot is written here as bytes INSTEAD of the float32
+                                array (node_features may then be NULL): exact, and 3 N A fewer bytes per env-step */
 } SyObs;
 
 /* Step results (reward_calculator.py:26-92). */

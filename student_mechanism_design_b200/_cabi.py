@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SY_LIB_PATH: profiling experiments only (kernel variants built side by side); the product loads the in-tree library
 LIB_PATH = os.environ.get("SY_LIB_PATH") or os.path.join(_HERE, "libsy_env.so")
 
-SY_ABI_VERSION = 2
+SY_ABI_VERSION = 3
 SY_NUM_REWARD_WEIGHTS = 11
 SY_MAX_AGENTS = 16
 SY_NUM_STATS = 16
@@ -38,7 +38,7 @@ class SyState(C.Structure):
 
 
 class SyObs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("action_mask", "node_features", "agent_budget", "mrx_revealed")]
+    _fields_ = [(n, C.c_void_p) for n in ("action_mask", "node_features", "agent_budget", "mrx_revealed", "node_features_u8")]
 
 
 class SyOut(C.Structure):

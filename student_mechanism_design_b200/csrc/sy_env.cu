@@ -967,7 +967,18 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
     }
     __syncwarp();
     warp_copy_bytes(mask, img, A * N, lane);
-    warp_write_node_features(nf, N * A, fpos, A, lane);
+    if (p.ob.node_features_u8) {  // byte one-hot: same image-and-copy scheme as the mask (no byte-sized global stores)
+      __syncwarp();
+      for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
+      __syncwarp();
+      uint8_t* nf8 = p.ob.node_features_u8 + (size_t)b * N * A;
+      uint8_t* img8 = s_img + (int)(reinterpret_cast<uintptr_t>(nf8) & 15u);
+      if (lane < A && fpos[lane] >= 0) img8[fpos[lane]] = 1;
+      __syncwarp();
+      warp_copy_bytes(nf8, img8, N * A, lane);
+    } else {
+      warp_write_node_features(nf, N * A, fpos, A, lane);
+    }
     __syncwarp();
     for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
     __syncwarp();
@@ -1821,7 +1832,7 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
 }
 
 int check_obs(const SyObs* ob) {
-  if (!ob || !ob->action_mask || !ob->node_features || !ob->agent_budget || !ob->mrx_revealed)
+  if (!ob || !ob->action_mask || (!ob->node_features && !ob->node_features_u8) || !ob->agent_budget || !ob->mrx_revealed)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyObs has NULL members");
   return SY_OK;
 }

@@ -69,7 +69,8 @@ class BatchedScotlandYardEnv:
                  tolls: float = 0, belief: bool = False, belief_ce: bool = False, reward_mode: Optional[str] = None, seed: int = 0,
                  auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
                  device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True,
-                 graph_offset: int = 0, max_edges_per_node: int = 4, max_weight: int = 5):
+                 graph_offset: int = 0, max_edges_per_node: int = 4, max_weight: int = 5,
+                 node_features_dtype: torch.dtype = torch.float32):
         if not torch.cuda.is_available():
             raise _cabi.SyError("BatchedScotlandYardEnv needs a CUDA device; there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -162,7 +163,10 @@ class BatchedScotlandYardEnv:
             self.visits = z(B, N, dtype=torch.uint16)
             self.belief_map = z(B, N, dtype=torch.float32) if self.belief_on else None
             self.action_mask = z(B, A, N, dtype=torch.bool)
-            self.node_features = z(B, N, A, dtype=torch.float32)
+            if node_features_dtype not in (torch.float32, torch.uint8):
+                raise ValueError("node_features_dtype must be torch.float32 or torch.uint8")
+            # uint8: the one-hot is exact in a byte and the step writes 3 N A fewer bytes per env (opt-in)
+            self.node_features = z(B, N, A, dtype=node_features_dtype)
             self.agent_budget = z(B, A, dtype=torch.float32)
             self.mrx_revealed = z(B, dtype=torch.int32)
             # step results live in ONE block (reward | terminated | truncated | done | winner) so that the host-buffer
@@ -174,8 +178,9 @@ class BatchedScotlandYardEnv:
             self.stats_vec = z(_cabi.SY_NUM_STATS, dtype=torch.int64) if collect_stats else None
         self._state = _cabi.SyState(_ptr(self.pos), _ptr(self.money), _ptr(self.timestep), _ptr(self.graph_id),
                                     _ptr(self.episode), _ptr(self.done), _ptr(self.visits), _ptr(self.belief_map))
-        self._obs = _cabi.SyObs(_ptr(self.action_mask), _ptr(self.node_features), _ptr(self.agent_budget),
-                                _ptr(self.mrx_revealed))
+        nf_f32 = self.node_features.dtype == torch.float32
+        self._obs = _cabi.SyObs(_ptr(self.action_mask), _ptr(self.node_features) if nf_f32 else None, _ptr(self.agent_budget),
+                                _ptr(self.mrx_revealed), None if nf_f32 else _ptr(self.node_features))
         self._out = _cabi.SyOut(_ptr(self.reward), _ptr(self.reward64), _ptr(self.terminated), _ptr(self.truncated),
                                 _ptr(self.done_flags), _ptr(self.winner), _ptr(self.stats_vec), _ptr(self.status))
         self._static = None

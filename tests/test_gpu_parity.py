@@ -56,7 +56,7 @@ def test_library_loaded_is_in_tree(torch_cuda):
     pkg = _pkg()
     lib = pkg.load_library()
     assert os.path.dirname(pkg.LIB_PATH).endswith("student_mechanism_design_b200")
-    assert lib.sy_abi_version() == pkg._cabi.SY_ABI_VERSION == 2
+    assert lib.sy_abi_version() == pkg._cabi.SY_ABI_VERSION == 3
 
 
 def test_graph_tables_match_oracle(torch_cuda, golden_traces):
@@ -974,3 +974,28 @@ def test_host_overlap_mode_is_equivalent(torch_cuda, tables):
         assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), k
     a.close()
     b.close()
+
+
+@pytest.mark.gpu
+def test_uint8_node_features_option(torch_cuda, tables):
+    """node_features_dtype=torch.uint8 (SyObs.node_features_u8): the same one-hot as bytes, everything else untouched."""
+    torch = torch_cuda
+    pkg = _pkg()
+    for c in (CASES[1], CASES[2], CASES[5]):
+        pool = pkg.generate_graph_pool(c["G"], c["N"], c["E"], seed=3)
+        mk = lambda dt: pkg.BatchedScotlandYardEnv(c["B"], c["P"], c["money"], graphs=pool, seed=5, auto_reset=True,  # noqa: E731
+                                                   reward_mode=c["mode"], keep_reward64=True, reward_tables=tables,
+                                                   node_features_dtype=dt, **c["kw"])
+        a, b = mk(torch.float32), mk(torch.uint8)
+        a.reset()
+        b.reset()
+        assert b.node_features.dtype == torch.uint8 and b.observation()["node_features"].dtype == torch.uint8
+        for s in range(12):
+            acts = a.sample_actions(step_counter=s)
+            a.step(acts)
+            b.step(acts)
+            assert torch.equal(a.node_features, b.node_features.float()), s
+            for k in ("pos", "money", "action_mask", "reward64", "terminated", "mrx_revealed") + (("belief_map",) if c["kw"].get("belief") else ()):
+                assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), (k, s)
+        a.close()
+        b.close()
