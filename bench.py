@@ -52,6 +52,13 @@ def algorithmic_bytes_per_env_step(N, P, belief, nf_bytes=4):
     return 8 * A + 2 * (4 * A + 4 * A + 4) + 2 * 2 * P + (2 * 4 * N if belief else 0) + 4 * A + 3 * A + A * N + nf_bytes * N * A
 
 
+def kernel_source_hash():
+    import hashlib
+
+    with open(os.path.join(ROOT, "student_mechanism_design_b200", "csrc", "sy_env.cu"), "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -109,7 +116,7 @@ class CpuRunner:
     OpenMP over envs, all host threads) or, if gcc is unavailable, the numpy/Python one (1 core).
     One `step()` = random-valid policy + env step + masks + node features + belief for `B` envs."""
 
-    def __init__(self, wl, all_cores=True):
+    def __init__(self, wl, all_cores=True, envs=None):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import sy_oracle as so
 
@@ -132,7 +139,8 @@ class CpuRunner:
                 cores = min(cores, len(os.sched_getaffinity(0)))
             except Exception:
                 pass
-            self.cores, self.B = cores, 1024 * max(1, cores)
+            # the workload's own batch (bounded at 65 536 envs: the large configs keep the host arrays to a few hundred MB)
+            self.cores, self.B = cores, int(envs or min(wl["B"], 65536))
             self.run = oc.CBatch(cfg, pool, self.B, seed=0, threads=cores)
             self.what = f"C oracle (oracle/sy_oracle.c, OpenMP, {cores} threads)"
             self.step = self._step_c
@@ -151,6 +159,20 @@ class CpuRunner:
         self.run.masks(), self.run.node_features()
         self.n += 1
 
+    def timed_passes(self, steps, warmup, min_seconds=2.0, max_seconds=150.0):
+        """`warmup` untimed steps, then passes of exactly `steps` steps until `min_seconds` of timed work have been
+        done (at most 5 passes, at most `max_seconds`); returns (median seconds per pass, passes)"""
+        for _ in range(warmup):
+            self.step()
+        passes, total = [], 0.0
+        while len(passes) < 5 and (not passes or total < min_seconds) and total < max_seconds:
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                self.step()
+            passes.append(time.perf_counter() - t0)
+            total += passes[-1]
+        return statistics.median(passes), passes
+
     def timed(self, budget_s, max_steps=None):
         for _ in range(3):
             self.step()
@@ -167,23 +189,26 @@ class CpuRunner:
 def run_reference_arm(args, wl):
     """`--impl reference`: the reference's CPU implementation of the path is Python and cannot travel
     to the GPU box, so this arm times its oracle port (bit-exact with it on the golden traces) on all
-    host threads.  One step = one pass over a bounded sample batch; the run is capped at ~2 minutes."""
+    host threads, on the SAME batch as the CUDA arm (`envs_per_gpu` envs; bounded at 65 536), with the same
+    warm-up count; exactly `--steps` steps per timed pass, passes repeated until >= 2 s of timed work, median reported."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = CpuRunner(wl, all_cores=True)
-    for _ in range(min(args.warmup, 20)):
-        r.step()
-    base, dt, n = r.timed(120.0, max_steps=args.steps)
-    v = base["value"]
+    r = CpuRunner(wl, all_cores=True, envs=args.envs or None)
+    sec, passes = r.timed_passes(args.steps, args.warmup)
+    v = r.B * args.steps / sec
+    base = dict(value=v, unit=UNIT, cores=r.cores, kind="port",
+                sample=f"{r.what}: {r.B} envs x {args.steps} steps of {wl['name']} (random policy + step + masks + node "
+                       f"features + belief) per pass, median of {len(passes)} passes, {sum(passes):.1f} s timed")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": min(args.warmup, 20) + 3, "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
-        "config": {"workload": f"{wl['name']}: {wl['desc']}", "sample_envs": r.B,
+        "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": wl["N"], "num_police": wl["P"],
+                   "envs_per_gpu": r.B, "passes_s": [round(x, 4) for x in passes],
                    "note": "CPU arm = oracle port of the reference env on all host threads (the reference is pure Python "
-                           "and is not present on the GPU box; survey-measured reference speed at this config: 0.6 "
-                           "env-steps/s/core); a step is one pass over a bounded sample batch"},
+                           "and is not present on the GPU box; the unmodified reference timed in the build container: "
+                           "profiles/r02_reference_python.json); one rank runs it, on one GPU's batch"},
         "cpu_baseline": base,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -215,6 +240,10 @@ def run_cuda_arm(args, wl):
         dist.barrier()
     from student_mechanism_design_b200 import BatchedScotlandYardEnv, _cabi
 
+    if os.environ.get("SY_LIB_PATH") and not args.allow_lib_override:
+        raise SystemExit("bench.py: SY_LIB_PATH is set; the benchmark times the in-tree library (--allow-lib-override for experiments)")
+    if os.environ.get("SY_DEBUG_SKIP"):
+        raise SystemExit("bench.py: SY_DEBUG_SKIP is set; refusing to time a run with kernel parts switched off")
     lib = _cabi.load_library()
     N, P, B = wl["N"], wl["P"], args.envs or wl["B"]
     A = P + 1
@@ -224,6 +253,8 @@ def run_cuda_arm(args, wl):
     env = BatchedScotlandYardEnv(B, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], seed=0, **pool_kw,
                                  tolls=wl["toll"], belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True,
                                  env_offset=rank * B, device=f"cuda:{local}")
+    if args.writer:
+        env.set_option("writer_path", args.writer)
     env.reset()
     dev = env.device
     actions = torch.empty(B, A, dtype=torch.int64, device=dev)
@@ -287,31 +318,49 @@ def run_cuda_arm(args, wl):
         rollout_graph, _ctr = env.capture_rollout(seg, actions=actions)
         counter += seg
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    if use_graph:  # one more warm replay: the first launch of an instantiated graph uploads it
+        rollout_graph.replay()
+        counter += seg
+
+    def timed_pass():
+        """exactly K steps between two CUDA events, barrier + synchronise on both sides, max over ranks"""
+        nonlocal counter
+        barrier()
+        ev0.record()
+        if use_graph:  # replay the captured segment: launch latency is paid once per segment instead of three times per step
+            for _ in range(K // seg):
+                rollout_graph.replay()
+            counter += K
+        elif py_loop:
+            for k in range(K):
+                choose(counter)
+                env.step(actions)
+                counter += 1
+        else:  # the K steps are issued by one C-ABI call (sy_rollout_random): no Python between steps
+            env.rollout_random(K, actions=actions, step_counter=counter)
+            counter += K
+        ev1.record()
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1))
+
     sampler.active = True
     launches0 = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0)
-    ev0.record()
-    if use_graph:  # replay the captured segment: launch latency is paid once per segment instead of three times per step
-        for _ in range(K // seg):
-            rollout_graph.replay()
-        counter += K
-    elif py_loop:
-        for k in range(K):
-            choose(counter)
-            env.step(actions)
-            counter += 1
-    else:  # the K steps are issued by one C-ABI call (sy_rollout_random): no Python between steps
-        env.rollout_random(K, actions=actions, step_counter=counter)
-        counter += K
-    stats_total = env.stats(reduce_group=True if dist is not None else None)  # the one collective (NCCL)
-    ev1.record()
-    barrier()
+    pass_ms = [timed_pass() for _ in range(args.passes)]  # SURVEY 8(d): median of 5
     sampler.active = False
     launches = lib.sy_launch_count() + (plib.sy_policy_launch_count() if plib else 0) - launches0
     if use_graph:  # kernels inside a replayed graph do not pass through the library's host-side counter
-        launches += (K // seg) * (3 * seg + 1)
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+        launches += args.passes * (K // seg) * (3 * seg + 1)
+    launches //= args.passes  # per timed pass of K steps
+    ms_total = statistics.median(pass_ms)
     value = world * B * K / (ms_total * 1e-3)
+    # the one collective of the path (SURVEY 8(e)): the statistics vector, folded on the device and summed over the ranks
+    # with one NCCL all-reduce per reporting interval -- here once, after the timed passes, timed on its own
+    barrier()
+    ev0.record()
+    stats_total = env.stats(reduce_group=True if dist is not None else None)
+    ev1.record()
+    barrier()
+    stats_ms = max_over_ranks(ev0.elapsed_time(ev1))
 
     # ---- duration of the sy_step call alone (its two kernels), CUDA events around every call, for the roofline
     Kk = min(K, 300)
@@ -333,46 +382,63 @@ def run_cuda_arm(args, wl):
 
     # ---- end to end through the host-buffer API
     Ke = max(3, min(K, args.e2e_steps))
+
+    def e2e_leg(wname, fl, passes=3):
+        """Ke steps of: host actions (pinned) -> H2D -> step -> D2H of the results -> synchronise, `passes` times; the
+        median pass.  The random policy's actions are also produced on the device and copied to the host every step, so
+        a host-side policy is emulated honestly (its D2H bytes are counted)."""
+        nonlocal counter
+        wire, wb = {"int64": (torch.int64, 8), "int32": (torch.int32, 4), "int16": (torch.int16, 2)}[wname]
+        env.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
+        for _ in range(3):
+            env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire), flags=fl)
+            counter += 1
+        ms = []
+        for _ in range(passes):
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            for _ in range(Ke):
+                host_actions = env.sample_actions_host(step_counter=counter, dtype=wire)  # the "policy" hands over HOST actions
+                res = env.step_host(host_actions, flags=fl)  # H2D actions, kernel, D2H reward/flags, synchronised
+                counter += 1
+            ev1.record()
+            barrier()
+            ms.append(max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)))
+        env.set_host_overlap(False)
+        assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
+        e2e_ms = statistics.median(ms)
+        return {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb, fl),
+                "steps": Ke, "passes_ms": [round(x, 3) for x in ms],
+                "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 [B,A] + winner + "
+                + ("one status byte per env (terminated/truncated/frozen bits; every agent of an env shares them)" if fl == "compact"
+                   else "terminated/truncated/done u8 [B,A] + status") +
+                " out to pinned host memory; observations stay on the device for the GPU policy; the D2H count includes the "
+                "random policy's actions coming back to the host"}
+
     # wire format of the host actions: node ids fit 16 bits at every BASELINE config; --e2e-int64 = the reference's dtype
     wname = "int64" if args.e2e_int64 else (args.e2e_wire if N <= 32767 or args.e2e_wire != "int16" else "int32")
-    wire, wb = {"int64": (torch.int64, 8), "int32": (torch.int32, 4), "int16": (torch.int16, 2)}[wname]
-    fl = args.e2e_flags
-    env.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
-    for _ in range(3):
-        env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire), flags=fl)
-        counter += 1
-    barrier()
     sampler.active = True
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(Ke):
-        host_actions = env.sample_actions_host(step_counter=counter, dtype=wire)  # the "policy" hands over HOST actions
-        res = env.step_host(host_actions, flags=fl)  # H2D actions, kernel, D2H reward/flags, synchronised
-        counter += 1
-    ev1.record()
-    barrier()
+    e2e = e2e_leg(wname, args.e2e_flags)
+    # the reference's own call shape (yard.py:144,269): int64 actions in, per-agent [B, A] flag arrays out
+    e2e_ref_shape = e2e if (wname, args.e2e_flags) == ("int64", "per_agent") else e2e_leg("int64", "per_agent")
     sampler.active = False
-    e2e_ms = max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3))
-    env.set_host_overlap(False)
-    assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
-    e2e = {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb, fl),
-           "steps": Ke, "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 [B,A] + winner + "
-           + ("one status byte per env (terminated/truncated/frozen bits; every agent of an env shares them)" if fl == "compact"
-              else "terminated/truncated/done u8 [B,A] + status") +
-           " out to pinned host memory; observations stay on the device for the GPU policy; the D2H count includes the "
-           "random policy's actions coming back to the host"}
 
     clocks = sampler.summary()
     if rank == 0:
         bstep = algorithmic_bytes_per_env_step(N, P, wl["belief"], 1 if args.nf_u8 else 4)
         peak, peak_src = measured_hbm_peak()
         achieved = bstep * B / (step_kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
         if os.path.isfile(tp) and not args.nf_u8:  # the ncu capture is of the float32 observation layout
             try:
-                traffic = json.load(open(tp)).get(wl["name"], {}).get("dram_bytes_per_launch")
+                rec = json.load(open(tp))
+                if rec.get("source_sha256") == kernel_source_hash():  # refuse a capture of other kernels
+                    traffic = rec.get(wl["name"], {}).get("dram_bytes_per_launch")
+                else:
+                    traffic_note = "profiles/step_kernel_traffic.json was captured from a different csrc/sy_env.cu: ignored"
             except Exception:
                 traffic = None
         line = {
@@ -384,14 +450,17 @@ def run_cuda_arm(args, wl):
                                 "python" if py_loop else "sy_rollout_random (C)"),
                        "auto_reset": True, "parallelism": f"batch-sharded x{world}",
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "e2e": e2e, "e2e_reference_shape": e2e_ref_shape, "gpu_launches": int(launches),
+            "passes_ms": [round(x, 4) for x in pass_ms], "stats_fold_allreduce_ms": stats_ms,
+            "library": {"path": os.path.relpath(_cabi.LIB_PATH, ROOT), "override": bool(os.environ.get("SY_LIB_PATH")),
+                        "options": getattr(env, "options", {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "sy_step = sy_logic_kernel + sy_observe_kernel", "kernel_ms": step_kernel_ms,
+                         "traffic": traffic, "traffic_note": traffic_note, "kernel": "sy_step = sy_logic_kernel + sy_observe_kernel", "kernel_ms": step_kernel_ms,
                          "algorithmic_bytes_per_env_step": bstep, "peak_source": peak_src},
             "episode_stats": stats_total,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = CpuRunner(wl, all_cores=True).timed(args.cpu_seconds)[0]
+            line["cpu_baseline"] = CpuRunner(wl, all_cores=True, envs=min(B, 65536)).timed(args.cpu_seconds)[0]
         print(json.dumps(line), flush=True)
     env.close()
     if dist is not None:
@@ -410,6 +479,9 @@ def main():
     ap.add_argument("--nf-u8", action="store_true",
                     help="write node_features as uint8 instead of float32 (opt-in observation dtype; the roofline bytes follow)")
     ap.add_argument("--graphs", type=int, default=1, help="graph pool size (> 1: sampled on the device; envs in blocks of 32 per graph)")
+    ap.add_argument("--passes", type=int, default=5, help="timed passes of --steps steps each; the median is reported")
+    ap.add_argument("--writer", default=None, choices=["bulk", "lsu"], help="observation writer path (sy_set_option; default bulk)")
+    ap.add_argument("--allow-lib-override", action="store_true", help="accept SY_LIB_PATH (kernel-variant experiments only)")
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SY_ABI_VERSION 3
+#define SY_ABI_VERSION 4
 #define SY_NUM_REWARD_WEIGHTS 11 /* order = REWARD_WEIGHT_NAMES, src/reward_net.py:5-17 */
 #define SY_MAX_AGENTS 16
 #define SY_NUM_STATS 16
@@ -98,10 +98,21 @@ typedef struct SyConfig {
   int64_t env_offset;      /* global index of env 0: keeps Philox streams shard-invariant */
   uint64_t seed;
   double reward_weights[SY_NUM_REWARD_WEIGHTS];
+  /* Robustness hook of src/eval/ood_eval.py:191-234 (RobustnessWrapper.reveal_skip_prob, and `reveal_probability`
+   * of src/configs/ablation/belief.yaml as 1 - p): every scheduled reveal is skipped with this probability, one
+   * Philox(seed; env, episode, timestep) Bernoulli draw per env and reveal step.  0 = every scheduled reveal happens
+   * (bit-identical to a library without the hook). */
+  float reveal_skip_prob;
+  int32_t reserved0;
 } SyConfig;
+
+/* Every pointer struct below starts with `struct_bytes` = sizeof(the struct): the library rejects a struct of another
+ * size with SY_ERR_INVALID_ARGUMENT instead of reading past the caller's memory (a binding written against an older
+ * header would otherwise hand the kernels garbage pointers). */
 
 /* Per-env state, device pointers, caller-owned (yard.py:111-127 state, batched). */
 typedef struct SyState {
+  uint64_t struct_bytes; /* = sizeof(SyState) */
   int32_t* pos;      /* [B, A]  MrX_pos + police_positions */
   int32_t* money;    /* [B, A]  agents_money */
   int32_t* timestep; /* [B] */
@@ -110,12 +121,17 @@ typedef struct SyState {
   uint8_t* done;     /* [B] 1 = finished and frozen until reset (only without auto_reset) */
   uint16_t* visits;  /* [B, N] node_visit_counts (yard.py:59,244-245) */
   float* belief;     /* [B, N] belief_map, may be NULL when config.belief == 0 */
+  const uint8_t* belief_hint; /* [B, N] or NULL: observation hint of ParticleBeliefTracker.update (belief_module.py:
+                                 102-106), non-zero = candidate node: after the propagation the belief of node j is
+                                 multiplied by 0.1 + 0.9 * (hint[j] != 0) before it is normalised.  Read by sy_step only;
+                                 envs whose row is all zero are not re-weighted (`if observation_hint:` is False) */
 } SyState;
 
 /* Dynamic observation tensors written every reset/step (yard.py:271-335).  Static graph
  * tensors (adjacency_matrix, edge_index, edge_features) are per-graph and are built once by
  * the host from the same CSR; belief_map is SyState.belief; agent_position is SyState.pos. */
 typedef struct SyObs {
+  uint64_t struct_bytes; /* = sizeof(SyObs) */
   uint8_t* action_mask;  /* [B, A, N] bool */
   float* node_features;  /* [B, N, A] one-hot of positions, column 0 = MrX (blank while hidden) */
   float* agent_budget;   /* [B, A]  yard.py:329-331 */
@@ -126,6 +142,7 @@ typedef struct SyObs {
 
 /* Step results (reward_calculator.py:26-92). */
 typedef struct SyOut {
+  uint64_t struct_bytes; /* = sizeof(SyOut) */
   float* reward;       /* [B, A] */
   double* reward64;    /* [B, A] or NULL: the float64 value before the float32 cast (fp64 mode) */
   uint8_t* terminated; /* [B, A] */
@@ -145,6 +162,13 @@ int64_t sy_launch_count(void);
 /* replaces CustomEnvironment.__init__ (yard.py:18-78) */
 int sy_create(const SyConfig* config, SyEnv** out_env);
 void sy_destroy(SyEnv* env);
+/* Tuning knobs of a handle (results are identical for every setting; bench.py records what it used).
+ *   SY_OPT_WRITER_PATH  how the observation kernel's writer warps move action_mask / node_features to HBM:
+ *                       SY_WRITER_BULK (default) = shared-memory images + cp.async.bulk (TMA) when the caller's
+ *                       buffers are 16-byte aligned, else the LSU path; SY_WRITER_LSU = 16-byte streaming stores. */
+enum { SY_OPT_WRITER_PATH = 0 };
+enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
+int sy_set_option(SyEnv* env, int32_t option, int32_t value);
 /* new Philox key for subsequent (auto-)resets and action sampling (torchrl `set_seed`) */
 int sy_set_seed(SyEnv* env, uint64_t seed);
 
@@ -198,6 +222,7 @@ int sy_step(SyEnv* env, const int64_t* actions, const SyState* state, const SyOb
 
 /* HOST pointers (pinned memory recommended) that `sy_step_host` fills; any member may be NULL. */
 typedef struct SyHostOut {
+  uint64_t struct_bytes; /* = sizeof(SyHostOut) */
   float* reward;       /* [B, A] */
   uint8_t* terminated; /* [B, A] */
   uint8_t* truncated;  /* [B, A] */

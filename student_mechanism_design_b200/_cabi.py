@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SY_LIB_PATH: profiling experiments only (kernel variants built side by side); the product loads the in-tree library
 LIB_PATH = os.environ.get("SY_LIB_PATH") or os.path.join(_HERE, "libsy_env.so")
 
-SY_ABI_VERSION = 3
+SY_ABI_VERSION = 4
 SY_NUM_REWARD_WEIGHTS = 11
 SY_MAX_AGENTS = 16
 SY_NUM_STATS = 16
@@ -29,24 +29,37 @@ class SyConfig(C.Structure):
         ("num_police", C.c_int32), ("agent_money", C.c_int32), ("mrx_money", C.c_int32), ("max_timestep", C.c_int32),
         ("reveal_interval", C.c_int32), ("toll", C.c_int32), ("belief", C.c_int32), ("reward_mode", C.c_int32),
         ("auto_reset", C.c_int32), ("resample_graph", C.c_int32), ("env_offset", C.c_int64), ("seed", C.c_uint64),
-        ("reward_weights", C.c_double * SY_NUM_REWARD_WEIGHTS),
+        ("reward_weights", C.c_double * SY_NUM_REWARD_WEIGHTS), ("reveal_skip_prob", C.c_float), ("reserved0", C.c_int32),
     ]
 
 
-class SyState(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("pos", "money", "timestep", "graph_id", "episode", "done", "visits", "belief")]
+class _PtrStruct(C.Structure):
+    """pointer struct of include/sy_env.h: `struct_bytes` (ABI guard, filled in here) followed by void* members,
+    constructed with the members positionally or by name"""
+
+    def __init__(self, *args, **kw):
+        names = [n for n, _ in self._fields_[1:]]
+        super().__init__(C.sizeof(type(self)), *args, **{k: v for k, v in kw.items() if k in names})
 
 
-class SyObs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("action_mask", "node_features", "agent_budget", "mrx_revealed", "node_features_u8")]
+class SyState(_PtrStruct):
+    _fields_ = [("struct_bytes", C.c_uint64)] + [(n, C.c_void_p) for n in (
+        "pos", "money", "timestep", "graph_id", "episode", "done", "visits", "belief", "belief_hint")]
 
 
-class SyOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("reward", "reward64", "terminated", "truncated", "done", "winner", "stats", "status")]
+class SyObs(_PtrStruct):
+    _fields_ = [("struct_bytes", C.c_uint64)] + [(n, C.c_void_p) for n in (
+        "action_mask", "node_features", "agent_budget", "mrx_revealed", "node_features_u8")]
 
 
-class SyHostOut(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("reward", "terminated", "truncated", "done", "winner", "status")]
+class SyOut(_PtrStruct):
+    _fields_ = [("struct_bytes", C.c_uint64)] + [(n, C.c_void_p) for n in (
+        "reward", "reward64", "terminated", "truncated", "done", "winner", "stats", "status")]
+
+
+class SyHostOut(_PtrStruct):
+    _fields_ = [("struct_bytes", C.c_uint64)] + [(n, C.c_void_p) for n in (
+        "reward", "terminated", "truncated", "done", "winner", "status")]
 
 
 # name -> (restype, argtypes); must list every function include/sy_env.h declares
@@ -56,6 +69,7 @@ SIGNATURES = {
     "sy_launch_count": (C.c_int64, []),
     "sy_create": (C.c_int, [C.POINTER(SyConfig), C.POINTER(C.c_void_p)]),
     "sy_destroy": (None, [C.c_void_p]),
+    "sy_set_option": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "sy_set_seed": (C.c_int, [C.c_void_p, C.c_uint64]),
     "sy_set_reward_tables": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_load_graphs": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),

@@ -25,11 +25,13 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -65,6 +67,12 @@ constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = 
 #endif
 #ifndef SY_STORE_HINT
 #define SY_STORE_HINT 0
+#endif
+#ifndef SY_BULK_HINT
+#define SY_BULK_HINT 0  // 1: L2 evict_first policy on the bulk stores
+#endif
+#ifndef SY_BULK_IMG_BUDGET
+#define SY_BULK_IMG_BUDGET 25344  // bytes of shared memory for the bulk writers' zero page and chunk images of a CTA
 #endif
 constexpr int BEL_WARPS = SY_BEL_WARPS;  // observe kernel: the first warps propagate the belief ...
 constexpr int WR_WARPS = SY_WR_WARPS;    // ... the others stream the dense observations
@@ -121,6 +129,10 @@ struct Params {
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr;  // writer warps: smem staging layout (bytes) and path flag
   int bel_share_csr;  // generic belief path gathers over the writers' staged CSR (+ 1/deg) instead of the global lists
+  // bulk (TMA) writers: the tile's action_mask / node_features regions are contiguous byte streams cut into chunks of
+  // wr_c_mask / wr_c_nf bytes (multiples of 16); each chunk is assembled in a per-warp shared-memory image and leaves
+  // the SM with one cp.async.bulk.  0 = the LSU writers (unaligned caller buffers, or selected with sy_set_option)
+  int wr_bulk, wr_c_mask, wr_c_nf, wr_img_bytes;
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
@@ -219,6 +231,26 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// bulk asynchronous copy shared -> global (TMA, SASS UBLKCP): one thread moves a whole image; the store stream never
+// touches the LSU or a register.  Source / destination 16-byte aligned, size a multiple of 16.
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+#if SY_BULK_HINT == 1
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;\n" ::"l"(gdst), "r"(sa), "r"(bytes), "l"(pol)
+               : "memory");
+#else
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void bulk_wait_read() {  // until at most PENDING of this thread's groups still read their source
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(PENDING) : "memory");
 }
 
 // warp-cooperative streaming zero-fill of n bytes at any alignment: byte head, 16-byte body, byte tail
@@ -985,6 +1017,293 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// bulk (TMA) writers.  The tile's action_mask [nEnv, A, N] bytes and node_features [nEnv, N, A] elements are two
+// contiguous byte streams that start 16-byte aligned (a tile is 32 envs).  Each stream is cut into chunks (multiples of
+// 16 bytes, whole envs or whole fractions of an env where the sizes allow: plan_bulk_chunk on the host).  A writer warp
+// owns two zeroed shared-memory images; per chunk it sets the few ones that fall into it (affordable
+// neighbours, action_mask.py:65-76; one-hot positions, yard.py:279-290), hands the image to the TMA engine with ONE
+// cp.async.bulk (SASS UBLKCP) and, once the engine has read it, clears the same ones again.  That is a few dozen
+// shared-memory accesses per chunk instead of hundreds of STG.128: the store stream no longer passes through the LSU
+// or the register file, which is what blocked every attempt to run the game logic next to the writers.
+// ---------------------------------------------------------------------------------------------
+struct BulkCtx {
+  const int* s_pos;    // [TILE * A] staged state of the tile
+  const int* s_money;  // [TILE * A]
+  const int* s_rev;    // [TILE]
+  const int* s_gid;    // [TILE]
+  const int* rp;       // staged CSR of the tile's graph (STAGED) ...
+  const uint16_t* col;
+  const uint8_t* wgt;
+};
+
+// ones of the action_mask stream that fall into bytes [lo, lo + len): lane = (env, agent) pair
+template <bool STAGED>
+__device__ __forceinline__ void bulk_mask_ones(const Params& p, const BulkCtx& c, uint8_t* img, int lo, int len, int lane, uint8_t v) {
+  const int N = p.N, A = p.A, S = A * N;
+  const int e_lo = lo / S, e_hi = (lo + len - 1) / S;
+  const int npairs = (e_hi - e_lo + 1) * A;
+  for (int q = lane; q < npairs; q += 32) {
+    const int de = (q * p.inv_A) >> 16, a = q - de * A, e = e_lo + de;
+    const int u = c.s_pos[e * A + a], m = c.s_money[e * A + a];
+    const int base = e * S + a * N - lo;
+    if (STAGED) {
+      const int r0 = c.rp[u], r1 = c.rp[u + 1];
+      for (int k = r0; k < r1; ++k) {
+        const int off = base + (int)c.col[k];
+        if ((int)c.wgt[k] + p.toll <= m && (unsigned)off < (unsigned)len) img[off] = v;
+      }
+    } else {
+      const int g = c.s_gid[e];
+      const int32_t* rp = p.tb.row_ptr + (size_t)g * (N + 1) + u;
+      const int r0 = __ldg(rp), r1 = __ldg(rp + 1);
+      const uint16_t* cl = p.tb.col + (size_t)g * p.tb.nnz_stride;
+      const uint8_t* wg = p.tb.wgt + (size_t)g * p.tb.nnz_stride;
+      for (int k = r0; k < r1; ++k) {
+        const int off = base + (int)__ldg(cl + k);
+        if ((int)__ldg(wg + k) + p.toll <= m && (unsigned)off < (unsigned)len) img[off] = v;
+      }
+    }
+  }
+}
+
+// ones of the node_features stream (ELEM = 4: float32 1.0f, 1: uint8 1) in bytes [lo, lo + len); the MrX column stays
+// blank while he is hidden (yard.py:279-290 with the reveal schedule)
+template <int ELEM>
+__device__ __forceinline__ void bulk_nf_ones(const Params& p, const BulkCtx& c, uint8_t* img, int lo, int len, int lane, bool set) {
+  const int N = p.N, A = p.A, S = N * A * ELEM;
+  const int e_lo = lo / S, e_hi = (lo + len - 1) / S;
+  const int npairs = (e_hi - e_lo + 1) * A;
+  for (int q = lane; q < npairs; q += 32) {
+    const int de = (q * p.inv_A) >> 16, a = q - de * A, e = e_lo + de;
+    if (a == 0 && c.s_rev[e] < 0) continue;
+    const int off = e * S + (c.s_pos[e * A + a] * A + a) * ELEM - lo;
+    if ((unsigned)off < (unsigned)len) {
+      if (ELEM == 4) *reinterpret_cast<unsigned*>(img + off) = set ? 0x3f800000u : 0u;
+      else img[off] = set ? 1 : 0;
+    }
+  }
+}
+
+// ---- writer streams -----------------------------------------------------------------------------------------------
+// float32 node_features: the region is filled with zeros by bulk copies from a read-only zero page (nothing to assemble,
+// nothing to wait for before the page can be reused); once a piece's fill has COMPLETED, the few 16-byte granules that
+// hold a one are stored whole from registers and merge with the zero lines still resident in L2.
+// action_mask (and uint8 node_features): chunk images, two per warp, so the engine reads one while the next is built.
+// A writer warp interleaves the two: per mask chunk it first issues the fill of the matching piece of the float32
+// stream (4x the bytes), then the chunk's image, and D chunks later -- when that piece's fill has completed -- the
+// piece's ones.  The interleaving keeps the SM's (in-order) bulk-copy queue short, so an image never waits behind more
+// than a few KB of fill.  Micro-benchmark of exactly this schedule (tools/exp/tma_fill.cu, B200): the 458 MB of config 3
+// leave the chip in 72 us with 2 warps on each of 2 CTAs per SM (cudaMemset: 66 us); issuing a whole tile's fill up
+// front instead made every image wait behind ~180 KB of queued copies and doubled the kernel time.
+struct ImageStreams {
+  int ncf, ncm;  // chunks of the uint8 node_features stream (0 when float32), of the action_mask stream
+  int Tf, Tm;    // stream lengths (bytes) of this tile
+  uint8_t* gf;
+  uint8_t* gm;
+};
+
+__device__ __forceinline__ ImageStreams image_streams(const Params& p, int tile0, int nEnv) {
+  ImageStreams st;
+  const int S = p.A * p.N;
+  const bool nf8 = p.ob.node_features_u8 != nullptr;
+  st.Tm = nEnv * S;
+  st.Tf = nf8 ? nEnv * S : 0;
+  st.ncm = (st.Tm + p.wr_c_mask - 1) / p.wr_c_mask;
+  st.ncf = nf8 ? (st.Tf + p.wr_c_nf - 1) / p.wr_c_nf : 0;
+  st.gm = p.ob.action_mask + (size_t)tile0 * S;
+  st.gf = nf8 ? p.ob.node_features_u8 + (size_t)tile0 * S : nullptr;
+  return st;
+}
+
+// zero fill of bytes [lo, hi) of the tile's float32 node_features stream (lo 16-byte aligned), issued by ONE lane
+__device__ __forceinline__ void nf32_fill_piece(uint8_t* gnf, int lo, int hi, const uint8_t* zero_page, int Z) {
+  const int body_hi = lo + ((hi - lo) & ~15);
+  for (int o = lo; o < body_hi; o += Z) bulk_store(gnf + o, zero_page, (unsigned)min(Z, body_hi - o));
+}
+
+// ones of the float32 node_features stream that fall into bytes [lo, hi) (yard.py:279-290; the MrX column stays blank
+// while he is hidden): lane = (env, agent) pair.  Env rows that are whole 16-byte granules get the granule rewritten
+// (assembled from every agent of the env that falls into it), others a 4-byte store.
+__device__ __forceinline__ void nf32_ones_piece(const Params& p, const BulkCtx& c, uint8_t* gnf, int lo, int hi, int lane) {
+  const int A = p.A, S = p.N * A * 4;
+  const int e_lo = lo / S, e_hi = (hi - 1) / S;
+  const int npairs = (e_hi - e_lo + 1) * A;
+  const bool granules = (S & 15) == 0;
+  for (int q = lane; q < npairs; q += 32) {
+    const int de = (q * p.inv_A) >> 16, a = q - de * A, e = e_lo + de;
+    const bool hidden = c.s_rev[e] < 0;
+    if (a == 0 && hidden) continue;
+    const int* pos = c.s_pos + e * A;
+    const int f = pos[a] * A + a;  // element index inside the env's row
+    const int off = e * S + f * 4;
+    if (off < lo || off >= hi) continue;
+    if (granules) {
+      const int g = f >> 2;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      for (int b2 = hidden ? 1 : 0; b2 < A; ++b2) {
+        const int f2 = pos[b2] * A + b2;
+        if ((f2 >> 2) == g) {
+          const unsigned one = 0x3f800000u;
+          const int sub = f2 & 3;
+          v.x = sub == 0 ? one : v.x;
+          v.y = sub == 1 ? one : v.y;
+          v.z = sub == 2 ? one : v.z;
+          v.w = sub == 3 ? one : v.w;
+        }
+      }
+      store_obs16(reinterpret_cast<uint4*>(gnf + (size_t)e * S) + g, v);
+    } else {
+      *reinterpret_cast<float*>(gnf + off) = 1.0f;
+    }
+  }
+}
+
+// writer warp `iw` of `niw`: items iw, iw + niw, ... of [uint8 node_features chunks | action_mask chunks]; with float32
+// node_features every mask chunk also carries the matching piece of that stream.  D = chunks between a piece's fill and
+// its ones.  prefilled: the caller already issued (from this warp's lane 0) the fill of all of this warp's pieces.
+template <int D>
+__device__ __forceinline__ void writer_stream_warp(const Params& p, const BulkCtx& c, const ImageStreams& st, bool staged, uint8_t* my_img,
+                                                   const uint8_t* zero_page, uint8_t* gnf32, int iw, int niw, int lane, bool prefilled) {
+  const int Cm = p.wr_c_mask, Cf = p.wr_c_nf;
+  const int Tf32 = 4 * st.Tm;  // float32 node_features stream: 4 bytes per mask byte
+  auto ones = [&](int item, uint8_t* img, uint8_t v) {
+    if (item < st.ncf) {
+      const int lo = item * Cf;
+      bulk_nf_ones<1>(p, c, img, lo, min(Cf, st.Tf - lo), lane, v != 0);
+    } else {
+      const int lo = (item - st.ncf) * Cm, len = min(Cm, st.Tm - lo);
+      if (staged) bulk_mask_ones<true>(p, c, img, lo, len, lane, v);
+      else bulk_mask_ones<false>(p, c, img, lo, len, lane, v);
+    }
+  };
+  auto piece_ones = [&](int item) {
+    if (gnf32 && item >= st.ncf) {
+      const int lo = 4 * (item - st.ncf) * Cm;
+      nf32_ones_piece(p, c, gnf32, lo, min(Tf32, lo + 4 * Cm), lane);
+    }
+  };
+  const int total = st.ncf + st.ncm;
+  int it = 0;
+  for (int item = iw; item < total; item += niw, ++it) {
+    const bool is_nf8 = item < st.ncf;
+    // ---- group F(it): zero fill of the float32 piece that belongs to this mask chunk
+    if (gnf32 && !is_nf8) {
+      const int lo = 4 * (item - st.ncf) * Cm, hi = min(Tf32, lo + 4 * Cm);
+      if (lane == 0 && !prefilled) nf32_fill_piece(gnf32, lo, hi, zero_page, Cm);
+      const int tail = (hi - lo) & 15;  // ragged end of the batch's last tile only
+      if (!prefilled && lane < tail) gnf32[hi - tail + lane] = 0;
+    }
+    if (lane == 0) bulk_commit();
+    // ---- group M(it): the chunk's image
+    uint8_t* img = my_img + (size_t)(it & 1) * p.wr_img_bytes;
+    if (it >= 2) {  // the image's previous chunk has left shared memory (younger groups: F(it-1), M(it-1), F(it)): take its ones out
+      if (lane == 0) bulk_wait_read<3>();
+      __syncwarp();
+      ones(item - 2 * niw, img, 0);
+      __syncwarp();
+    }
+    ones(item, img, 1);
+    fence_proxy_async_smem();  // generic-proxy writes of every lane -> visible to the async proxy
+    __syncwarp();
+    const int lo = is_nf8 ? item * Cf : (item - st.ncf) * Cm;
+    const int len = is_nf8 ? min(Cf, st.Tf - lo) : min(Cm, st.Tm - lo);
+    uint8_t* dst = (is_nf8 ? st.gf : st.gm) + lo;
+    const int body = len & ~15;
+    if (lane == 0) {
+      if (body) bulk_store(dst, img, (unsigned)body);
+      bulk_commit();
+    }
+    if (lane < len - body) dst[body + lane] = img[body + lane];  // ragged end of the batch's last tile only
+    // ---- ones of the piece filled D chunks ago: F(it-D) and everything older has completed
+    if (gnf32 && it >= D) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(2 * D + 1) : "memory");
+      __syncwarp();
+      piece_ones(item - D * niw);
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+  __syncwarp();
+  for (int k = max(0, it - D); k < it; ++k) piece_ones(iw + k * niw);
+  // leave both images zeroed (the next tile of a persistent CTA starts from clean images)
+  for (int k = max(0, it - 2); k < it; ++k) ones(iw + k * niw, my_img + (size_t)(k & 1) * p.wr_img_bytes, 0);
+  __syncwarp();
+}
+
+#ifndef SY_BULK_WARPS
+#define SY_BULK_WARPS 4
+#endif
+#ifndef SY_BULK_DEPTH
+#define SY_BULK_DEPTH 2
+#endif
+constexpr int BULK_WARPS = SY_BULK_WARPS;  // writer warps that stream on the bulk path (more only deepen the copy queue)
+constexpr int BULK_DEPTH = SY_BULK_DEPTH;  // chunks between a float32 piece's fill and its ones
+
+// stage the tile's post-step state (and, when the tile sits on one graph, its CSR) into shared memory: what every
+// writer needs to place the ones.  Returns whether the CSR was staged.
+template <int NTHREADS>
+__device__ __forceinline__ bool stage_tile_inputs(const Params& p, unsigned char* dyn, int tile0, int nEnv, int tw, int lane,
+                                                  int* s_pos, int* s_money, int* s_rev, int* s_gid) {
+  const Tables& tb = p.tb;
+  const int N = p.N, A = p.A;
+  int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);  // [N + 1]
+  uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
+  uint8_t* s_wgt = reinterpret_cast<uint8_t*>(s_col + tb.nnz_stride);
+  const int gl = (lane < nEnv) ? p.st.graph_id[tile0 + lane] : -1;
+  const int g0 = __shfl_sync(FULL, gl, 0);
+  const bool staged = p.wr_stage_csr && __all_sync(FULL, gl == g0 || gl < 0);
+  for (int i = tw; i < nEnv * A; i += NTHREADS) {
+    s_pos[i] = p.st.pos[(size_t)tile0 * A + i];
+    s_money[i] = p.st.money[(size_t)tile0 * A + i];
+  }
+  if (tw < nEnv) {
+    s_rev[tw] = p.ob.mrx_revealed[tile0 + tw];
+    s_gid[tw] = gl;
+  }
+  if (staged) {
+    const int32_t* grp = tb.row_ptr + (size_t)g0 * (N + 1);
+    const int nnz = __ldg(grp + N);
+    for (int i = tw; i <= N; i += NTHREADS) s_rp[i] = __ldg(grp + i);
+    for (int k = tw; k < nnz; k += NTHREADS) {
+      s_col[k] = __ldg(tb.col + (size_t)g0 * tb.nnz_stride + k);
+      s_wgt[k] = __ldg(tb.wgt + (size_t)g0 * tb.nnz_stride + k);
+    }
+    if (p.bel_share_csr) {
+      float* s_inv = reinterpret_cast<float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + tb.nnz_stride * 3 + 3) & ~3));
+      uint16_t* s_perm = reinterpret_cast<uint16_t*>(s_inv + N);
+      for (int i = tw; i < N; i += NTHREADS) {
+        s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
+        s_perm[i] = __ldg(tb.deg_perm + (size_t)g0 * N + i);
+      }
+    }
+  }
+  return staged;
+}
+
+template <int WRW>
+__device__ __forceinline__ void writer_role_bulk(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
+  constexpr int NW = WRW < BULK_WARPS ? WRW : BULK_WARPS;
+  const int N = p.N, A = p.A;
+  int* s_pos = reinterpret_cast<int*>(dyn + p.wr_off);  // [TILE * A]
+  int* s_money = s_pos + TILE * A;                      // [TILE * A]
+  int* s_rev = s_money + TILE * A;                      // [TILE]
+  int* s_gid = s_rev + TILE;                            // [TILE]
+  uint8_t* zero_page = reinterpret_cast<uint8_t*>(s_gid + TILE);  // [wr_img_bytes] read-only zeros, 16-byte aligned
+  uint8_t* imgs = zero_page + p.wr_img_bytes;                     // [BULK_WARPS][2][wr_img_bytes]
+  for (int i = (w * 32 + lane) * 16; i < (1 + 2 * NW) * p.wr_img_bytes; i += WRW * 32 * 16) *reinterpret_cast<uint4*>(zero_page + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  const bool staged = stage_tile_inputs<WRW * 32>(p, dyn, tile0, nEnv, w * 32 + lane, lane, s_pos, s_money, s_rev, s_gid);
+  named_barrier(2, WRW * 32);
+  if (p.bel_share_csr) asm volatile("bar.arrive 3, %0;\n" ::"r"(THREADS) : "memory");
+  if (w >= NW) return;
+  int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);
+  uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
+  const BulkCtx c{s_pos, s_money, s_rev, s_gid, s_rp, s_col, reinterpret_cast<uint8_t*>(s_col + p.tb.nnz_stride)};
+  const ImageStreams st = image_streams(p, tile0, nEnv);
+  uint8_t* gnf32 = p.ob.node_features_u8 ? nullptr : reinterpret_cast<uint8_t*>(p.ob.node_features) + (size_t)tile0 * N * A * 4;
+  writer_stream_warp<BULK_DEPTH>(p, c, st, staged, imgs + (size_t)w * 2 * p.wr_img_bytes, zero_page, gnf32, w, NW, lane, false);
+}
+
 // generic belief path: one warp per env, lane = node; any N, any mix of graphs.  sb: N floats of this warp.
 // The env's row is copied to shared memory (LDGSTS), every lane then gathers its nodes' padded neighbour lists
 // {node, 1/deg} straight from the (L1-resident) pool tables.  The normaliser is the sum of the INPUT row: the
@@ -1312,11 +1631,12 @@ __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
   if (warp < nbw) {
     if (!(p.dbg_skip & 4)) belief_role<BW>(p, dyn, tile0, nEnv, warp, lane);
   } else if (!(p.dbg_skip & 1)) {
-    writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+    if (p.wr_bulk) writer_role_bulk<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+    else writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
   }
 }
 
-constexpr int GEN_BEL_WARPS = 12, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
+constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? 12 : BEL_WARPS, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
 
 // statistics: fold the replicated accumulators into the caller's vector and clear them
 __global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
@@ -1728,6 +2048,8 @@ struct SyEnv {
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
   int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0;
+  int wr_c_mask = 0, wr_c_nf32 = 0, wr_c_nf8 = 0, wr_img_bytes = 0;  // bulk writers: chunk sizes per stream, image size
+  int opt_writer = SY_WRITER_LSU;  // sy_set_option(SY_OPT_WRITER_PATH) for the stand-alone observe kernel (sy_reset, two-kernel sy_step)
   int bel_warps = BEL_WARPS, wr_warps = WR_WARPS;  // role split of the observe kernel for this pool
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
 };
@@ -1771,6 +2093,20 @@ int alloc_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_strid
   return SY_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to a handle: it is only ever
+// raised, so a small env created next to a large one cannot pull the limit below what the large one launches with
+int raise_observe_smem_limit(int device, size_t bytes) {
+  static std::mutex mu;
+  static size_t limit[64] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = limit[device & 63];
+  if (bytes <= cur) return SY_OK;
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  cur = bytes;
+  return SY_OK;
+}
+
 void launch_observe(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t s) {
   if (e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS)
     sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
@@ -1809,10 +2145,12 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
     p.w32[i] = (float)c.reward_weights[i];
   }
   p.tb = env->tb;
+#ifdef SY_PROFILING_BUILD  // kernel-part ablations for profiling variants only; the shipped library has no such switch
   {
     static const int dbg = [] { const char* v = getenv("SY_DEBUG_SKIP"); return v ? atoi(v) : 0; }();
     p.dbg_skip = dbg;
   }
+#endif
   p.bel_flags = (uint8_t*)env->d_bel_flags;
   p.stats_rep = (unsigned long long*)env->d_stats_rep;
   p.bel_fast = env->bel_fast;
@@ -1828,7 +2166,34 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.st = *st;
   if (ob) p.ob = *ob;
   if (out) p.out = *out;
+  if (ob) {  // bulk stores need 16-byte aligned streams (a tile is 32 envs, so aligned bases are enough)
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(ob->action_mask) | reinterpret_cast<uintptr_t>(ob->node_features_u8 ? (void*)ob->node_features_u8 : (void*)ob->node_features);
+    p.wr_bulk = (env->opt_writer == SY_WRITER_BULK && (bits & 15u) == 0) ? 1 : 0;
+    p.wr_c_mask = env->wr_c_mask;
+    p.wr_c_nf = ob->node_features_u8 ? env->wr_c_nf8 : env->wr_c_nf32;
+    p.wr_img_bytes = env->wr_img_bytes;
+  }
   return SY_OK;
+}
+
+// chunk size (bytes, multiple of 16, <= cap) of a bulk-writer stream whose envs are S bytes each: whole groups of envs
+// when the smallest 16-byte sized group fits (leaving every writer warp a few chunks per tile), else a 16-byte
+// multiple that divides the group evenly when there is one in [cap / 2, cap], else just cap (chunks may then straddle
+// env boundaries, which the writers handle)
+int plan_bulk_chunk(size_t S, int cap, int wr_warps) {
+  size_t g = 16;
+  while (S % g) g >>= 1;  // gcd(S, 16)
+  const size_t m = 16 / g, group = S * m;
+  cap &= ~15;
+  if (group <= (size_t)cap) {
+    size_t k = cap / group;
+    const size_t kmax = std::max<size_t>(1, (TILE / m) / (2 * (size_t)wr_warps));
+    k = std::min(k, kmax);
+    return (int)(group * k);
+  }
+  for (int c = cap; c >= cap / 2 && c >= 16; c -= 16)
+    if (group % (size_t)c == 0) return c;
+  return cap;
 }
 
 int check_obs(const SyObs* ob) {
@@ -1908,6 +2273,18 @@ void sy_destroy(SyEnv* e) {
   if (e->ev_logic) cudaEventDestroy(e->ev_logic);
   if (e->ev_copied) cudaEventDestroy(e->ev_copied);
   delete e;
+}
+
+int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
+  if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
+  switch (option) {
+    case SY_OPT_WRITER_PATH:
+      if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
+      e->opt_writer = value;
+      return SY_OK;
+    default:
+      return fail(SY_ERR_INVALID_ARGUMENT, "unknown option %d", option);
+  }
 }
 
 int sy_set_seed(SyEnv* e, uint64_t seed) {
@@ -2060,7 +2437,15 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   {  // writer staging area: pos, money [TILE, A], revealed, graph id [TILE], per-warp flat one-hot indices and
      // action_mask images, then (optionally) the graph's CSR
     const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
-    const size_t base = ((size_t)2 * TILE * e->A + 2 * TILE + e->wr_warps * SY_MAX_AGENTS) * sizeof(int) + e->wr_warps * img_stride;
+    const size_t base_lsu = ((size_t)2 * TILE * e->A + 2 * TILE + e->wr_warps * SY_MAX_AGENTS) * sizeof(int) + e->wr_warps * img_stride;
+    // bulk writers: one zero page + two chunk images for each of the (at most BULK_WARPS) streaming warps
+    const int nbw = std::min(e->wr_warps, BULK_WARPS);
+    const int cap = std::max(256, (int)(SY_BULK_IMG_BUDGET / (2 * nbw + 1)));
+    e->wr_c_mask = plan_bulk_chunk((size_t)e->A * N, cap, nbw);
+    e->wr_c_nf32 = e->wr_c_nf8 = e->wr_c_mask;  // the uint8 node_features stream has the mask's geometry
+    e->wr_img_bytes = e->wr_c_mask;
+    const size_t base_bulk = ((size_t)2 * TILE * e->A + 2 * TILE) * sizeof(int) + (size_t)(2 * nbw + 1) * e->wr_img_bytes;
+    const size_t base = std::max(base_lsu, base_bulk);  // either writer path can be selected at run time
     // generic (large-N) belief path: it gathers over the same staged CSR, plus the 1/deg row, instead of walking the
     // neighbour lists in global memory (at N = 1000 they no longer fit the L1 left over by the shared-memory carve-out)
     const bool share = e->cfg.belief && !e->bel_fast;
@@ -2072,8 +2457,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     e->bel_share_csr = (share && e->wr_stage_csr) ? 1 : 0;
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
-    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
-    CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem));
+    if (int rc = raise_observe_smem_limit(e->cfg.device, e->obs_smem)) return rc;
   }
   e->tb.G = G;
   e->tb.Ns = Ns;

@@ -222,6 +222,15 @@ class BatchedScotlandYardEnv:
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
 
+    OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1})}  # include/sy_env.h SY_OPT_*
+
+    def set_option(self, name: str, value):
+        """Tuning knobs of the handle (results are identical for every setting): `writer_path` = "bulk" (TMA bulk
+        stores from shared-memory images, the default) | "lsu" (16-byte streaming stores)."""
+        opt, values = self.OPTIONS[name]
+        _cabi.check(self._lib.sy_set_option(self._handle, opt, values[value] if isinstance(value, str) else int(value)))
+        self.options = dict(getattr(self, "options", {}), **{name: value})
+
     def set_seed(self, seed: int):
         self.seed = int(seed)
         self.config.seed = self.seed & 0xFFFFFFFFFFFFFFFF

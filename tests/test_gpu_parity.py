@@ -56,7 +56,7 @@ def test_library_loaded_is_in_tree(torch_cuda):
     pkg = _pkg()
     lib = pkg.load_library()
     assert os.path.dirname(pkg.LIB_PATH).endswith("student_mechanism_design_b200")
-    assert lib.sy_abi_version() == pkg._cabi.SY_ABI_VERSION == 3
+    assert lib.sy_abi_version() == pkg._cabi.SY_ABI_VERSION == 4
 
 
 def test_graph_tables_match_oracle(torch_cuda, golden_traces):
