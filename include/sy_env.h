@@ -162,12 +162,25 @@ int64_t sy_launch_count(void);
 /* replaces CustomEnvironment.__init__ (yard.py:18-78) */
 int sy_create(const SyConfig* config, SyEnv** out_env);
 void sy_destroy(SyEnv* env);
-/* Tuning knobs of a handle (results are identical for every setting; bench.py records what it used).
- *   SY_OPT_WRITER_PATH  how the observation kernel's writer warps move action_mask / node_features to HBM:
- *                       SY_WRITER_BULK (default) = shared-memory images + cp.async.bulk (TMA) when the caller's
- *                       buffers are 16-byte aligned, else the LSU path; SY_WRITER_LSU = 16-byte streaming stores. */
-enum { SY_OPT_WRITER_PATH = 0 };
+/* Tuning knobs of a handle (results are identical for every setting -- tests/test_gpu_fullsize.py runs the BASELINE
+ * configs through each of them; bench.py records what it used; measurements in DESIGN.md section 4c).
+ *   SY_OPT_STEP_KERNEL  SY_STEP_AUTO (default): batches whose 32-env tiles fit one wave of the fused kernel's grid
+ *                       (<= ~9 500 envs) take SY_STEP_FUSED, larger ones SY_STEP_TWO_KERNELS.
+ *                       SY_STEP_FUSED: sy_step is ONE persistent kernel -- dynamics, belief propagation and a bulk-store
+ *                       (cp.async.bulk / TMA) observation stream as three warp-specialised roles, software-pipelined
+ *                       over the tiles of a CTA; in sy_rollout_random* its dynamics warps also draw the next step's
+ *                       actions.  Needs 16-byte aligned observation buffers and a belief map of <= ~400 nodes (else the
+ *                       call falls back to two kernels).  SY_STEP_TWO_KERNELS: dynamics kernel, then observation kernel.
+ *   SY_OPT_WRITER_PATH  writers of the two-kernel path's observation kernel: SY_WRITER_LSU (default) = 16-byte
+ *                       streaming stores; SY_WRITER_BULK = zero-page bulk fill + chunk images + bulk stores.
+ *   SY_OPT_NF_FILL      0 (default).  1: split step for batches of >= 8192 envs with float32 node_features: the zero
+ *                       fill of node_features (63 % of a step's bytes, independent of the state) is handed to the TMA
+ *                       engine by its own small kernel NEXT TO the dynamics kernel (second stream), then the belief
+ *                       propagation and the writers of the ones run as two concurrent kernels; all joined on the
+ *                       caller's stream before sy_step returns (events; capturable).  Measured slower. */
+enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2 };
 enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
+enum { SY_STEP_FUSED = 0, SY_STEP_TWO_KERNELS = 1, SY_STEP_AUTO = 2 };
 int sy_set_option(SyEnv* env, int32_t option, int32_t value);
 /* new Philox key for subsequent (auto-)resets and action sampling (torchrl `set_seed`) */
 int sy_set_seed(SyEnv* env, uint64_t seed);

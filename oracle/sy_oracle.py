@@ -300,7 +300,7 @@ _PHILOX_M0, _PHILOX_M1 = 0xD2511F53, 0xCD9E8D57
 _PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
 _M32 = 0xFFFFFFFF
 
-RNG_RESET_POS, RNG_RESET_GRAPH, RNG_ACTION = 0, 1, 2
+RNG_RESET_POS, RNG_RESET_GRAPH, RNG_ACTION, RNG_REVEAL_SKIP = 0, 1, 2, 3
 
 
 def philox4x32(ctr, key):
@@ -476,6 +476,8 @@ class OracleConfig:
     reveal_interval: int = 0  # 0 -> reference behaviour (MrX always visible)
     toll: int = 0  # 0 -> reference behaviour
     belief: bool = False
+    # robustness hook of src/eval/ood_eval.py:227-229 (RobustnessWrapper): probability that a scheduled reveal is skipped
+    reveal_skip_prob: float = 0.0
     # optional recorded float64 tables (tests/golden/tables.npz); None -> NumPy on this host
     exp_table: Optional[np.ndarray] = None
     cov_table: Optional[np.ndarray] = None
@@ -526,7 +528,9 @@ class OracleEnv:
         return np.nonzero((row > 0) & (row + self.cfg.toll <= m))[0].astype(np.int32)
 
     # yard.py:144-269
-    def step(self, actions: Sequence[Optional[int]]):
+    def step(self, actions: Sequence[Optional[int]], hint: Optional[Sequence[int]] = None, skip_reveal=None):
+        """`hint`: candidate nodes of belief_module.py:102-106 for this step's belief update; `skip_reveal(t)`: the
+        batch's Philox draw that decides whether the reveal scheduled at timestep t is skipped (ood_eval.py:227-229)"""
         P, A = self.P, self.A
         pos, money = self.pos, self.money
         # MrX (yard.py:155-188); None and any non-legal value both end in "stay"
@@ -555,6 +559,8 @@ class OracleEnv:
         self.winner = winner
         # extensions (parity unpinned): reveal schedule + belief propagation on the new timestep
         rev = is_reveal(self.t, self.cfg.reveal_interval)
+        if rev and skip_reveal is not None and skip_reveal(self.t):
+            rev = False
         if self.cfg.reveal_interval > 0:
             self.revealed = pos[0] if rev else -1
         else:
@@ -563,7 +569,7 @@ class OracleEnv:
         if self.cfg.belief:
             if rev:  # score the prediction before the reveal collapses it (metrics.py:142-147)
                 self.last_ce = belief_cross_entropy(belief_update(self.belief, self.graph), pos[0])
-            self.belief = belief_update(self.belief, self.graph, reveal=pos[0] if rev else None)
+            self.belief = belief_update(self.belief, self.graph, reveal=pos[0] if rev else None, hint=None if rev else hint)
         return rewards, terminated, truncated, winner
 
     # reward_calculator.py:26-92
@@ -738,9 +744,19 @@ class OracleBatch:
             sp.append(philox_start_positions(seed, e, 0, N, cfg.num_police + 1))
         return cls(cfg, graphs, gid, sp, seed, auto_reset, env_offset, resample_graph)
 
-    def step(self, actions):
-        """actions int [B, A] (-1 == None).  Returns dict of arrays for this step, then applies
-        the same-step auto-reset (observations afterwards describe the fresh episode)."""
+    def _skip_draw(self, b):
+        """the device's draw: skip iff Philox(seed; global env, t, RNG_REVEAL_SKIP, episode)[0] < float32(p) * 2^32"""
+        p = float(np.float32(self.cfg.reveal_skip_prob))
+        if p <= 0.0:
+            return None
+        thresh = int(min(p, 1.0) * 4294967296.0)
+        key = (self.seed & _M32, (self.seed >> 32) & _M32)
+        return lambda t: philox4x32((self.env_offset + b, t, RNG_REVEAL_SKIP, self.episode[b]), key)[0] < thresh
+
+    def step(self, actions, hints=None):
+        """actions int [B, A] (-1 == None); hints: optional bool/uint8 [B, N] observation hints (belief_module.py:
+        102-106).  Returns dict of arrays for this step, then applies the same-step auto-reset (observations afterwards
+        describe the fresh episode)."""
         B, A = len(self.envs), self.cfg.num_police + 1
         f = np.float32 if self.cfg.reward_mode == "fp32" else np.float64
         out = dict(
@@ -752,7 +768,8 @@ class OracleBatch:
         for b, env in enumerate(self.envs):
             if self.done[b]:  # frozen until reset (no auto-reset): zero reward, flags stay
                 continue
-            r, te, tr, win = env.step([int(x) for x in actions[b]])
+            hint = None if hints is None else [int(j) for j in np.nonzero(np.asarray(hints[b]))[0]]
+            r, te, tr, win = env.step([int(x) for x in actions[b]], hint=hint, skip_reveal=self._skip_draw(b))
             out["reward"][b] = r
             out["terminated"][b], out["truncated"][b], out["winner"][b] = te, tr, win
             if env.last_ce is not None and not ((te or tr) and self.auto_reset):

@@ -27,11 +27,91 @@ from .graphs import GraphSpec, generate_connected_graph
 WINNER_NAMES = {0: None, 1: "MrX", 2: "Police"}  # env.current_winner, yard.py:250
 
 
-class _Discrete:
-    """stand-in for gymnasium.spaces.Discrete (only `.n` is used by the trainers, gnn_trainer.py:133-135)"""
+class _Space:
+    """stand-in for a gymnasium space when gymnasium is not installed: same attribute names"""
 
+    def __repr__(self):
+        return f"{type(self).__name__}({', '.join(f'{k}={v!r}' for k, v in vars(self).items())})"
+
+
+class _Discrete(_Space):
+    def __init__(self, n, start=0):
+        self.n, self.start, self.dtype, self.shape = int(n), int(start), np.int64, ()
+
+
+class _MultiDiscrete(_Space):
+    def __init__(self, nvec):
+        self.nvec = np.asarray(nvec, dtype=np.int64)
+        self.dtype, self.shape = np.int64, self.nvec.shape
+
+
+class _MultiBinary(_Space):
     def __init__(self, n):
-        self.n, self.start, self.dtype = int(n), 0, np.int64
+        self.n, self.dtype, self.shape = int(n), np.int8, (int(n),)
+
+
+class _Box(_Space):
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+class _Dict(_Space):
+    def __init__(self, spaces):
+        self.spaces = dict(spaces)
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def keys(self):
+        return self.spaces.keys()
+
+
+def _space_classes():
+    """gymnasium's classes when it is installed (what the reference builds, yard.py:5), else the stand-ins above"""
+    try:
+        import gymnasium
+        from gymnasium.spaces import Box, Dict, Discrete, MultiBinary, MultiDiscrete
+
+        if not hasattr(gymnasium, "__version__"):  # a test stub on sys.path, not the library
+            raise ImportError
+        return Discrete, MultiDiscrete, MultiBinary, Box, Dict
+    except Exception:
+        return _Discrete, _MultiDiscrete, _MultiBinary, _Box, _Dict
+
+
+MAX_WEIGHT = 5  # ConnectedGraph.MAX_WEIGHT, graph_layout.py:12
+MAX_MONEY_LIMIT = 1000  # yard.py:11
+
+
+def reference_action_space(num_nodes: int):
+    """yard.py:482-498: Discrete(num_nodes), action i = move to node i (invalid ones are masked)"""
+    return _space_classes()[0](int(num_nodes))
+
+
+def reference_observation_space(num_nodes: int, num_police: int, num_edges: int, agent_money: int, *, belief: bool = False,
+                                reveal: bool = False):
+    """yard.py:500-554, key for key and with the DECLARED dtypes (the reference's produced arrays differ: adjacency and
+    node_features are float64, edge_features int64 -- SURVEY.md 8(a) a5; the declaration is reproduced as written).
+    `belief` / `reveal` add the keys this env's extensions emit (belief_map f32 [N]; MrX_revealed in {-1..N-1})."""
+    Discrete, MultiDiscrete, MultiBinary, Box, Dict = _space_classes()
+    N, P, E = int(num_nodes), int(num_police), int(num_edges)
+    spaces = {
+        "adjacency_matrix": Box(low=0.0, high=1.0, shape=(N, N), dtype=np.int64),
+        "node_features": Box(low=0.0, high=1.0, shape=(N, P + 1), dtype=np.int64),
+        "edge_index": Box(low=0, high=N, shape=(2, E), dtype=np.int32),
+        "edge_features": Box(low=0, high=MAX_WEIGHT, shape=(E,), dtype=np.int32),
+        "MrX_pos": Discrete(N),
+        "Polices_pos": MultiDiscrete([N] * P),
+        "Currency": MultiDiscrete([int(agent_money) + 1] * P),
+        "action_mask": MultiBinary(N),
+        "agent_position": Discrete(N),
+        "agent_budget": Box(low=0.0, high=MAX_MONEY_LIMIT, shape=(1,), dtype=np.float32),
+    }
+    if belief:
+        spaces["belief_map"] = Box(low=0.0, high=1.0, shape=(N,), dtype=np.float32)
+    if reveal:
+        spaces["MrX_revealed"] = Discrete(N + 1, start=-1)
+    return Dict(spaces)
 
 
 class CustomEnvironment:
@@ -115,7 +195,12 @@ class CustomEnvironment:
         return self._env.get_possible_moves(agent_idx, 0)
 
     def action_space(self, agent):
-        return _Discrete(self.graph_nodes)  # yard.py:482-498
+        return reference_action_space(self.graph_nodes)  # yard.py:482-498
+
+    def observation_space(self, agent):
+        """yard.py:500-554 (same keys and declared dtypes), plus the keys of this env's extensions when they are on"""
+        return reference_observation_space(self.graph_nodes, self.number_of_agents, self.actual_num_edges, self.agent_money,
+                                           belief=bool(self._kw["belief"]), reveal=bool(self._kw["reveal_interval"]))
 
     def get_distance(self, node1, node2):
         return self._env.get_distance(int(node1), int(node2), 0)  # yard.py:375-388

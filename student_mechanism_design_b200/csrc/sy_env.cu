@@ -30,6 +30,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -90,7 +91,7 @@ constexpr int AS = SY_MAX_AGENTS + 1;  // odd smem row stride -> conflict-free l
 constexpr unsigned FULL = 0xffffffffu;
 enum { DIST_INF = 0xFFFF };
 
-enum { RNG_RESET_POS = 0, RNG_RESET_GRAPH = 1, RNG_ACTION = 2 };
+enum { RNG_RESET_POS = 0, RNG_RESET_GRAPH = 1, RNG_ACTION = 2, RNG_REVEAL_SKIP = 3 };
 enum { ST_RUNNING = 0, ST_CAPTURE = 1, ST_TIMEOUT = 2, ST_NO_MONEY = 3 };
 enum { BEL_KEEP = 0, BEL_UNIFORM = 1, BEL_DELTA = 2, BEL_PROPAGATE = 3 };
 
@@ -116,6 +117,8 @@ struct Params {
   int inv_A;  // ceil(2^16 / A): (i * inv_A) >> 16 == i / A for i < 2^12
   int agent_money, mrx_money, max_t, reveal, toll, belief_on, belief_score, auto_reset, resample_graph, reward_mode;
   unsigned long long env_offset;
+  unsigned long long reveal_skip_thresh;  // a scheduled reveal is skipped when its Philox word < this (reveal_skip_prob * 2^32)
+  const uint8_t* belief_hint;             // [B, N] or NULL (SyState.belief_hint)
   unsigned seed_lo, seed_hi;
   double w64[SY_NUM_REWARD_WEIGHTS];
   float w32[SY_NUM_REWARD_WEIGHTS];
@@ -133,9 +136,17 @@ struct Params {
   // wr_c_mask / wr_c_nf bytes (multiples of 16); each chunk is assembled in a per-warp shared-memory image and leaves
   // the SM with one cp.async.bulk.  0 = the LSU writers (unaligned caller buffers, or selected with sy_set_option)
   int wr_bulk, wr_c_mask, wr_c_nf, wr_img_bytes;
+  int nf_prefilled;  // float32 node_features were zero-filled by the logic kernel (bulk stores): the writers only store the ones
+  int f_off_sbuf, f_sbuf_stride, f_off_zero, f_off_imgs;  // fused kernel: staged tile state (x2), zero page, chunk images
+  int f_off_nbr4;  // fused kernel: packed neighbour table [N] uint4 + flag (after the staged CSR)
+  int wr_epc;      // fused kernel fast geometry: whole envs per chunk (0: chunks cut through envs / more than 32 pairs)
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
+  // fused rollout steps: the logic warps also draw the NEXT step's random valid actions (sy_sample_actions semantics)
+  long long* next_actions;          // int64 [B, A] or NULL; may alias `actions` (a tile reads its actions before it writes them)
+  unsigned next_counter;            // step counter of the draw (+ *next_counter_base when that is set)
+  const unsigned* next_counter_base;
   // reset-only inputs
   const uint8_t* reset_mask;
   const int32_t* init_pos;
@@ -181,6 +192,15 @@ __device__ void philox_start_positions(const Params& p, unsigned env, unsigned e
     chosen[j] = (T)x;
     out[a] = (T)x;
   }
+}
+
+// reveal schedule (src/eval/run_ablations.py:225-229) with the robustness hook of src/eval/ood_eval.py:227-229: a scheduled
+// reveal is skipped with probability reveal_skip_prob, one Philox(seed; env, timestep, RNG_REVEAL_SKIP, episode) draw
+__device__ __forceinline__ bool reveal_now(const Params& p, unsigned env, int t, int episode) {
+  if (p.reveal <= 0 || t <= 0 || (t % p.reveal) != 0) return false;
+  if (p.reveal_skip_thresh == 0) return true;
+  const uint4 r = philox4x32(make_uint4(env, (unsigned)t, RNG_REVEAL_SKIP, (unsigned)episode), make_uint2(p.seed_lo, p.seed_hi));
+  return (unsigned long long)r.x >= p.reveal_skip_thresh;
 }
 
 __device__ __forceinline__ int philox_graph_choice(const Params& p, unsigned env, unsigned episode) {
@@ -704,7 +724,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
         p.out.winner[b] = SY_WINNER_NONE;
       }
       // reveal schedule (src/eval/run_ablations.py:225-229) on the new timestep
-      const bool rev = p.reveal > 0 && t_new > 0 && (t_new % p.reveal) == 0;
+      const bool rev = reveal_now(p, (unsigned)(p.env_offset + (unsigned long long)b), t_new, episode);
       if (rev && bel == BEL_PROPAGATE) bel = BEL_DELTA;
       revealed = (p.reveal <= 0 || rev) ? (int)pos[0] : -1;
     }
@@ -793,6 +813,33 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     if (n % LOGIC_WARPS == warp)
       warp_zero_bytes(reinterpret_cast<uint8_t*>(p.st.visits + (size_t)(b0 + e) * N), N * (int)sizeof(uint16_t), lane);
   }
+  if (p.next_actions) {
+    // the next step's random valid actions from the NEW state still held in shared memory: the same draw as
+    // sy_sample_actions_kernel (Philox(seed; env, step counter, agent) -> the pick-th affordable neighbour)
+    const unsigned ctr = p.next_counter + (p.next_counter_base ? *p.next_counter_base : 0u);
+    for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
+      const int e = (i * p.inv_A) >> 16, a = i - e * A;
+      const int gg = sm.gid[e], u = (int)sm.pos[e * HS + a], m = sm.money[e * AS + a];
+      const int nvalid = move_count(p.tb, N, gg, u, m, p.toll);
+      long long act = -1;
+      if (nvalid > 0) {
+        const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)(b0 + e));
+        const uint4 r = philox4x32(make_uint4(env_id, ctr, RNG_ACTION, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
+        int pick = (int)__umulhi(r.x, (unsigned)nvalid);
+        const uint8_t* wg = p.tb.wgt + (size_t)gg * p.tb.nnz_stride;
+        for (int k = __ldg(p.tb.row_ptr + (size_t)gg * (N + 1) + u);; ++k) {  // the pick-th affordable neighbour exists
+          if (__ldg(wg + k) + p.toll <= m) {
+            if (pick == 0) {
+              act = __ldg(p.tb.col + (size_t)gg * p.tb.nnz_stride + k);
+              break;
+            }
+            --pick;
+          }
+        }
+      }
+      p.next_actions[(size_t)b0 * A + i] = act;
+    }
+  }
   PHASE_MARK(7);
 }
 
@@ -800,6 +847,36 @@ template <int MODE, int MAXA>
 __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_kernel(const Params p) {
   __shared__ LogicSmem<MAXA> sm;
   logic_tile<MODE, MAXA, 3>(p, sm, blockIdx.x * 32, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fill kernel: the zero fill of the float32 node_features array is 63 % of a step's bytes and does not depend on the
+// state, while the dynamics and the belief propagation are latency / issue bound and leave HBM idle.  In the split step
+// (step_impl) this kernel therefore runs from the first microsecond of the step NEXT TO the dynamics kernel: a handful
+// of threads per SM hand the whole array to the TMA engine (cp.async.bulk from a shared-memory zero page: no LSU, no
+// registers, ~2 % of the issue slots) and wait for completion; the observation writers later only store the 16-byte
+// granules that hold a one (p.nf_prefilled).  Micro-benchmark (tools/exp/tma_fill.cu): 6.1-6.2 TB/s with 1 CTA per SM.
+// ---------------------------------------------------------------------------------------------
+#ifndef SY_FILL_PAGE
+#define SY_FILL_PAGE 8192
+#endif
+constexpr int FILL_THREADS = 64;
+#ifndef SY_SPLIT_MIN_ENVS
+#define SY_SPLIT_MIN_ENVS 8192
+#endif
+constexpr int SPLIT_MIN_ENVS = SY_SPLIT_MIN_ENVS;  // smaller batches are launch-latency bound: two plain launches
+__global__ void __launch_bounds__(FILL_THREADS) sy_fill_kernel(uint8_t* dst, size_t bytes) {
+  __shared__ __align__(128) uint8_t zero_page[SY_FILL_PAGE];
+  for (int i = threadIdx.x * 16; i < SY_FILL_PAGE; i += FILL_THREADS * 16) *reinterpret_cast<uint4*>(zero_page + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  __syncthreads();
+  const size_t body = bytes & ~(size_t)15;
+  const size_t stride = (size_t)gridDim.x * FILL_THREADS * SY_FILL_PAGE;
+  for (size_t o = ((size_t)blockIdx.x * FILL_THREADS + threadIdx.x) * SY_FILL_PAGE; o < body; o += stride)
+    bulk_store(dst + o, zero_page, (unsigned)min((size_t)SY_FILL_PAGE, body - o));
+  bulk_commit();
+  if (blockIdx.x == 0 && threadIdx.x < (int)(bytes - body)) dst[body + threadIdx.x] = 0;
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // complete before the kernel ends: the ones follow in stream order
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -846,7 +923,7 @@ __global__ void __launch_bounds__(LOGIC_THREADS) sy_reset_kernel(const Params p)
       done = p.st.done[b];
       g = p.st.graph_id[b];
     }
-    const bool rev = p.reveal > 0 && t > 0 && (t % p.reveal) == 0;
+    const bool rev = reveal_now(p, (unsigned)(p.env_offset + (unsigned long long)b), t, episode);
     revealed = (p.reveal <= 0 || rev) ? wt.pos[lane * AS] : -1;
   }
   store_state(p, wt, b0, nEnv, lane, t, g, episode, done, rst ? BEL_UNIFORM : BEL_KEEP, revealed, rst);
@@ -881,6 +958,30 @@ __device__ __forceinline__ void warp_copy_bytes(uint8_t* dst, const uint8_t* src
 // (yard.py:279-290).  The region is zero-filled with 16-byte stores; lane a then overwrites, with one full 16-byte
 // store, the chunk that holds agent a's one (assembled in registers from all agents that fall into it).  Measured:
 // rewriting a handful of whole chunks costs nothing, whereas byte-sized ones after the fill cost 60 %.
+// the same after a completed zero fill of the region (p.nf_prefilled): only the ones -- whole granules when the env rows
+// are granule-aligned, single floats otherwise
+__device__ __forceinline__ void warp_write_node_feature_ones(float* nf, int n, const int* fpos, int A, int lane) {
+  if (lane >= A || fpos[lane] < 0) return;
+  if ((n & 3) || (reinterpret_cast<uintptr_t>(nf) & 15u)) {
+    nf[fpos[lane]] = 1.0f;
+    return;
+  }
+  const int myc = fpos[lane] >> 2;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  for (int a = 0; a < A; ++a) {
+    const int f = fpos[a];
+    if (f >= 0 && (f >> 2) == myc) {
+      const unsigned one = 0x3f800000u;
+      const int sub = f & 3;
+      v.x = sub == 0 ? one : v.x;
+      v.y = sub == 1 ? one : v.y;
+      v.z = sub == 2 ? one : v.z;
+      v.w = sub == 3 ? one : v.w;
+    }
+  }
+  store_obs16(reinterpret_cast<uint4*>(nf) + myc, v);
+}
+
 __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const int* fpos /*smem, A entries, -1 = none*/,
                                                           int A, int lane) {
   const int head = min(n, (int)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(nf) & 15u)) & 15u) >> 2));
@@ -1009,7 +1110,8 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
       __syncwarp();
       warp_copy_bytes(nf8, img8, N * A, lane);
     } else {
-      warp_write_node_features(nf, N * A, fpos, A, lane);
+      if (p.nf_prefilled) warp_write_node_feature_ones(nf, N * A, fpos, A, lane);
+      else warp_write_node_features(nf, N * A, fpos, A, lane);
     }
     __syncwarp();
     for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
@@ -1357,14 +1459,14 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
   float* bel = p.st.belief + (size_t)b * N;
   const float unif = 1.0f / (float)N;
   const bool score = op == BEL_DELTA && p.belief_score && p.out.stats != nullptr;  // reveal: score the prediction, then collapse it
-  const int x = op == BEL_DELTA ? p.st.pos[(size_t)b * p.A] : -1;
+  const int x = op == BEL_DELTA ? __ldcg(p.st.pos + (size_t)b * p.A) : -1;
   if (op == BEL_UNIFORM) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
   } else if (op == BEL_DELTA && !score) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
   } else if (op == BEL_PROPAGATE || score) {
     float S = 0.0f, vx = 0.0f;
-    const int g = p.st.graph_id[b];
+    const int g = __ldcg(p.st.graph_id + b);
     const int32_t* gptr = tb.pack_ptr + (size_t)g * (N + 1);
     const int2* gpack = tb.nbr_pack + (size_t)g * tb.pack_stride;
     __syncwarp();
@@ -1466,6 +1568,15 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
     if (score) {
       ce_record(ce, S, vx);
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
+    } else if (p.belief_hint && op == BEL_PROPAGATE && tot != 0.0f) {
+      // observation hint (belief_module.py:102-106) on the row this warp just wrote (every lane re-reads its own stores)
+      const uint8_t* hint = p.belief_hint + (size_t)b * N;
+      float hs = 0.0f;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) hs += bel[j] * (hint[j] ? 1.0f : 0.1f);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) hs += __shfl_xor_sync(FULL, hs, o);
+      const float inv = hs == 0.0f ? 0.0f : 1.0f / hs;
+      _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = hs == 0.0f ? unif : bel[j] * (hint[j] ? 1.0f : 0.1f) * inv;
     }
   }
 }
@@ -1476,8 +1587,8 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   // every belief warp reads the same 32 flags / graph ids, so the branches below are uniform across the role
   int op = BEL_KEEP, g = -1;
   if (lane < nEnv) {
-    op = p.bel_flags[tile0 + lane];
-    g = p.st.graph_id[tile0 + lane];
+    op = __ldcg(p.bel_flags + tile0 + lane);
+    g = __ldcg(p.st.graph_id + tile0 + lane);
   }
   // rows that go through the propagation: moving envs, plus revealed ones while their prediction is being scored
   const bool score = p.belief_score && p.out.stats != nullptr;
@@ -1584,7 +1695,21 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       float tot = 0.0f;
 #pragma unroll
       for (int ww = 0; ww < BW; ++ww) tot += part[ww * 32 + e];
-      if (tot == 0.0f) {  // belief_module.py:29-38
+      if (p.belief_hint && tot != 0.0f) {
+        // observation hint (belief_module.py:102-106): likelihood 0.1 + 0.9 * [j is a candidate], then normalise.  An
+        // all-zero hint row scales every node alike and normalises away, like the reference's `if observation_hint:`
+        const uint8_t* hint = p.belief_hint + (size_t)(tile0 + e) * N;
+        float hs = 0.0f;
+        _Pragma("unroll 1") for (int j = lane; j < N; j += 32) hs += tout[j * BSTRIDE + e] * (hint[j] ? 1.0f : 0.1f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hs += __shfl_xor_sync(FULL, hs, o);
+        if (hs == 0.0f) {
+          _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
+        } else {
+          const float inv = 1.0f / hs;
+          _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = tout[j * BSTRIDE + e] * (hint[j] ? 1.0f : 0.1f) * inv;
+        }
+      } else if (tot == 0.0f) {  // belief_module.py:29-38
         _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
       } else {
         const float inv = 1.0f / tot;
@@ -1593,7 +1718,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
     } else if (ope == BEL_UNIFORM) {
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
-      const int x = p.st.pos[(size_t)(tile0 + e) * p.A];
+      const int x = __ldcg(p.st.pos + (size_t)(tile0 + e) * p.A);
       if (score) {
         float tot = 0.0f, vx = 0.0f, S = 0.0f;
 #pragma unroll
@@ -1619,9 +1744,11 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
 
 // BW belief warps + WRW writer warps.  <8, 8> everywhere the belief hides under the write stream (fast path); the
 // large-N generic belief path is the critical role, there the split is <12, 4> (c4: 82 -> 91 M env-steps/s).
+// <BW, 0> / <0, WRW>: one role per launch (the split step runs them as two concurrent kernels; the role hand-over
+// barrier of the large-N belief path counts THREADS, so that path keeps both roles in one launch)
 template <int BW, int WRW>
-__global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
-  static_assert((BW + WRW) * 32 == THREADS, "the role hand-over barrier counts THREADS");
+__global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Params p) {
+  static_assert((BW + WRW) * 32 == THREADS || BW == 0 || WRW == 0, "the role hand-over barrier counts THREADS");
   extern __shared__ __align__(16) unsigned char dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile0 = blockIdx.x * TILE;
@@ -1629,14 +1756,380 @@ __global__ void __launch_bounds__(THREADS) sy_observe_kernel(const Params p) {
   const int nbw = BW;  // without a belief map the belief warps simply exit
   if (warp < nbw && !p.belief_on) return;
   if (warp < nbw) {
-    if (!(p.dbg_skip & 4)) belief_role<BW>(p, dyn, tile0, nEnv, warp, lane);
+    if constexpr (BW > 0) {
+      if (!(p.dbg_skip & 4)) belief_role<BW>(p, dyn, tile0, nEnv, warp, lane);
+    }
   } else if (!(p.dbg_skip & 1)) {
-    if (p.wr_bulk) writer_role_bulk<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
-    else writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+    if constexpr (WRW > 0) {
+      if (p.wr_bulk) {
+        if constexpr (WRW >= 2) writer_role_bulk<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+      } else {
+        writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+      }
+    }
   }
 }
 
 constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? 12 : BEL_WARPS, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
+
+// ---------------------------------------------------------------------------------------------
+// fused persistent step kernel: ONE launch per sy_step.  Every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// with three warp-specialised roles that run at their own pace:
+//   logic warps   (LOGIC_WARPS)  the dynamics of tile k, k+1, ... back to back (logic_tile); after each tile they
+//                                publish `tiles_done` (st.release).  Nothing they touch is shared with the other roles
+//                                except through global memory, so they may run ahead freely.
+//   writer warps  (FUSED_WR)     the dense observations of the tiles whose dynamics are done, as ONE continuous
+//                                software pipeline over all of the CTA's chunks: zero fill of the NEXT chunk's float32
+//                                piece (needs no state, so the store stream starts at cycle 0 and never stalls on the
+//                                logic), image of this chunk, ones of the piece filled BULK_DEPTH chunks ago.
+//   belief warps  (BW)           the belief propagation of the finished tiles (belief_role).
+// The store stream goes through the TMA engine, so the logic's loads and shared-memory accesses no longer queue behind
+// it in the LSU (what made the round-1 fused attempts slower than two kernels), and the latency-bound dynamics hide
+// under a stream that is HBM-bound from the first microsecond.
+// ---------------------------------------------------------------------------------------------
+constexpr int FUSED_WR = 2;
+#ifdef SY_FUSED_CLOCKS  // profiling builds: per-role time inside the fused kernel, summed over CTAs (sy_debug_fused_clocks)
+__device__ unsigned long long g_fused_clk[16];
+#define FCLK_ADD(slot, v) do { if (lane == 0) atomicAdd(&g_fused_clk[slot], (unsigned long long)(v)); } while (0)
+#define FCLK_NOW() clock64()
+#else
+#define FCLK_ADD(slot, v) do { } while (0)
+#define FCLK_NOW() 0ll
+#pragma nv_diag_suppress 177
+#endif
+
+__device__ __forceinline__ void publish_u32(unsigned* smem_word, unsigned v) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_word);
+  asm volatile("st.release.cta.shared.u32 [%0], %1;\n" ::"r"(sa), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned acquire_u32(const unsigned* smem_word) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_word);
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(sa) : "memory");
+  return v;
+}
+// every lane of the warp continues only after the logic warps have finished tile index k of this CTA
+__device__ __forceinline__ void wait_tiles_done(const unsigned* tiles_done, unsigned k, int lane, int clk_slot = -1) {
+  const long long t0 = FCLK_NOW();
+  if (lane == 0) {
+    // the logic warps of this CTA never wait for anything, so the wait is bounded by their progress; the spin is
+    // capped (~1 s) so that a can't-happen stall shows up as a wrong result in the parity tests, never as a hung GPU
+    for (unsigned spins = 0; acquire_u32(tiles_done) <= k && spins < (1u << 24); ++spins) __nanosleep(64);
+  }
+  __syncwarp();
+  if (clk_slot >= 0) FCLK_ADD(clk_slot, FCLK_NOW() - t0);
+}
+
+struct FusedSmemPlan {  // byte offsets into the dynamic shared memory of the fused kernel (Params carries them)
+  int sbuf, sbuf_stride, zero, imgs, csr;
+};
+
+// One chunk of the writers' FAST geometry: a chunk is `epc` whole envs (epc * A <= 32), lane = (env, agent) pair, the
+// tile sits on one staged graph whose nodes have at most 4 neighbours (s_nbr4: one LDS.128 per node holding 4 x
+// {col | wgt << 16}, 0xFFFFFFFF = none).  Everything is straight-line code: no division, no loop.
+struct PairView {
+  bool valid;   // lane holds a live (env, agent) pair of the chunk
+  int e, a;     // env inside the tile, agent
+  int u, m;     // node, budget
+};
+__device__ __forceinline__ PairView pair_of(const Params& p, const int* s_pos, const int* s_money, int cm, int epc, int nEnv, int lane) {
+  PairView v;
+  const int A = p.A;
+  const int de = (lane * p.inv_A) >> 16;
+  v.a = lane - de * A;
+  v.e = cm * epc + de;
+  v.valid = de < epc && v.e < nEnv;
+  v.u = v.valid ? s_pos[v.e * A + v.a] : 0;
+  v.m = v.valid ? s_money[v.e * A + v.a] : 0;
+  return v;
+}
+// affordable neighbours of the pair's node into (v = 1) or out of (v = 0) the chunk image (action_mask.py:65-76).
+// s_nbr4[u] = the first four neighbours as {col | wgt << 16}, the degree in the top byte of .x; the rare nodes with
+// more neighbours finish over the staged CSR.
+__device__ __forceinline__ void fast_mask_ones(const Params& p, const PairView& pv, const uint4* s_nbr4, const int* s_rp, const uint16_t* s_col,
+                                               const uint8_t* s_wgt, uint8_t* img, int epc, int cm, uint8_t v) {
+  if (!pv.valid) return;
+  const uint4 nb = s_nbr4[pv.u];
+  const int deg = (int)(nb.x >> 24);
+  uint8_t* row = img + ((pv.e - cm * epc) * p.A + pv.a) * p.N;
+  const int lim = pv.m - p.toll;  // wgt + toll <= m
+  if (deg > 0 && (int)((nb.x >> 16) & 0xffu) <= lim) row[nb.x & 0xffffu] = v;
+  if (deg > 1 && (int)(nb.y >> 16) <= lim) row[nb.y & 0xffffu] = v;
+  if (deg > 2 && (int)(nb.z >> 16) <= lim) row[nb.z & 0xffffu] = v;
+  if (deg > 3 && (int)(nb.w >> 16) <= lim) row[nb.w & 0xffffu] = v;
+  if (deg > 4) {
+    const int r0 = s_rp[pv.u];
+    for (int k = r0 + 4; k < r0 + deg; ++k)
+      if ((int)s_wgt[k] <= lim) row[s_col[k]] = v;
+  }
+}
+// one-hot granules of the chunk's envs (float32 node_features, rows of whole 16-byte granules): pairs whose ones share a
+// granule find each other with match.any and the lowest lane stores the merged granule
+__device__ __forceinline__ void fast_nf32_ones(const Params& p, const PairView& pv, const int* s_rev, uint8_t* gnf, int lane) {
+  const int A = p.A;
+  const bool on = pv.valid && !(pv.a == 0 && s_rev[pv.e] < 0);  // the MrX column stays blank while he is hidden
+  const int f = pv.u * A + pv.a;                                  // element index in the env's [N, A] row
+  const unsigned key = on ? (unsigned)(pv.e * (p.N * A / 4) + (f >> 2)) : (0x80000000u | (unsigned)lane);
+  const unsigned peers = __match_any_sync(FULL, key);
+  const unsigned bits = __reduce_or_sync(peers, on ? (1u << (f & 3)) : 0u);
+  if (on && (peers & ((1u << lane) - 1u)) == 0) {
+    const unsigned one = 0x3f800000u;
+    const uint4 v = make_uint4(bits & 1u ? one : 0u, bits & 2u ? one : 0u, bits & 4u ? one : 0u, bits & 8u ? one : 0u);
+    store_obs16(reinterpret_cast<uint4*>(gnf + (size_t)pv.e * p.N * A * 4) + (f >> 2), v);
+  }
+}
+
+template <int BW>
+__device__ __forceinline__ void fused_writer_role(const Params& p, unsigned char* dyn, const unsigned* tiles_done, int w, int lane) {
+  constexpr int D = BULK_DEPTH;
+  const Tables& tb = p.tb;
+  const int N = p.N, A = p.A;
+  const int ntiles = (p.B + TILE - 1) / TILE;
+  const int nk = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  if (nk == 0) return;
+  const int Cm = p.wr_c_mask;
+  const bool nf8 = p.ob.node_features_u8 != nullptr;
+  const size_t Sm = (size_t)A * N;
+  uint8_t* zero_page = dyn + p.f_off_zero;
+  uint8_t* my_img = dyn + p.f_off_imgs + (size_t)w * 2 * p.wr_img_bytes;
+  int* s_rp = reinterpret_cast<int*>(dyn + p.wr_off_csr);
+  uint16_t* s_col = reinterpret_cast<uint16_t*>(s_rp + N + 1);
+  uint8_t* s_wgt = reinterpret_cast<uint8_t*>(s_col + tb.nnz_stride);
+  uint4* s_nbr4 = reinterpret_cast<uint4*>(dyn + p.f_off_nbr4);  // [N] packed neighbour table of the staged graph (wr_epc only)
+  const int tw = w * 32 + lane;
+  for (int i = tw * 16; i < (1 + 2 * FUSED_WR) * p.wr_img_bytes; i += FUSED_WR * 32 * 16) *reinterpret_cast<uint4*>(zero_page + i) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  named_barrier(2, FUSED_WR * 32);
+  auto tile_of = [&](int k) { return (int)blockIdx.x + k * (int)gridDim.x; };
+  auto envs_of = [&](int k) { return min(TILE, p.B - tile_of(k) * TILE); };
+  auto gnf_of = [&](int k) { return reinterpret_cast<uint8_t*>(p.ob.node_features) + (size_t)tile_of(k) * TILE * Sm * 4; };
+  auto sbuf = [&](int k) { return reinterpret_cast<int*>(dyn + p.f_off_sbuf + (size_t)(k & 1) * p.f_sbuf_stride); };
+  auto ctx_of = [&](int k) {
+    int* b = sbuf(k);
+    return BulkCtx{b, b + TILE * A, b + 2 * TILE * A, b + 2 * TILE * A + TILE, s_rp, s_col, s_wgt};
+  };
+  // zero fill of the float32 piece that belongs to mask chunk `cm` of a tile (lane 0 issues, the ragged tail is bytes)
+  auto fill_piece = [&](uint8_t* g, int Tf32, int cm) {
+    const int lo = 4 * cm * Cm, hi = min(Tf32, lo + 4 * Cm);
+    if (lane == 0) nf32_fill_piece(g, lo, hi, zero_page, Cm);
+    const int tail = (hi - lo) & 15;
+    if (lane < tail) g[hi - tail + lane] = 0;
+  };
+  // ---- prologue: the whole float32 fill of this warp's share of the first tile -- it needs no state, so the store
+  // stream runs while the logic warps are still busy with the tile
+  if (!nf8) {
+    const int Tm0 = envs_of(0) * (int)Sm;
+    uint8_t* g0 = gnf_of(0);
+    for (int cm = w; cm < (Tm0 + Cm - 1) / Cm; cm += FUSED_WR) fill_piece(g0, 4 * Tm0, cm);
+  }
+  if (lane == 0) bulk_commit();
+  // chunks whose image ones / float32 ones are still owed, oldest first: (tile index k, item, fast geometry?)
+  int ring_k[D], ring_item[D], ring_fast[D];
+  int pending = 0, it = 0, last_g = -2;
+  bool staged = false;
+  // generic (any geometry) forms, used when a tile is not on the fast path
+  auto generic_img = [&](int k, int item, const ImageStreams& st, uint8_t* img, uint8_t v) {
+    const BulkCtx c = ctx_of(k);
+    if (item < st.ncf) {
+      const int lo = item * p.wr_c_nf;
+      bulk_nf_ones<1>(p, c, img, lo, min(p.wr_c_nf, st.Tf - lo), lane, v != 0);
+    } else {
+      const int lo = (item - st.ncf) * Cm, len = min(Cm, st.Tm - lo);
+      if (staged) bulk_mask_ones<true>(p, c, img, lo, len, lane, v);
+      else bulk_mask_ones<false>(p, c, img, lo, len, lane, v);
+    }
+  };
+  auto owed_ones = [&](int k, int item, int fast) {  // float32 ones of an older chunk, after its fill has completed
+    if (nf8) return;
+    int* b = sbuf(k);
+    if (fast) {
+      const PairView pv = pair_of(p, b, b + TILE * A, item, p.wr_epc, envs_of(k), lane);
+      fast_nf32_ones(p, pv, b + 2 * TILE * A, gnf_of(k), lane);
+    } else {
+      const ImageStreams so = image_streams(p, tile_of(k) * TILE, envs_of(k));
+      if (item >= so.ncf) {
+        const int lo = 4 * (item - so.ncf) * Cm;
+        nf32_ones_piece(p, ctx_of(k), gnf_of(k), lo, min(4 * so.Tm, lo + 4 * Cm), lane);
+      }
+    }
+  };
+  for (int k = 0; k < nk; ++k) {
+    const int tile0 = tile_of(k) * TILE, nEnv = envs_of(k);
+    const ImageStreams st = image_streams(p, tile0, nEnv);
+    uint8_t* gnf = nf8 ? nullptr : gnf_of(k);
+    // the state buffer of tile k is the one tile k-2 used: its owed ones (tiny tiles only) must be out first
+    if (pending && ring_k[0] <= k - 2) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+      __syncwarp();
+      for (int q = 0; q < pending; ++q) owed_ones(ring_k[q], ring_item[q], ring_fast[q]);
+      pending = 0;
+    }
+    named_barrier(2, FUSED_WR * 32);  // every writer warp is done with the staged tables of the previous tile
+    wait_tiles_done(tiles_done, (unsigned)k, lane, w == 0 ? 0 : -1);
+    int* sb = sbuf(k);
+    bool restage = false;
+    {  // stage the tile's post-step state (and its graph's tables when the graph changed)
+      const int gl = (lane < nEnv) ? __ldcg(p.st.graph_id + tile0 + lane) : -1;
+      const int g0 = __shfl_sync(FULL, gl, 0);
+      const bool one_graph = p.wr_stage_csr && __all_sync(FULL, gl == g0 || gl < 0);
+      for (int i = tw; i < nEnv * A; i += FUSED_WR * 32) {
+        sb[i] = __ldcg(p.st.pos + (size_t)tile0 * A + i);
+        sb[TILE * A + i] = __ldcg(p.st.money + (size_t)tile0 * A + i);
+      }
+      if (tw < nEnv) {
+        sb[2 * TILE * A + tw] = __ldcg(p.ob.mrx_revealed + tile0 + tw);
+        sb[2 * TILE * A + TILE + tw] = gl;
+      }
+      if (one_graph && g0 != last_g) {
+        restage = true;
+        const int32_t* grp = tb.row_ptr + (size_t)g0 * (N + 1);
+        const int nnz = __ldg(grp + N);
+        for (int i = tw; i <= N; i += FUSED_WR * 32) s_rp[i] = __ldg(grp + i);
+        for (int q = tw; q < nnz; q += FUSED_WR * 32) {
+          s_col[q] = __ldg(tb.col + (size_t)g0 * tb.nnz_stride + q);
+          s_wgt[q] = __ldg(tb.wgt + (size_t)g0 * tb.nnz_stride + q);
+        }
+      }
+      staged = one_graph;
+      last_g = one_graph ? g0 : -2;
+    }
+    named_barrier(2, FUSED_WR * 32);
+    if (restage && p.wr_epc) {  // packed neighbour table of the newly staged graph
+      for (int u = tw; u < N; u += FUSED_WR * 32) {
+        const int r0 = s_rp[u], deg = s_rp[u + 1] - r0;  // deg <= 255 (sy_load_graphs)
+        unsigned e4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) e4[q] = q < deg ? ((unsigned)s_col[r0 + q] | ((unsigned)s_wgt[r0 + q] << 16)) : 0u;
+        s_nbr4[u] = make_uint4(e4[0] | ((unsigned)deg << 24), e4[1], e4[2], e4[3]);
+      }
+      named_barrier(2, FUSED_WR * 32);
+    }
+    const int fast = (p.wr_epc && staged && st.ncf == 0) ? 1 : 0;
+    const int total = st.ncf + st.ncm;
+    // next tile's geometry, for the look-ahead fill of its first chunk
+    const bool have_next = !nf8 && k + 1 < nk;
+    const int Tm_next = have_next ? envs_of(k + 1) * (int)Sm : 0;
+    uint8_t* gnf_next = have_next ? gnf_of(k + 1) : nullptr;
+    for (int item = w; item < total; item += FUSED_WR, ++it) {
+      // ---- group F: zero fill for this warp's NEXT chunk (same tile, or the first chunk of the next tile)
+      long long tc = FCLK_NOW();
+      if (!nf8) {
+        if (item + FUSED_WR < total) {
+          if (k > 0) fill_piece(gnf, 4 * st.Tm, item + FUSED_WR);  // (tile 0 was filled by the prologue)
+        } else if (have_next && w < (Tm_next + Cm - 1) / Cm) {
+          fill_piece(gnf_next, 4 * Tm_next, w);
+        }
+      }
+      if (lane == 0) bulk_commit();
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(8, t1 - tc); tc = t1; }
+      // ---- group M: the chunk's image
+      uint8_t* img = my_img + (size_t)(it & 1) * p.wr_img_bytes;
+      if (it >= 2) {  // the engine has read the image's previous chunk (younger groups: F, M of the last chunk and this F)
+        const long long tw0 = FCLK_NOW();
+        if (lane == 0) bulk_wait_read<3>();
+        __syncwarp();
+        if (w == 0) FCLK_ADD(6, FCLK_NOW() - tw0);
+        // take that chunk's ones back out (it is the oldest entry of the ring: D == 2 chunks ago)
+        static_assert(D == 2, "the image ring and the owed-ones ring are the same two chunks");
+        if (pending == D && ring_fast[0]) {  // (after a tile-boundary flush the ring is short: clear the whole image)
+          int* ob = sbuf(ring_k[0]);
+          const PairView pv = pair_of(p, ob, ob + TILE * A, ring_item[0], p.wr_epc, envs_of(ring_k[0]), lane);
+          fast_mask_ones(p, pv, s_nbr4, s_rp, s_col, s_wgt, img, p.wr_epc, ring_item[0], 0);
+        } else {
+          for (int i = lane * 16; i < p.wr_img_bytes; i += 32 * 16) *reinterpret_cast<uint4*>(img + i) = make_uint4(0, 0, 0, 0);
+        }
+        __syncwarp();
+      }
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(9, t1 - tc); tc = t1; }
+      const bool is_nf8 = item < st.ncf;
+      const int lo = is_nf8 ? item * p.wr_c_nf : (item - st.ncf) * Cm;
+      const int len = is_nf8 ? min(p.wr_c_nf, st.Tf - lo) : min(Cm, st.Tm - lo);
+      if (fast) {
+        const PairView pv = pair_of(p, sb, sb + TILE * A, item, p.wr_epc, nEnv, lane);
+        fast_mask_ones(p, pv, s_nbr4, s_rp, s_col, s_wgt, img, p.wr_epc, item, 1);
+      } else {
+        generic_img(k, item, st, img, 1);
+      }
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(10, t1 - tc); tc = t1; }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(11, t1 - tc); tc = t1; }
+      uint8_t* dst = (is_nf8 ? st.gf : st.gm) + lo;
+      const int body = len & ~15;
+      if (lane == 0) {
+        if (body) bulk_store(dst, img, (unsigned)body);
+        bulk_commit();
+      }
+      if (lane < len - body) dst[body + lane] = img[body + lane];  // ragged end of the batch's last tile only
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(12, t1 - tc); tc = t1; }
+      // ---- ones of the chunk whose piece was filled D + 1 chunks ago (younger groups: its own M, then F + M of D + 1 chunks)
+      if (pending == D) {
+        const long long tw0 = FCLK_NOW();
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(2 * D + 3) : "memory");
+        __syncwarp();
+        if (w == 0) FCLK_ADD(7, FCLK_NOW() - tw0);
+        owed_ones(ring_k[0], ring_item[0], ring_fast[0]);
+#pragma unroll
+        for (int q = 0; q + 1 < D; ++q) {
+          ring_k[q] = ring_k[q + 1];
+          ring_item[q] = ring_item[q + 1];
+          ring_fast[q] = ring_fast[q + 1];
+        }
+        pending = D - 1;
+      }
+      if (w == 0) { const long long t1 = FCLK_NOW(); FCLK_ADD(13, t1 - tc); tc = t1; }
+      ring_k[pending] = k;
+      ring_item[pending] = item;
+      ring_fast[pending] = fast;
+      ++pending;
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");  // also: shared memory outlives the engine's reads
+  __syncwarp();
+  for (int q = 0; q < pending; ++q) owed_ones(ring_k[q], ring_item[q], ring_fast[q]);
+}
+
+template <int MODE, int MAXA, int BW>
+__global__ void __launch_bounds__((BW + FUSED_WR + LOGIC_WARPS) * 32, 2) sy_step_fused_kernel(const Params p) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ LogicSmem<MAXA> lsm;
+  __shared__ unsigned tiles_done;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) tiles_done = 0;
+  __syncthreads();
+  const int ntiles = (p.B + TILE - 1) / TILE;
+  if (warp < BW) {
+    if constexpr (BW > 0) {
+      if (!p.belief_on) return;
+      const long long t0 = FCLK_NOW();
+      for (int k = 0, t = blockIdx.x; t < ntiles; t += gridDim.x, ++k) {
+        if (k) named_barrier(1, BW * 32);  // every belief warp has left the previous tile's scratch
+        wait_tiles_done(&tiles_done, (unsigned)k, lane, warp == 0 ? 2 : -1);
+        belief_role<BW>(p, dyn, t * TILE, min(TILE, p.B - t * TILE), warp, lane);
+      }
+      if (warp == 0) FCLK_ADD(3, FCLK_NOW() - t0);
+    }
+  } else if (warp < BW + FUSED_WR) {
+    const long long t0 = FCLK_NOW();
+    fused_writer_role<BW>(p, dyn, &tiles_done, warp - BW, lane);
+    if (warp == BW) FCLK_ADD(1, FCLK_NOW() - t0);
+  } else {
+    const int tid = threadIdx.x - (BW + FUSED_WR) * 32;
+    unsigned k = 0;
+    const long long t0 = FCLK_NOW();
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      logic_tile<MODE, MAXA, 3>(p, lsm, t * TILE, tid);
+      __threadfence_block();
+      named_barrier(3, LOGIC_THREADS);  // every logic thread's stores of the tile are ordered; lsm may be reused
+      ++k;
+      if (tid == 0) publish_u32(&tiles_done, k);
+    }
+    if (tid == 0) {
+      FCLK_ADD(4, FCLK_NOW() - t0);
+      FCLK_ADD(5, 1);
+    }
+  }
+}
 
 // statistics: fold the replicated accumulators into the caller's vector and clear them
 __global__ void sy_fold_stats_kernel(unsigned long long* rep, long long* out) {
@@ -2049,6 +2542,19 @@ struct SyEnv {
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
   int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0;
   int wr_c_mask = 0, wr_c_nf32 = 0, wr_c_nf8 = 0, wr_img_bytes = 0;  // bulk writers: chunk sizes per stream, image size
+  // fused persistent step kernel (sy_step_fused_kernel): plan made with the graph tables
+  bool fused_ok = false;
+  int f_bw = 0, f_off_sbuf = 0, f_sbuf_stride = 0, f_off_zero = 0, f_off_imgs = 0, f_off_csr = 0, f_c_mask = 0, f_img_bytes = 0;
+  int f_stage_csr = 0, f_grid = 0, f_epc = 0, f_off_nbr4 = 0;
+  size_t f_smem = 0;
+  // sy_set_option(SY_OPT_STEP_KERNEL): SY_STEP_AUTO = the fused persistent kernel for batches that fit its grid in one
+  // wave (launch-latency bound: one launch instead of two, c2 runs 19 % faster), else the dynamics + observation kernels
+  // (at 65 536 envs the fused kernel is slower: DESIGN.md section 4c)
+  int opt_fused = SY_STEP_AUTO;
+  int opt_fill = 0;   // sy_set_option(SY_OPT_NF_FILL): 1 = split step (fill kernel next to the dynamics, belief next to the writers)
+  cudaStream_t split_stream = nullptr;  // split step: dynamics + belief run here, fill + writers on the caller's stream
+  cudaEvent_t ev_split_start = nullptr, ev_split_logic = nullptr, ev_split_belief = nullptr;
+  int fill_grid = 0;
   int opt_writer = SY_WRITER_LSU;  // sy_set_option(SY_OPT_WRITER_PATH) for the stand-alone observe kernel (sy_reset, two-kernel sy_step)
   int bel_warps = BEL_WARPS, wr_warps = WR_WARPS;  // role split of the observe kernel for this pool
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
@@ -2093,6 +2599,78 @@ int alloc_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_strid
   return SY_OK;
 }
 
+// chunk size (bytes, multiple of 16, <= cap) of a bulk-writer stream whose envs are S bytes each: whole groups of envs
+// when the smallest 16-byte sized group fits (leaving every writer warp a few chunks per tile), else a 16-byte
+// multiple that divides the group evenly when there is one in [cap / 2, cap], else just cap (chunks may then straddle
+// env boundaries, which the writers handle)
+int plan_bulk_chunk(size_t S, int cap, int wr_warps) {
+  size_t g = 16;
+  while (S % g) g >>= 1;  // gcd(S, 16)
+  const size_t m = 16 / g, group = S * m;
+  cap &= ~15;
+  if (group <= (size_t)cap) {
+    size_t k = cap / group;
+    const size_t kmax = std::max<size_t>(1, (TILE / m) / (2 * (size_t)wr_warps));
+    k = std::min(k, kmax);
+    return (int)(group * k);
+  }
+  for (int c = cap; c >= cap / 2 && c >= 16; c -= 16)
+    if (group % (size_t)c == 0) return c;
+  return cap;
+}
+
+using FusedFn = void (*)(const Params);
+template <int BW>
+FusedFn fused_fn_bw(int reward_mode, int A) {
+  const bool f64 = reward_mode == SY_REWARD_FP64;
+  if (A <= 4) return f64 ? sy_step_fused_kernel<SY_REWARD_FP64, 4, BW> : sy_step_fused_kernel<SY_REWARD_FP32, 4, BW>;
+  if (A <= 8) return f64 ? sy_step_fused_kernel<SY_REWARD_FP64, 8, BW> : sy_step_fused_kernel<SY_REWARD_FP32, 8, BW>;
+  return f64 ? sy_step_fused_kernel<SY_REWARD_FP64, 16, BW> : sy_step_fused_kernel<SY_REWARD_FP32, 16, BW>;
+}
+FusedFn fused_fn(int bw, int reward_mode, int A) { return bw ? fused_fn_bw<BEL_WARPS>(reward_mode, A) : fused_fn_bw<0>(reward_mode, A); }
+
+// shared-memory plan, grid and eligibility of the fused step kernel for this handle's shape (called with the tables)
+int plan_fused(SyEnv* e, int nnz_stride) {
+  const int N = e->cfg.num_nodes, A = e->A;
+  e->fused_ok = false;
+  if (e->cfg.belief && !e->bel_fast) return SY_OK;  // large-N belief path shares the writers' CSR: two-kernel path
+  e->f_bw = e->cfg.belief ? BEL_WARPS : 0;
+  auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+  const int cap = std::max(256, (int)(SY_BULK_IMG_BUDGET / (2 * FUSED_WR + 1)));
+  e->f_c_mask = plan_bulk_chunk((size_t)A * N, cap, FUSED_WR);
+  e->f_img_bytes = e->f_c_mask;
+  const size_t csr = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + 16;
+  e->f_stage_csr = csr <= 32 * 1024 ? 1 : 0;
+  e->f_sbuf_stride = (int)up16(((size_t)2 * TILE * A + 2 * TILE) * sizeof(int));
+  e->f_off_sbuf = (int)up16(e->cfg.belief ? e->bel_smem : 0);
+  e->f_off_zero = e->f_off_sbuf + 2 * e->f_sbuf_stride;
+  e->f_off_imgs = e->f_off_zero + e->f_img_bytes;
+  e->f_off_csr = (int)up16((size_t)e->f_off_imgs + (size_t)2 * FUSED_WR * e->f_img_bytes);
+  // fast geometry: a chunk is whole envs with at most 32 (env, agent) pairs, rows are whole granules, and the staged
+  // graph gets a packed neighbour table (one uint4 per node)
+  const size_t S = (size_t)A * N;
+  e->f_epc = (e->f_stage_csr && e->f_c_mask % S == 0 && (e->f_c_mask / S) * A <= 32 && S % 4 == 0 && N <= 2048) ? (int)(e->f_c_mask / S) : 0;
+  e->f_off_nbr4 = (int)up16((size_t)e->f_off_csr + (e->f_stage_csr ? csr : 0));
+  e->f_smem = (size_t)e->f_off_nbr4 + (e->f_epc ? (size_t)N * 16 : 0);
+  if (e->f_smem > 200 * 1024) return SY_OK;
+  FusedFn fn = fused_fn(e->f_bw, e->cfg.reward_mode, A);
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    cudaGetLastError();
+    return SY_OK;
+  }
+  int per_sm = 0, sms = 0;
+  const int threads = (e->f_bw + FUSED_WR + LOGIC_WARPS) * 32;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, e->f_smem) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    return SY_OK;
+  }
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+  const int ntiles = (e->cfg.num_envs + TILE - 1) / TILE;
+  e->f_grid = std::min(ntiles, per_sm * sms);
+  e->fused_ok = true;
+  return SY_OK;
+}
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the FUNCTION (per device), not to a handle: it is only ever
 // raised, so a small env created next to a large one cannot pull the limit below what the large one launches with
 int raise_observe_smem_limit(int device, size_t bytes) {
@@ -2103,6 +2681,8 @@ int raise_observe_smem_limit(int device, size_t bytes) {
   if (bytes <= cur) return SY_OK;
   CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<0, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   cur = bytes;
   return SY_OK;
 }
@@ -2118,7 +2698,13 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   const SyConfig& c = env->cfg;
   if (!env->graphs_loaded) return fail(SY_ERR_STATE, "sy_load_graphs must be called first");
   if (!env->tables_set) return fail(SY_ERR_STATE, "sy_set_reward_tables must be called first");
-  if (!st || !st->pos || !st->money || !st->timestep || !st->graph_id || !st->episode || !st->done || !st->visits)
+  // ABI guard of the pointer structs: a binding compiled against another header revision is refused before any of its
+  // (mis-laid-out) pointers can reach a kernel
+  if (!st) return fail(SY_ERR_INVALID_ARGUMENT, "SyState is NULL");
+  if (st->struct_bytes != sizeof(SyState)) return fail(SY_ERR_INVALID_ARGUMENT, "SyState size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)st->struct_bytes, sizeof(SyState), SY_ABI_VERSION);
+  if (ob && ob->struct_bytes != sizeof(SyObs)) return fail(SY_ERR_INVALID_ARGUMENT, "SyObs size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)ob->struct_bytes, sizeof(SyObs), SY_ABI_VERSION);
+  if (out && out->struct_bytes != sizeof(SyOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyOut size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)out->struct_bytes, sizeof(SyOut), SY_ABI_VERSION);
+  if (!st->pos || !st->money || !st->timestep || !st->graph_id || !st->episode || !st->done || !st->visits)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyState has NULL members");
   if (c.belief && !st->belief) return fail(SY_ERR_INVALID_ARGUMENT, "SyState.belief is NULL but config.belief is on");
   std::memset(&p, 0, sizeof(p));
@@ -2138,6 +2724,8 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.resample_graph = c.resample_graph;
   p.reward_mode = c.reward_mode;
   p.env_offset = (unsigned long long)c.env_offset;
+  p.reveal_skip_thresh = c.reveal_skip_prob > 0.0f ? (unsigned long long)((double)fminf(c.reveal_skip_prob, 1.0f) * 4294967296.0) : 0ull;
+  p.belief_hint = st->belief_hint;
   p.seed_lo = (unsigned)(c.seed & 0xffffffffu);
   p.seed_hi = (unsigned)(c.seed >> 32);
   for (int i = 0; i < SY_NUM_REWARD_WEIGHTS; ++i) {
@@ -2176,27 +2764,10 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   return SY_OK;
 }
 
-// chunk size (bytes, multiple of 16, <= cap) of a bulk-writer stream whose envs are S bytes each: whole groups of envs
-// when the smallest 16-byte sized group fits (leaving every writer warp a few chunks per tile), else a 16-byte
-// multiple that divides the group evenly when there is one in [cap / 2, cap], else just cap (chunks may then straddle
-// env boundaries, which the writers handle)
-int plan_bulk_chunk(size_t S, int cap, int wr_warps) {
-  size_t g = 16;
-  while (S % g) g >>= 1;  // gcd(S, 16)
-  const size_t m = 16 / g, group = S * m;
-  cap &= ~15;
-  if (group <= (size_t)cap) {
-    size_t k = cap / group;
-    const size_t kmax = std::max<size_t>(1, (TILE / m) / (2 * (size_t)wr_warps));
-    k = std::min(k, kmax);
-    return (int)(group * k);
-  }
-  for (int c = cap; c >= cap / 2 && c >= 16; c -= 16)
-    if (group % (size_t)c == 0) return c;
-  return cap;
-}
+
 
 int check_obs(const SyObs* ob) {
+  if (ob && ob->struct_bytes != sizeof(SyObs)) return fail(SY_ERR_INVALID_ARGUMENT, "SyObs size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)ob->struct_bytes, sizeof(SyObs), SY_ABI_VERSION);
   if (!ob || !ob->action_mask || (!ob->node_features && !ob->node_features_u8) || !ob->agent_budget || !ob->mrx_revealed)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyObs has NULL members");
   return SY_OK;
@@ -2217,6 +2788,17 @@ int sy_debug_phase_clocks(unsigned long long* out8, int reset) {  // profiling b
   return 0;
 }
 #endif
+#ifdef SY_FUSED_CLOCKS
+int sy_debug_fused_clocks(unsigned long long* out16, int reset) {  // profiling builds only, not declared in sy_env.h
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, g_fused_clk, sizeof(unsigned long long) * 16);
+  if (reset) {
+    unsigned long long z[16] = {};
+    cudaMemcpyToSymbol(g_fused_clk, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 int sy_abi_version(void) { return SY_ABI_VERSION; }
 const char* sy_last_error(void) { return g_err.c_str(); }
 int64_t sy_launch_count(void) { return (int64_t)g_launches.load(); }
@@ -2233,6 +2815,7 @@ int sy_create(const SyConfig* c, SyEnv** out_env) {
     return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes must be in [num_police + 1, 65534]");  // nodes are staged as u16
   if (c->agent_money < 0 || c->mrx_money < 0 || c->toll < 0 || c->reveal_interval < 0 || c->max_timestep < 0)
     return fail(SY_ERR_INVALID_ARGUMENT, "negative money / toll / reveal_interval / max_timestep");
+  if (!(c->reveal_skip_prob >= 0.0f && c->reveal_skip_prob <= 1.0f)) return fail(SY_ERR_INVALID_ARGUMENT, "reveal_skip_prob must be in [0, 1]");
   if (c->reward_mode != SY_REWARD_FP64 && c->reward_mode != SY_REWARD_FP32)
     return fail(SY_ERR_INVALID_ARGUMENT, "unknown reward_mode %d", c->reward_mode);
   int ndev = 0;
@@ -2267,6 +2850,9 @@ void sy_destroy(SyEnv* e) {
   if (e->d_bel_flags) cudaFree(e->d_bel_flags);
   if (e->d_stats_rep) cudaFree(e->d_stats_rep);
   if (e->aux_stream) cudaStreamDestroy(e->aux_stream);
+  if (e->split_stream) cudaStreamDestroy(e->split_stream);
+  for (cudaEvent_t ev : {e->ev_split_start, e->ev_split_logic, e->ev_split_belief})
+    if (ev) cudaEventDestroy(ev);
   if (e->ev_main) cudaEventDestroy(e->ev_main);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -2278,6 +2864,15 @@ void sy_destroy(SyEnv* e) {
 int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
   if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
   switch (option) {
+    case SY_OPT_STEP_KERNEL:
+      if (value != SY_STEP_FUSED && value != SY_STEP_TWO_KERNELS && value != SY_STEP_AUTO)
+        return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_STEP_KERNEL: 0 (fused), 1 (two kernels) or 2 (auto)");
+      e->opt_fused = value;
+      return SY_OK;
+    case SY_OPT_NF_FILL:
+      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_NF_FILL: 0 or 1");
+      e->opt_fill = value;
+      return SY_OK;
     case SY_OPT_WRITER_PATH:
       if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
       e->opt_writer = value;
@@ -2463,6 +3058,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   e->tb.Ns = Ns;
   e->tb.nnz_stride = nnz_stride;
   e->tb.wcap = wcap;
+  if (int rc = plan_fused(e, nnz_stride)) return rc;
   e->graphs_loaded = true;
   return SY_OK;
 }
@@ -2616,12 +3212,24 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
 
 namespace {
 // after_logic (optional): recorded between the two kernels -- rewards / flags are final once the logic kernel is done
+bool fused_eligible(const SyEnv* e, const SyObs* ob) {
+  if (!e->fused_ok || e->opt_fused == SY_STEP_TWO_KERNELS || !ob) return false;
+  if (e->opt_fused == SY_STEP_AUTO && (e->cfg.num_envs + TILE - 1) / TILE > e->f_grid) return false;  // more than one wave of tiles
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(ob->action_mask) | reinterpret_cast<uintptr_t>(ob->node_features_u8 ? (void*)ob->node_features_u8 : (void*)ob->node_features);
+  return (bits & 15u) == 0;  // bulk stores need 16-byte aligned streams
+}
+
+// next_actions (+ counter): a fused launch also draws the next step's random actions; *fused_sampled reports whether it did
 int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
-              sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr) {
+              sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr,
+              int64_t* next_actions = nullptr, uint32_t next_counter = 0, const uint32_t* next_counter_base = nullptr,
+              bool* fused_sampled = nullptr) {
   if (!e || (!actions && !actions32 && !actions16)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   if (actions16 && e->cfg.num_nodes > 32767) return fail(SY_ERR_INVALID_ARGUMENT, "int16 actions need num_nodes <= 32767");
   e->aux_after_logic = false;
-  if (!out || !out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
+  if (!out) return fail(SY_ERR_INVALID_ARGUMENT, "SyOut is NULL");
+  if (out->struct_bytes != sizeof(SyOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyOut size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)out->struct_bytes, sizeof(SyOut), SY_ABI_VERSION);
+  if (!out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
     return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
   Params p;
   int rc = fill_params(e, st, ob, out, p);
@@ -2644,20 +3252,89 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   // overlap gains.
   // Also measured: an L2 persisting access-policy window on the belief map (52 MB at c3) slowed the step to 166-255 us
   // (the carve-out starves the write stream of L2), so no residency hints are set.
+  if (fused_eligible(e, ob) && !p.dbg_skip) {
+    // ONE persistent launch: dynamics, belief and the bulk-store observation stream of all tiles, software-pipelined
+    p.next_actions = reinterpret_cast<long long*>(next_actions);
+    p.next_counter = next_counter;
+    p.next_counter_base = next_counter_base;
+    p.bel_share_csr = 0;
+    p.wr_bulk = 1;
+    p.wr_c_mask = p.wr_c_nf = e->f_c_mask;
+    p.wr_img_bytes = e->f_img_bytes;
+    p.wr_stage_csr = e->f_stage_csr;
+    p.wr_off_csr = e->f_off_csr;
+    p.f_off_sbuf = e->f_off_sbuf;
+    p.f_sbuf_stride = e->f_sbuf_stride;
+    p.f_off_zero = e->f_off_zero;
+    p.f_off_imgs = e->f_off_imgs;
+    p.f_off_nbr4 = e->f_off_nbr4;
+    p.wr_epc = e->f_epc;
+    const int threads = (e->f_bw + FUSED_WR + LOGIC_WARPS) * 32;
+    fused_fn(e->f_bw, e->cfg.reward_mode, p.A)<<<(unsigned)e->f_grid, threads, e->f_smem, s>>>(p);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
+    if (fused_sampled) *fused_sampled = true;
+    return SY_OK;
+  }
+  // Split step: the state-independent zero fill of float32 node_features (63 % of the bytes) goes to the TMA engine in
+  // its own tiny kernel on the caller's stream while the dynamics kernel runs on the handle's split stream; afterwards
+  // the belief propagation (split stream) and the writers of the ones (caller's stream) run next to each other.  Both
+  // join on the caller's stream before step_impl returns (events; capturable in a CUDA graph as a DAG).
+  const bool split = e->opt_fill && !ob->node_features_u8 && !p.wr_bulk && (reinterpret_cast<uintptr_t>(ob->node_features) & 15u) == 0 &&
+                     !p.dbg_skip && !e->bel_share_csr && e->cfg.num_envs >= SPLIT_MIN_ENVS;
+  cudaStream_t ls = s;  // stream of the dynamics kernel
+  if (split) {
+    if (!e->split_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&e->split_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_split_start, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_split_logic, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&e->ev_split_belief, cudaEventDisableTiming));
+      int sms = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device));
+      e->fill_grid = sms;
+    }
+    CUDA_TRY(cudaEventRecord(e->ev_split_start, s));
+    CUDA_TRY(cudaStreamWaitEvent(e->split_stream, e->ev_split_start, 0));
+    sy_fill_kernel<<<(unsigned)e->fill_grid, FILL_THREADS, 0, s>>>(reinterpret_cast<uint8_t*>(ob->node_features),
+                                                                  (size_t)p.B * p.N * p.A * sizeof(float));
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    p.nf_prefilled = 1;
+    ls = e->split_stream;
+  }
   if (p.dbg_skip & 32) {
   } else if (p.A <= 4) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
   } else if (p.A <= 8) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, s>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
   } else {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, s>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, s>>>(p);
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
   }
   g_launches++;
   CUDA_TRY(cudaGetLastError());
-  if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
+  if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, ls));
+  if (split) {
+    CUDA_TRY(cudaEventRecord(e->ev_split_logic, ls));
+    if (p.belief_on) {  // belief propagation: one role per launch, next to the writers
+      sy_observe_kernel<BEL_WARPS, 0><<<grid, BEL_WARPS * 32, e->bel_smem, ls>>>(p);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaEventRecord(e->ev_split_belief, ls));
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s, e->ev_split_logic, 0));
+    Params pw = p;  // writers only: their staging area starts at the beginning of the dynamic shared memory
+    pw.wr_off = 0;
+    pw.wr_off_csr = e->wr_off_csr - e->wr_off;
+    sy_observe_kernel<0, WR_WARPS><<<grid, WR_WARPS * 32, e->obs_smem - (size_t)e->wr_off, s>>>(pw);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (p.belief_on) CUDA_TRY(cudaStreamWaitEvent(s, e->ev_split_belief, 0));
+    return SY_OK;
+  }
   if (!(p.dbg_skip & 16)) launch_observe(e, p, grid, s);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -2729,6 +3406,7 @@ int sy_step_i32(SyEnv* e, const int32_t* actions, const SyState* st, const SyObs
 int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, const SyState* st, const SyObs* ob,
                  const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
   if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  if (ho->struct_bytes != sizeof(SyHostOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyHostOut size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)ho->struct_bytes, sizeof(SyHostOut), SY_ABI_VERSION);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)e->cfg.num_envs * e->A;
@@ -2741,6 +3419,7 @@ int sy_step_host(SyEnv* e, const int64_t* actions_host, int64_t* actions_dev, co
 int sy_step_host_i32(SyEnv* e, const int32_t* actions_host, int32_t* actions_dev, const SyState* st, const SyObs* ob,
                      const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
   if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  if (ho->struct_bytes != sizeof(SyHostOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyHostOut size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)ho->struct_bytes, sizeof(SyHostOut), SY_ABI_VERSION);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)e->cfg.num_envs * e->A;
@@ -2757,6 +3436,7 @@ int sy_step_i16(SyEnv* e, const int16_t* actions, const SyState* st, const SyObs
 int sy_step_host_i16(SyEnv* e, const int16_t* actions_host, int16_t* actions_dev, const SyState* st, const SyObs* ob,
                      const SyOut* out, const SyHostOut* ho, sy_stream_t stream) {
   if (!e || !actions_host || !actions_dev || !ho) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / host_out");
+  if (ho->struct_bytes != sizeof(SyHostOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyHostOut size mismatch: got %llu, library expects %zu (ABI %d)", (unsigned long long)ho->struct_bytes, sizeof(SyHostOut), SY_ABI_VERSION);
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)e->cfg.num_envs * e->A;
@@ -2825,10 +3505,16 @@ int sy_stats(SyEnv* e, int64_t* stats, sy_stream_t stream) {
 int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,
                       const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions or negative num_steps");
+  bool have_actions = false;  // the fused step kernel draws the next step's actions itself
   for (int32_t k = 0; k < num_steps; ++k) {
-    int rc = sy_sample_actions(e, st, step_counter0 + (uint32_t)k, actions, stream);
-    if (rc) return rc;
-    if ((rc = sy_step(e, actions, st, ob, out, stream))) return rc;
+    int rc;
+    if (!have_actions && (rc = sy_sample_actions(e, st, step_counter0 + (uint32_t)k, actions, stream))) return rc;
+    have_actions = false;
+    const bool more = k + 1 < num_steps;
+    if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, more ? actions : nullptr,
+                        step_counter0 + (uint32_t)k + 1u, nullptr, &have_actions)))
+      return rc;
+    have_actions = have_actions && more;
   }
   return SY_OK;
 }
@@ -2836,23 +3522,32 @@ int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64
 int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_dev, int64_t* actions, const SyState* st,
                           const SyObs* ob, const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || !step_counter_dev || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / counter or negative num_steps");
-  // The sampler of step k + 1 only needs the state the dynamics of step k wrote, not its observations: it is forked
-  // onto the library stream right behind the logic kernel (fork / join with events, capturable), so it runs next to
-  // the observation kernel of step k instead of after it.
   cudaStream_t s = (cudaStream_t)stream;
-  if (!e->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-  if (!e->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
   int rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
   if (rc) return rc;
-  for (int32_t k = 0; k < num_steps; ++k) {
-    const bool more = k + 1 < num_steps;
-    if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, more ? e->ev_fork : nullptr))) return rc;
-    if (more) {
-      CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
-      if ((rc = sample_impl<long long>(e, st, (uint32_t)(k + 1), reinterpret_cast<long long*>(actions), (sy_stream_t)e->aux_stream, step_counter_dev)))
+  if (fused_eligible(e, ob)) {
+    // one launch per step: the fused kernel's logic warps draw the next step's actions from the new state
+    for (int32_t k = 0; k < num_steps; ++k) {
+      const bool more = k + 1 < num_steps;
+      if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, more ? actions : nullptr, (uint32_t)(k + 1), step_counter_dev)))
         return rc;
-      CUDA_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
-      CUDA_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+    }
+  } else {
+    // The sampler of step k + 1 only needs the state the dynamics of step k wrote, not its observations: it is forked
+    // onto the library stream right behind the logic kernel (fork / join with events, capturable), so it runs next to
+    // the observation kernel of step k instead of after it.
+    if (!e->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    if (!e->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+    for (int32_t k = 0; k < num_steps; ++k) {
+      const bool more = k + 1 < num_steps;
+      if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, more ? e->ev_fork : nullptr))) return rc;
+      if (more) {
+        CUDA_TRY(cudaStreamWaitEvent(e->aux_stream, e->ev_fork, 0));
+        if ((rc = sample_impl<long long>(e, st, (uint32_t)(k + 1), reinterpret_cast<long long*>(actions), (sy_stream_t)e->aux_stream, step_counter_dev)))
+          return rc;
+        CUDA_TRY(cudaEventRecord(e->ev_join, e->aux_stream));
+        CUDA_TRY(cudaStreamWaitEvent(s, e->ev_join, 0));
+      }
     }
   }
   sy_advance_counter_kernel<<<1, 1, 0, s>>>(step_counter_dev, (unsigned)num_steps);

@@ -70,7 +70,7 @@ class BatchedScotlandYardEnv:
                  auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
                  device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True,
                  graph_offset: int = 0, max_edges_per_node: int = 4, max_weight: int = 5,
-                 node_features_dtype: torch.dtype = torch.float32):
+                 node_features_dtype: torch.dtype = torch.float32, reveal_skip_prob: float = 0.0):
         if not torch.cuda.is_available():
             raise _cabi.SyError("BatchedScotlandYardEnv needs a CUDA device; there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -129,6 +129,9 @@ class BatchedScotlandYardEnv:
         cfg.reward_mode = _cabi.SY_REWARD_FP32 if reward_mode == "fp32" else _cabi.SY_REWARD_FP64
         cfg.auto_reset, cfg.resample_graph = int(bool(auto_reset)), int(bool(resample_graph))
         cfg.env_offset, cfg.seed = int(env_offset), int(seed) & 0xFFFFFFFFFFFFFFFF
+        # robustness hook of src/eval/ood_eval.py:191-234 (RobustnessWrapper.reveal_skip_prob; `reveal_probability` of
+        # src/configs/ablation/belief.yaml is 1 - this): every scheduled reveal is skipped with this probability
+        cfg.reveal_skip_prob = float(reveal_skip_prob)
         for i, v in enumerate(wvals):
             cfg.reward_weights[i] = v
         self.config = cfg
@@ -222,14 +225,32 @@ class BatchedScotlandYardEnv:
             raise ValueError(f"expected shape {tuple(shape)}, got {tuple(t.shape)}")
         return t
 
-    OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1})}  # include/sy_env.h SY_OPT_*
+    OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1}), "step_kernel": (1, {"fused": 0, "two_kernels": 1, "auto": 2}),
+               "nf_fill": (2, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
 
     def set_option(self, name: str, value):
-        """Tuning knobs of the handle (results are identical for every setting): `writer_path` = "bulk" (TMA bulk
-        stores from shared-memory images, the default) | "lsu" (16-byte streaming stores)."""
+        """Tuning knobs of the handle (results are identical for every setting; include/sy_env.h SY_OPT_*):
+        `step_kernel` = "auto" (default: the fused persistent kernel for batches of up to ~9 500 envs, else two kernels)
+        | "fused" | "two_kernels"; `writer_path` of the two-kernel path's observation kernel = "lsu" (default) | "bulk"
+        (TMA bulk stores); `nf_fill` = "off" (default) | "on" (split step: TMA fill kernel next to the dynamics)."""
         opt, values = self.OPTIONS[name]
         _cabi.check(self._lib.sy_set_option(self._handle, opt, values[value] if isinstance(value, str) else int(value)))
         self.options = dict(getattr(self, "options", {}), **{name: value})
+
+    def set_belief_hint(self, hint: Optional[torch.Tensor]):
+        """Observation hint of ParticleBeliefTracker.update (belief_module.py:102-106) for the following steps: uint8 /
+        bool [B, N] on the device, non-zero = candidate node; after the propagation the belief of node j is multiplied by
+        0.1 + 0.9 * hint[j] and renormalised (an all-zero row leaves the env's belief as it is).  None switches it off."""
+        if hint is not None:
+            if not self.belief_on:
+                raise _cabi.SyError("belief hints need belief=True")
+            hint = hint.to(device=self.device).contiguous()
+            if hint.dtype == torch.bool:
+                hint = hint.view(torch.uint8)
+            if hint.dtype != torch.uint8 or tuple(hint.shape) != (self.num_envs, self.graph_nodes):
+                raise ValueError(f"hint must be uint8/bool [{self.num_envs}, {self.graph_nodes}]")
+        self._belief_hint = hint  # keeps the buffer alive
+        self._state.belief_hint = _ptr(hint)
 
     def set_seed(self, seed: int):
         self.seed = int(seed)

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     lib.sy_abi_version.restype = ctypes.c_int
     assert lib.sy_abi_version() == _cabi.SY_ABI_VERSION
-    assert ctypes.sizeof(_cabi.SyConfig) == 160
+    assert ctypes.sizeof(_cabi.SyConfig) == 168  # ABI 4: + reveal_skip_prob, reserved0
 
 
 def test_policy_header_and_library_agree():
@@ -75,3 +75,35 @@ def test_product_never_imports_oracle():
                 assert not pat_py.search(open(src_path).read()), f
             elif f.endswith((".cu", ".h", ".cuh", ".cpp")):
                 assert not pat_c.search(open(src_path).read()), f
+
+
+def _header_struct_fields(name):
+    """member names of `typedef struct <name> { ... } <name>;` in include/sy_env.h, in order"""
+    import re
+
+    text = open(os.path.join(ROOT, "include", "sy_env.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    return [re.search(r"(\w+)(\[[^\]]*\])?\s*$", stmt.strip()).group(1) for stmt in body.split(";") if stmt.strip()]
+
+
+def test_struct_layouts_of_binding_and_integration_doc_match_the_header():
+    """the ctypes structs of _cabi.py AND the `_fields_` lists a maintainer would copy from INTEGRATION.md section 3 name
+    exactly the header's members, in order (round-1 finding: the document was two ABI revisions behind, so a binding
+    written from it made sy_step read pointers past the caller's structs)"""
+    import re
+
+    from student_mechanism_design_b200 import _cabi
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert "SY_ABI_VERSION" in doc and f"sy_abi_version() == {_cabi.SY_ABI_VERSION}" in doc
+    for name in ("SyConfig", "SyState", "SyObs", "SyOut", "SyHostOut"):
+        want = _header_struct_fields(name)
+        assert [f[0] for f in getattr(_cabi, name)._fields_] == want, name
+        stmt = re.search(r"class %s\(C\.Structure\):(.*?)(?=\nclass |\n# |\nhandle|\nP = )" % name, doc, re.S).group(1)
+        assert re.findall(r'"(\w+)"', stmt) == want, (name, "INTEGRATION.md")
+    # sizes: 8 bytes of struct_bytes + one pointer per member
+    for name in ("SyState", "SyObs", "SyOut", "SyHostOut"):
+        import ctypes as C
+
+        assert C.sizeof(getattr(_cabi, name)) == 8 * len(getattr(_cabi, name)._fields_)

@@ -40,8 +40,14 @@ def _pair(N, E, P, money, B, seed, *, toll, belief, reveal, graphs=1, writer=Non
     pool = pkg.generate_graph_pool(graphs, N, E, seed=0)
     env = pkg.BatchedScotlandYardEnv(B, P, money, graphs=pool, seed=seed, auto_reset=True, tolls=toll, belief=belief,
                                      reveal_interval=reveal, keep_reward64=True, **env_kw)
+    # "fused": one persistent kernel | two kernels with: "lsu" = all observation stores through the LSU (the default for
+    # large batches) | "bulk" = chunk images + bulk stores in the observation kernel | "split" = TMA fill kernel next to
+    # the dynamics kernel, then belief and writers as two concurrent kernels
     if writer is not None:
-        env.set_option("writer_path", writer)
+        env.set_option("step_kernel", "fused" if writer == "fused" else "two_kernels")
+        if writer != "fused":
+            env.set_option("writer_path", "bulk" if writer == "bulk" else "lsu")
+            env.set_option("nf_fill", "on" if writer == "split" else "off")
     cfg = so.OracleConfig(num_police=P, agent_money=money, toll=toll, belief=belief, reveal_interval=reveal)
     # the env's default graph assignment: blocks of 32 consecutive envs share a graph
     gid = (np.arange(B) // 32) % graphs
@@ -100,26 +106,28 @@ def _rollout_against_oracle(env, ob, steps, belief, dense_every=1):
     return done
 
 
-@pytest.mark.parametrize("writer", ["bulk", "lsu"])
+@pytest.mark.parametrize("writer", ["lsu", "fused", "bulk", "split"])
 def test_config3_full_size_matches_oracle(torch_cuda, writer):
     """BASELINE config 3 exactly as benchmarked: 200 nodes / 400 edges / 6 police, budget 20, toll 1, belief on,
-    reveal every 5, 65 536 envs, same-step auto-reset, 25 steps -- every tile of the 2 048-tile grid, both waves of the
-    logic kernel and all statistics replicas, with both writer paths (TMA bulk stores and LSU stores)."""
+    reveal every 5, 65 536 envs, same-step auto-reset, 25 steps -- every tile of the 2 048-tile grid and all statistics
+    replicas, through the fused persistent step kernel and through the two-kernel path with both writer paths (TMA bulk
+    stores and LSU stores)."""
     env, ob = _pair(200, 400, 6, 20, 65536, 1, toll=1, belief=True, reveal=5, writer=writer)
     done = _rollout_against_oracle(env, ob, 25, True, dense_every=3)
     assert done > 1000  # captures / out-of-money endings + same-step auto-resets happened at scale
     env.close()
 
 
-def test_config2_full_size_matches_oracle(torch_cuda):
+@pytest.mark.parametrize("writer", ["fused", "lsu"])
+def test_config2_full_size_matches_oracle(torch_cuda, writer):
     """BASELINE config 2: 50 nodes, 3 police, reveal every 5, 1024 envs, 60 steps (reveals and all endings occur)."""
-    env, ob = _pair(50, 110, 3, 10, 1024, 2, toll=0, belief=False, reveal=5)
+    env, ob = _pair(50, 110, 3, 10, 1024, 2, toll=0, belief=False, reveal=5, writer=writer)
     done = _rollout_against_oracle(env, ob, 60, False)
     assert done > 100
     env.close()
 
 
-@pytest.mark.parametrize("writer", ["bulk", "lsu"])
+@pytest.mark.parametrize("writer", ["lsu", "bulk"])
 def test_config4_full_size_matches_oracle(torch_cuda, writer):
     """BASELINE config 4's per-GPU shard: 1000 nodes / 2000 edges / 6 police, 32 768 envs, 10 steps (large-N belief path,
     staged-CSR writers, chunks that cut through envs on the bulk path)."""
@@ -136,13 +144,15 @@ def test_config3_ragged_batch_graph_pool(torch_cuda):
     env.close()
 
 
-def test_timed_path_graph_replay_matches_oracle(torch_cuda):
-    """The path bench.py times -- capture_rollout (sy_rollout_random_dev: device-resident step counter, the sampler of
-    step k+1 forked next to the observation kernel of step k) replayed from a CUDA graph -- against the oracle after
-    K replays, at c3 with a ragged 65 523-env batch."""
+@pytest.mark.parametrize("writer", ["lsu", "fused", "split"])
+def test_timed_path_graph_replay_matches_oracle(torch_cuda, writer):
+    """The path bench.py times -- capture_rollout (sy_rollout_random_dev: device-resident step counter; fused: one
+    persistent kernel per step whose logic warps also draw the next step's actions; two kernels: the sampler of step
+    k+1 forked next to the observation kernel of step k) replayed from a CUDA graph -- against the oracle after K
+    replays, at c3 with a ragged 65 523-env batch."""
     torch = torch_cuda
     B, seg, replays = 65536 - 13, 5, 6
-    env, ob = _pair(200, 400, 6, 20, B, 7, toll=1, belief=True, reveal=5)
+    env, ob = _pair(200, 400, 6, 20, B, 7, toll=1, belief=True, reveal=5, writer=writer)
     env.reset()
     graph, counter = env.capture_rollout(seg)  # runs `seg` steps as warm-up, then captures
     for _ in range(replays):

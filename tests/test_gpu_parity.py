@@ -510,9 +510,16 @@ def test_torchrl_adapter_on_device(torch_cuda, tables):
     pkg = _pkg()
     c = dict(N=20, E=34, P=2, money=8, G=2, B=40, kw=dict(belief=True, reveal_interval=2), mode="fp64")
     env, ob = _make_pair(pkg, c, tables, auto_reset=False)
-    tenv = torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict)(env)
+    tenv = torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict, fake_torchrl.SPECS)(env)
+    # the declared specs against what a real device env emits (stand-in for torchrl's check_env_specs): every key,
+    # shape, dtype and bound, on reset and on random steps drawn from the action spec
+    probe, _ = _make_pair(pkg, c, tables, auto_reset=False)
+    assert fake_torchrl.check_env_specs(torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict, fake_torchrl.SPECS)(probe))
+    probe.close()
     td = tenv.reset()
     assert td.get(("agents", "observation", "action_mask")).data_ptr() == env.action_mask.data_ptr()
+    hidden = (env.mrx_revealed < 0)
+    assert bool((td.get(("Police0", "observation", "MrX_pos"))[:, 0][hidden] == -1).all())  # no leak while MrX is hidden
     assert np.array_equal(td.get(("MrX", "observation", "agent_position"))[:, 0].cpu().numpy(), ob.pos()[:, 0])
     for s in range(15):
         acts = ob.sample_actions(s)
@@ -999,3 +1006,83 @@ def test_uint8_node_features_option(torch_cuda, tables):
                 assert getattr(a, k).cpu().numpy().tobytes() == getattr(b, k).cpu().numpy().tobytes(), (k, s)
         a.close()
         b.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("step_kernel", ["two_kernels", "fused"])
+@pytest.mark.parametrize("mixed_graphs", [False, True])
+def test_belief_hint_and_reveal_skip_match_oracle(torch_cuda, tables, step_kernel, mixed_graphs):
+    """The two remaining parts of the belief definition: the observation-hint re-weighting of
+    ParticleBeliefTracker.update (belief_module.py:102-106: likelihood 0.1 + 0.9 * [j in hint], then normalise) and the
+    reveal-skip robustness hook (ood_eval.py:227-229: a scheduled reveal is skipped with probability p).  Device fp32 vs
+    the float64 oracle within 1e-6; the skip decisions (one Philox draw per env and reveal step) bit-exact.  Mixed graphs
+    per tile take the generic belief path, a single graph per tile the lane = env fast path."""
+    torch = torch_cuda
+    pkg = _pkg()
+    N, E, P, B, G = 30, 55, 3, 96, (3 if mixed_graphs else 1)
+    pool = pkg.generate_graph_pool(G, N, E, seed=3)
+    kw = dict(reveal_interval=3, tolls=1, belief=True)
+    env = pkg.BatchedScotlandYardEnv(B, P, 10, graphs=pool, seed=23, auto_reset=True, keep_reward64=True, reward_tables=tables,
+                                     resample_graph=mixed_graphs, reveal_skip_prob=0.4, **kw)
+    env.set_option("step_kernel", step_kernel)
+    cfg = so.OracleConfig(num_police=P, agent_money=10, reveal_interval=3, toll=1, belief=True, reveal_skip_prob=0.4,
+                          exp_table=tables[0], cov_table=tables[1])
+    ob = so.OracleBatch.from_seed(cfg, [so.Graph(g.num_nodes, g.edge_links, g.edges) for g in pool], B, seed=23, auto_reset=True,
+                                  resample_graph=mixed_graphs)
+    env.reset()
+    rng = np.random.default_rng(4)
+    skipped = revealed = 0
+    for s in range(24):
+        hints = rng.random((B, N)) < 0.15
+        hints[::5] = False  # envs without any candidate: no re-weighting (`if observation_hint:` is False)
+        use_hint = s % 3 != 2
+        env.set_belief_hint(torch.from_numpy(hints).cuda() if use_hint else None)
+        acts = env.sample_actions(step_counter=s)
+        env.step(acts)
+        want = ob.step(acts.cpu().numpy(), hints=hints if use_hint else None)
+        assert env.reward64.cpu().numpy().tobytes() == want["reward"].tobytes(), s
+        assert np.array_equal(env.pos.cpu().numpy(), ob.pos()) and np.array_equal(env.timestep.cpu().numpy(), ob.timestep())
+        assert np.array_equal(env.mrx_revealed.cpu().numpy(), ob.revealed()), ("reveal / skip decisions", s)
+        assert np.array_equal(env.node_features.cpu().numpy(), ob.node_features()), s
+        err = np.abs(env.belief_map.cpu().numpy().astype(np.float64) - ob.belief()).max()
+        assert err <= BELIEF_TOL, (s, err)
+        t = ob.timestep()
+        due = (t > 0) & (t % 3 == 0)
+        revealed += int((ob.revealed()[due] >= 0).sum())
+        skipped += int((ob.revealed()[due] < 0).sum())
+    assert revealed > 50 and skipped > 50  # both outcomes of the Bernoulli(0.4) draw occurred
+    assert abs(skipped / (skipped + revealed) - 0.4) < 0.1
+    env.close()
+
+
+@pytest.mark.gpu
+def test_pointer_structs_of_another_abi_revision_are_rejected(torch_cuda):
+    """every pointer struct carries struct_bytes = sizeof(struct); a binding built against another header revision (e.g.
+    from a stale copy of INTEGRATION.md) is refused with SY_ERR_INVALID_ARGUMENT before any pointer reaches a kernel"""
+    import ctypes as C
+
+    pkg = _pkg()
+    from student_mechanism_design_b200 import _cabi
+
+    env = pkg.BatchedScotlandYardEnv(64, 2, 10, graph_nodes=15, graph_edges=20, seed=0)
+    env.reset()
+    acts = env.sample_actions()
+    lib = _cabi.load_library()
+    stream = env._stream()
+    for name in ("_state", "_obs", "_out"):
+        good = getattr(env, name)
+        bad = type(good).from_buffer_copy(good)
+        bad.struct_bytes = good.struct_bytes - 8  # the previous revision's size
+        args = {"_state": (bad, env._obs, env._out), "_obs": (env._state, bad, env._out), "_out": (env._state, env._obs, bad)}[name]
+        rc = lib.sy_step(env._handle, acts.data_ptr(), C.byref(args[0]), C.byref(args[1]), C.byref(args[2]), stream)
+        assert rc == 1 and b"size mismatch" in lib.sy_last_error(), name
+    host = env._host_buffers()
+    bad = type(env._host_out).from_buffer_copy(env._host_out)
+    bad.struct_bytes = 0
+    rc = lib.sy_step_host(env._handle, host["actions"].data_ptr(), env._actions_dev.data_ptr(), C.byref(env._state), C.byref(env._obs),
+                          C.byref(env._out), C.byref(bad), stream)
+    assert rc == 1 and b"SyHostOut size mismatch" in lib.sy_last_error()
+    before = env.pos.clone()
+    env.step(acts)  # the handle is still usable and the rejected calls changed nothing
+    assert env.timestep.max().item() == 1 and before.shape == env.pos.shape
+    env.close()

@@ -19,9 +19,11 @@ class StubEnv:
 
     DEFAULT_ACTION = -1
 
-    def __init__(self, B=6, P=2, N=9, belief=True):
+    def __init__(self, B=6, P=2, N=9, belief=True, reveal_interval=0, auto_reset=False):
         A = P + 1
         self.num_envs, self.num_agents, self.number_of_agents = B, A, P
+        self.graph_nodes, self.agent_money, self.num_graphs = N, 10, 1
+        self.reveal_interval, self.auto_reset, self._is_reset = reveal_interval, auto_reset, False
         self.possible_agents = ["MrX"] + [f"Police{i}" for i in range(P)]
         self.device = torch.device("cpu")
         self.belief_on = belief
@@ -32,6 +34,8 @@ class StubEnv:
         self.action_mask = torch.zeros(B, A, N, dtype=torch.bool)
         self.agent_budget = self.money.float()
         self.mrx_revealed = self.pos[:, 0].clone()
+        if reveal_interval:
+            self.mrx_revealed[::2] = -1  # hidden in every other env
         self.graph_id = torch.zeros(B, dtype=torch.int32)
         self.belief_map = torch.full((B, N), 1.0 / N)
         self.reward = torch.zeros(B, A)
@@ -43,6 +47,7 @@ class StubEnv:
 
     def reset(self, reset_mask=None, **kw):
         self.calls.append(("reset", None if reset_mask is None else reset_mask.clone(), kw))
+        self._is_reset = True
 
     def step(self, actions):
         self.calls.append(("step", actions.clone()))
@@ -58,8 +63,64 @@ class StubEnv:
 
 
 def _adapter(stub):
-    cls = torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict)
+    cls = torchrl_env.make_env_class(fake_torchrl.EnvBase, fake_torchrl.TensorDict, fake_torchrl.SPECS)
     return cls(stub)
+
+
+def test_adapter_declares_specs_and_passes_check_env_specs():
+    """torchrl's EnvBase.rollout / check_env_specs / SyncDataCollector need observation / action / reward / done specs:
+    every key the adapter emits is declared with its shape, dtype and bounds, and random actions drawn from the action
+    spec step the env (against the stand-in's check_env_specs; a real torchrl is not installed here)."""
+    for kw in (dict(), dict(belief=False), dict(reveal_interval=3), dict(P=5, N=20)):
+        stub = StubEnv(**kw)
+        env = _adapter(stub)
+        B, A, N = stub.num_envs, stub.num_agents, stub.graph_nodes
+        act = env.action_spec[("agents", "action")]
+        assert tuple(act.shape) == (B, A) and act.dtype == torch.int64 and act.n == N  # Categorical(N) per agent
+        assert tuple(env.reward_spec[("agents", "reward")].shape) == (B, A, 1)
+        for k in ("done", "terminated", "truncated"):
+            assert tuple(env.done_spec[k].shape) == (B, 1) and env.done_spec[k].dtype == torch.bool
+        assert fake_torchrl.check_env_specs(env, steps=3)
+        out = env.rollout(4)  # EnvBase.rollout with random actions from the spec
+        assert len(out) == 4 and out[-1].get(("agents", "reward")).shape == (B, A, 1)
+        assert stub.calls[-1][0] == "step" and stub.calls[-1][1].dtype == torch.int64
+
+
+def test_adapter_hides_mrx_from_the_police_groups():
+    """with a reveal schedule the police groups see MrX only at reveal steps: MrX_pos = -1 while hidden, never his
+    position or mask row; MrX's own group and the privileged state keep the true node"""
+    stub = StubEnv(reveal_interval=3)
+    env = _adapter(stub)
+    td = env.reset()
+    hidden = stub.mrx_revealed < 0
+    assert hidden.any() and (~hidden).any()
+    for i, name in enumerate(stub.possible_agents):
+        seen = td.get((name, "observation", "MrX_pos"))[:, 0]
+        if i == 0:
+            assert torch.equal(seen, stub.pos[:, 0])
+        else:
+            assert bool((seen[hidden] == -1).all()) and torch.equal(seen[~hidden], stub.pos[~hidden, 0])
+            assert td.get((name, "observation", "action_mask")).shape[1] == 1  # own row only
+    shared = td.get(("agents", "observation", "agent_position"))
+    assert bool((shared[hidden, 0] == -1).all()) and torch.equal(shared[:, 1:], stub.pos[:, 1:])
+    assert torch.equal(td.get(("agents", "state", "agent_position")), stub.pos)
+    # without a schedule nothing is masked (reference behaviour, yard.py:282,324)
+    td0 = _adapter(StubEnv()).reset()
+    assert td0.get(("agents", "observation", "agent_position")).data_ptr() == td0.get(("agents", "state", "agent_position")).data_ptr()
+
+
+def test_adapter_partial_reset_is_a_noop_under_auto_reset():
+    stub = StubEnv(auto_reset=True)
+    env = _adapter(stub)
+    env.reset()
+    n = len(stub.calls)
+    B = stub.num_envs
+    m = torch.tensor([1, 0, 0, 1, 0, 0], dtype=torch.bool).reshape(B, 1)
+    td = env.reset(fake_torchrl.TensorDict({"_reset": m}, batch_size=[B]))
+    assert len(stub.calls) == n, "finished envs were already reset inside the step: no second reset"
+    assert td.get("done").shape == (B, 1)
+    env.reset()  # a full reset is still a reset
+    assert len(stub.calls) == n + 1
 
 
 def test_adapter_reset_keys_and_partial_reset():
