@@ -229,6 +229,17 @@ def run_cuda_arm(args, wl):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
+    # one slice of the host cores per rank: the ranks' pinned copies, spin-waits and policy threads do not migrate onto
+    # each other's cores (round 1 lost 13 % of the 8-GPU host-buffer throughput to that)
+    affinity = None
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(world, 1)
+        if world > 1 and per >= 2:
+            affinity = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, affinity)
+    except Exception:
+        affinity = None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -381,41 +392,105 @@ def run_cuda_arm(args, wl):
     policy_ms = statistics.mean(c.elapsed_time(a) for a, _, c in kev)
 
     # ---- end to end through the host-buffer API
+    # The rank's batch is driven as `--e2e-halves` half-batch envs (own handle, own stream, own host thread; ctypes calls
+    # release the GIL): while one half waits for its PCIe copies the other half's kernels run, so the host round trips of
+    # the two halves hide behind each other's device work (ping-pong).  Every step of every half still moves its actions
+    # host -> device and its results device -> host and synchronises before the next step of that half.
     Ke = max(3, min(K, args.e2e_steps))
+    H = max(1, args.e2e_halves)
+    while B % H:
+        H -= 1
+    Bh = B // H
+    e2e_envs, e2e_streams, e2e_policies = [], [], []
+    for h in range(H):
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(st):
+            eh = BatchedScotlandYardEnv(Bh, P, wl["money"], graph_nodes=N, graph_edges=wl["E"], seed=0, **pool_kw,
+                                        tolls=wl["toll"], belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True,
+                                        env_offset=rank * B + h * Bh, device=f"cuda:{local}")
+            eh.reset()
+            if policy == "gnn":
+                e2e_policies.append(GNNPolicy(eh, seed=0))
+            elif policy == "mappo":
+                e2e_policies.append(MappoPolicy(eh, obs_size=A, hidden_size=64, seed=0))
+            else:
+                e2e_policies.append(None)
+        e2e_envs.append(eh)
+        e2e_streams.append(st)
+    torch.cuda.synchronize(dev)
 
     def e2e_leg(wname, fl, passes=3):
-        """Ke steps of: host actions (pinned) -> H2D -> step -> D2H of the results -> synchronise, `passes` times; the
-        median pass.  The random policy's actions are also produced on the device and copied to the host every step, so
-        a host-side policy is emulated honestly (its D2H bytes are counted)."""
-        nonlocal counter
+        """Ke steps per half of: the policy's actions in pinned HOST memory -> H2D -> step -> D2H of the results ->
+        synchronise; `passes` times, the median pass.  The policy (random sampler, or the GNN / MAPPO forward of config 5)
+        runs on the device from the resident state and its actions travel to the host first, so a host-side consumer is
+        emulated honestly (those D2H bytes are counted)."""
         wire, wb = {"int64": (torch.int64, 8), "int32": (torch.int32, 4), "int16": (torch.int16, 2)}[wname]
-        env.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
-        for _ in range(3):
-            env.step_host(env.sample_actions_host(step_counter=counter, dtype=wire), flags=fl)
-            counter += 1
+        errors, last = [], [None] * H
+
+        def host_actions(h, eh, pol, c):
+            if pol is None:
+                return eh.sample_actions_host(step_counter=c, dtype=wire)  # kernel + D2H + synchronise in one C call
+            buf = eh._host_buffers()["actions"]
+            if policy == "gnn":
+                acts = pol.act(args.epsilon, args.epsilon, step_counter=c)
+            else:
+                obs = (eh.pos.float() / N).unsqueeze(1).expand(Bh, A, A).contiguous()
+                acts, _ = pol.act(obs, step_counter=c)
+            buf.copy_(acts, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            return buf
+
+        def worker(h, steps, c0):
+            try:
+                eh, pol = e2e_envs[h], e2e_policies[h]
+                with torch.cuda.device(dev), torch.cuda.stream(e2e_streams[h]):
+                    if pol is None and not args.e2e_python_loop:
+                        # the same two C-ABI calls per step (sy_sample_actions_host, sy_step_host*), issued from C
+                        last[h] = eh.host_rollout_random(steps, step_counter=c0, dtype=wire, flags=fl)
+                    else:
+                        for k in range(steps):
+                            last[h] = eh.step_host(host_actions(h, eh, pol, c0 + k), flags=fl)
+                    torch.cuda.current_stream(dev).synchronize()
+            except Exception as exc:  # surfaced below: a dead worker must not look like a fast one
+                errors.append(exc)
+
+        def run(steps, c0):
+            ts = [threading.Thread(target=worker, args=(h, steps, c0)) for h in range(H)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errors:
+                raise errors[0]
+
+        for eh in e2e_envs:
+            eh.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
+        c = 1 << 20
+        run(3, c)
         ms = []
         for _ in range(passes):
+            c += Ke + 3
             barrier()
             t0 = time.perf_counter()
-            ev0.record()
-            for _ in range(Ke):
-                host_actions = env.sample_actions_host(step_counter=counter, dtype=wire)  # the "policy" hands over HOST actions
-                res = env.step_host(host_actions, flags=fl)  # H2D actions, kernel, D2H reward/flags, synchronised
-                counter += 1
-            ev1.record()
-            barrier()
-            ms.append(max_over_ranks(max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3)))
-        env.set_host_overlap(False)
-        assert res["reward"].shape == (B, A) and not res["reward"].is_cuda
+            run(Ke, c)
+            torch.cuda.synchronize(dev)
+            ms.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+        for eh in e2e_envs:
+            eh.set_host_overlap(False)
+        assert all(r["reward"].shape == (Bh, A) and not r["reward"].is_cuda for r in last)
         e2e_ms = statistics.median(ms)
+        pol_wb = wb if policy == "random" else 8  # the agents' kernels emit int64 actions
         return {"value": world * B * Ke / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": env.host_h2d_bytes_per_step(wb), "d2h_bytes_per_step": env.host_d2h_bytes_per_step(wb, fl),
-                "steps": Ke, "passes_ms": [round(x, 3) for x in ms],
-                "note": f"actions int{wb * 8}[B,A] from pinned host memory in; reward f32 [B,A] + winner + "
+                "h2d_bytes_per_step": H * e2e_envs[0].host_h2d_bytes_per_step(wb if policy == "random" else 8),
+                "d2h_bytes_per_step": H * e2e_envs[0].host_d2h_bytes_per_step(pol_wb, fl),
+                "steps": Ke, "passes_ms": [round(x, 3) for x in ms], "half_batches": H, "policy": policy,
+                "loop": "python" if (policy != "random" or args.e2e_python_loop) else "sy_host_rollout_random (C)",
+                "note": f"{H} half-batch env(s) of {Bh} envs, one host thread and stream each (ping-pong); per step and half: "
+                f"actions int{(wb if policy == 'random' else 8) * 8}[B,A] from pinned host memory in; reward f32 [B,A] + winner + "
                 + ("one status byte per env (terminated/truncated/frozen bits; every agent of an env shares them)" if fl == "compact"
                    else "terminated/truncated/done u8 [B,A] + status") +
-                " out to pinned host memory; observations stay on the device for the GPU policy; the D2H count includes the "
-                "random policy's actions coming back to the host"}
+                " out to pinned host memory, synchronised; observations stay on the device for the GPU policy; the D2H count "
+                "includes the policy's actions coming back to the host; wall clock with device synchronisation on both sides"}
 
     # wire format of the host actions: node ids fit 16 bits at every BASELINE config; --e2e-int64 = the reference's dtype
     wname = "int64" if args.e2e_int64 else (args.e2e_wire if N <= 32767 or args.e2e_wire != "int16" else "int32")
@@ -424,6 +499,8 @@ def run_cuda_arm(args, wl):
     # the reference's own call shape (yard.py:144,269): int64 actions in, per-agent [B, A] flag arrays out
     e2e_ref_shape = e2e if (wname, args.e2e_flags) == ("int64", "per_agent") else e2e_leg("int64", "per_agent")
     sampler.active = False
+    for eh in e2e_envs:
+        eh.close()
 
     clocks = sampler.summary()
     if rank == 0:
@@ -448,7 +525,7 @@ def run_cuda_arm(args, wl):
             "config": {"workload": f"{wl['name']}: {wl['desc']}", "num_nodes": N, "num_police": P,
                        "envs_per_gpu": B, "global_envs": world * B, "graph_pool": env.num_graphs, "node_features_dtype": "uint8 (opt-in)" if args.nf_u8 else "float32", "policy": policy_desc, "policy_ms_per_step": policy_ms, "loop": (f"CUDA graph replay of {seg}-step sy_rollout_random_dev segments" if use_graph else
                                 "python" if py_loop else "sy_rollout_random (C)"),
-                       "auto_reset": True, "parallelism": f"batch-sharded x{world}",
+                       "auto_reset": True, "parallelism": f"batch-sharded x{world}", "host_cores_per_rank": None if affinity is None else len(affinity),
                        "l2": f"per-step working set {bstep * B / 1e6:.0f} MB per GPU > 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "e2e_reference_shape": e2e_ref_shape, "gpu_launches": int(launches),
             "passes_ms": [round(x, 4) for x in pass_ms], "stats_fold_allreduce_ms": stats_ms,
@@ -483,6 +560,10 @@ def main():
     ap.add_argument("--writer", default=None, choices=["bulk", "lsu"], help="observation writer path (sy_set_option; default bulk)")
     ap.add_argument("--allow-lib-override", action="store_true", help="accept SY_LIB_PATH (kernel-variant experiments only)")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-python-loop", action="store_true",
+                    help="host-buffer leg: call sample_actions_host / step_host from Python every step instead of sy_host_rollout_random")
+    ap.add_argument("--e2e-halves", type=int, default=4,
+                    help="host-buffer leg: number of half-batch envs (one host thread + stream each) the rank's batch is driven as")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-int64", action="store_true", help="host actions as int64 (the reference dtype)")

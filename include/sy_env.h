@@ -273,6 +273,12 @@ int sy_set_host_overlap(SyEnv* env, int32_t on);
  * bytes_per_action = 8 | 4 | 2 selects the wire format of actions_dev / actions_host. */
 int sy_sample_actions_host(SyEnv* env, const SyState* state, uint32_t step_counter, void* actions_dev, void* actions_host,
                            int32_t bytes_per_action, sy_stream_t stream);
+/* `num_steps` iterations of { sy_sample_actions_host(step_counter0 + k); sy_step_host*(those HOST actions) } issued from C:
+ * the host-buffer loop of a host-side policy (gnn_trainer.py:201-250 with RandomAgent) with every per-step copy and
+ * synchronisation of the two calls, and no interpreter between them.  Buffers as in the two calls. */
+int sy_host_rollout_random(SyEnv* env, int32_t num_steps, uint32_t step_counter0, void* actions_dev, void* actions_host,
+                           int32_t bytes_per_action, const SyState* state, const SyObs* obs, const SyOut* out,
+                           const SyHostOut* host_out, sy_stream_t stream);
 int sy_step_host_i32(SyEnv* env, const int32_t* actions_host, int32_t* actions_dev, const SyState* state,
                      const SyObs* obs, const SyOut* out, const SyHostOut* host_out, sy_stream_t stream);
 int sy_sample_actions_i32(SyEnv* env, const SyState* state, uint32_t step_counter, int32_t* actions,
@@ -288,6 +294,15 @@ int sy_sample_actions(SyEnv* env, const SyState* state, uint32_t step_counter, i
  * sy_step only while SyOut.stats is non-NULL (they are kept in per-tile-group lines inside the library so that the
  * step kernel's atomics do not serialise on one cache line). */
 int sy_stats(SyEnv* env, int64_t* stats, sy_stream_t stream);
+
+/* The path's one collective: fold the accumulated statistics into `stats_local` (device, int64
+ * [SY_NUM_STATS], this rank's cumulative vector, as sy_stats does) and write their sum over all ranks of `nccl_comm`
+ * (an `ncclComm_t`, passed as void*) to `stats_global` (device, int64 [SY_NUM_STATS]) with one ncclAllReduce on `stream`
+ * (NVLink / NVSwitch on a B200 box).  NCCL is resolved at run time from the host process (libnccl.so.2; SY_NCCL_LIB
+ * overrides the name), so the library does not link against it.  Replaces the Python-side aggregation of
+ * src/eval/metrics.py:168-232 across workers; student_mechanism_design_b200.sharding.allreduce_stats is the
+ * torch.distributed form of the same reduction. */
+int sy_allreduce_stats(SyEnv* env, void* nccl_comm, int64_t* stats_local, int64_t* stats_global, sy_stream_t stream);
 
 /* `num_steps` steps of the random-valid policy rollout the reference's trainers start from (gnn_trainer.py:201-250 with
  * RandomAgent, src/agent/random_agent.py:7): per step sy_sample_actions(step_counter0 + k) into `actions` (device,

@@ -90,10 +90,13 @@ SIGNATURES = {
     "sy_step_host_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                    C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),
     "sy_set_host_overlap": (C.c_int, [C.c_void_p, C.c_int32]),
+    "sy_host_rollout_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SyState),
+                                         C.POINTER(SyObs), C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),
     "sy_sample_actions_host": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "sy_sample_actions_i32": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_sample_actions": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
     "sy_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sy_allreduce_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sy_rollout_random_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                         C.POINTER(SyOut), C.c_void_p]),
     "sy_rollout_random": (C.c_int, [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),

@@ -24,6 +24,7 @@
 #include "../../include/sy_env.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -68,6 +69,9 @@ constexpr int TILE = 32;       // envs per observe CTA / per logic warp (lane = 
 #endif
 #ifndef SY_STORE_HINT
 #define SY_STORE_HINT 0
+#endif
+#ifndef SY_NF_SCALAR_ONES
+#define SY_NF_SCALAR_ONES 0  // 1: node_features ones as 4-byte stores after the zero fill instead of merged 16-byte chunks
 #endif
 #ifndef SY_BULK_HINT
 #define SY_BULK_HINT 0  // 1: L2 evict_first policy on the bulk stores
@@ -998,6 +1002,13 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
 #pragma unroll 4
   for (int i = lane; i < nvec; i += 32) store_obs16(body + i, z);
   __syncwarp();  // orders the zero stores before the chunks below (same warp, same addresses)
+#if SY_NF_SCALAR_ONES
+  // one 4-byte store per agent: no merging of ones that share a chunk (A x A loop) is needed; the lines are still in L2
+  if (lane < A) {
+    const int f0 = fpos[lane] - head;
+    if (fpos[lane] >= 0 && f0 >= 0 && f0 < (nvec << 2)) __stcs(reinterpret_cast<float*>(body) + f0, 1.0f);
+  }
+#else
   if (lane < A) {
     const int f0 = fpos[lane] - head;
     if (fpos[lane] >= 0 && f0 >= 0 && f0 < (nvec << 2)) {
@@ -1014,9 +1025,10 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
           v.w = sub == 3 ? one : v.w;
         }
       }
-      store_obs16(body + myc, v);
+      store_obs16(body + myc, v);  // (match.any + redux instead of this loop was measured 18 % SLOWER per step: MATCH is slow)
     }
   }
+#endif
 }
 
 // writer warps: stream the dense observations of the tile.  Everything the ones depend on is staged into shared
@@ -1024,7 +1036,7 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
 // on one graph and its CSR fits -- the graph's row pointers / neighbours / weights.  Each env's action_mask rows are
 // assembled in a per-warp shared-memory image and copied out, node_features are zero-filled and the (at most A) chunks
 // with a one rewritten whole: no byte-sized stores anywhere (they cost 60 % extra time when tried).
-template <int WRW>
+template <int WRW, bool PREFILLED = false>
 __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
   const Tables& tb = p.tb;
   const int N = p.N, A = p.A;
@@ -1110,7 +1122,7 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
       __syncwarp();
       warp_copy_bytes(nf8, img8, N * A, lane);
     } else {
-      if (p.nf_prefilled) warp_write_node_feature_ones(nf, N * A, fpos, A, lane);
+      if constexpr (PREFILLED) warp_write_node_feature_ones(nf, N * A, fpos, A, lane);
       else warp_write_node_features(nf, N * A, fpos, A, lane);
     }
     __syncwarp();
@@ -1713,7 +1725,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
         _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
       } else {
         const float inv = 1.0f / tot;
-        _Pragma("unroll 2") for (int j = lane; j < N; j += 32) bel[j] = tout[j * BSTRIDE + e] * inv;
+        _Pragma("unroll 4") for (int j = lane; j < N; j += 32) bel[j] = tout[j * BSTRIDE + e] * inv;
       }
     } else if (ope == BEL_UNIFORM) {
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
@@ -1744,9 +1756,13 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
 
 // BW belief warps + WRW writer warps.  <8, 8> everywhere the belief hides under the write stream (fast path); the
 // large-N generic belief path is the critical role, there the split is <12, 4> (c4: 82 -> 91 M env-steps/s).
+// WV selects the writers at compile time, so the default kernel carries none of the experimental paths' code or
+// registers: WV_LSU = 16-byte streaming stores (default), WV_BULK = zero-page fill + chunk images through the TMA engine,
+// WV_ONES = node_features were zero-filled by sy_fill_kernel, only the ones are stored (split step).
 // <BW, 0> / <0, WRW>: one role per launch (the split step runs them as two concurrent kernels; the role hand-over
 // barrier of the large-N belief path counts THREADS, so that path keeps both roles in one launch)
-template <int BW, int WRW>
+enum { WV_LSU = 0, WV_BULK = 1, WV_ONES = 2 };
+template <int BW, int WRW, int WV = WV_LSU>
 __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Params p) {
   static_assert((BW + WRW) * 32 == THREADS || BW == 0 || WRW == 0, "the role hand-over barrier counts THREADS");
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -1761,10 +1777,10 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
     }
   } else if (!(p.dbg_skip & 1)) {
     if constexpr (WRW > 0) {
-      if (p.wr_bulk) {
+      if constexpr (WV == WV_BULK) {
         if constexpr (WRW >= 2) writer_role_bulk<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
       } else {
-        writer_role<WRW>(p, dyn, tile0, nEnv, warp - nbw, lane);
+        writer_role<WRW, WV == WV_ONES>(p, dyn, tile0, nEnv, warp - nbw, lane);
       }
     }
   }
@@ -1863,20 +1879,13 @@ __device__ __forceinline__ void fast_mask_ones(const Params& p, const PairView& 
       if ((int)s_wgt[k] <= lim) row[s_col[k]] = v;
   }
 }
-// one-hot granules of the chunk's envs (float32 node_features, rows of whole 16-byte granules): pairs whose ones share a
-// granule find each other with match.any and the lowest lane stores the merged granule
+// one-hot entries of the chunk's envs (float32 node_features): one 4-byte store per (env, agent) pair into the lines the
+// zero fill has just completed (they are still in L2, the partial writes merge there).  Merging the ones that share a
+// 16-byte granule with match.any + redux was measured far slower (MATCH is a slow instruction on this part).
 __device__ __forceinline__ void fast_nf32_ones(const Params& p, const PairView& pv, const int* s_rev, uint8_t* gnf, int lane) {
   const int A = p.A;
-  const bool on = pv.valid && !(pv.a == 0 && s_rev[pv.e] < 0);  // the MrX column stays blank while he is hidden
-  const int f = pv.u * A + pv.a;                                  // element index in the env's [N, A] row
-  const unsigned key = on ? (unsigned)(pv.e * (p.N * A / 4) + (f >> 2)) : (0x80000000u | (unsigned)lane);
-  const unsigned peers = __match_any_sync(FULL, key);
-  const unsigned bits = __reduce_or_sync(peers, on ? (1u << (f & 3)) : 0u);
-  if (on && (peers & ((1u << lane) - 1u)) == 0) {
-    const unsigned one = 0x3f800000u;
-    const uint4 v = make_uint4(bits & 1u ? one : 0u, bits & 2u ? one : 0u, bits & 4u ? one : 0u, bits & 8u ? one : 0u);
-    store_obs16(reinterpret_cast<uint4*>(gnf + (size_t)pv.e * p.N * A * 4) + (f >> 2), v);
-  }
+  if (pv.valid && !(pv.a == 0 && s_rev[pv.e] < 0))  // the MrX column stays blank while he is hidden
+    __stcs(reinterpret_cast<float*>(gnf + (size_t)pv.e * p.N * A * 4) + pv.u * A + pv.a, 1.0f);
 }
 
 template <int BW>
@@ -2681,17 +2690,23 @@ int raise_observe_smem_limit(int device, size_t bytes) {
   if (bytes <= cur) return SY_OK;
   CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, WR_WARPS, WV_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS, WV_BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<BEL_WARPS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<0, WR_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  CUDA_TRY(cudaFuncSetAttribute(sy_observe_kernel<0, WR_WARPS, WV_ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   cur = bytes;
   return SY_OK;
 }
 
 void launch_observe(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t s) {
-  if (e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS)
-    sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
-  else
-    sy_observe_kernel<BEL_WARPS, WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
+  const bool gen = e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS;
+  if (p.wr_bulk) {
+    if (gen) sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
+    else sy_observe_kernel<BEL_WARPS, WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
+  } else {
+    if (gen) sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
+    else sy_observe_kernel<BEL_WARPS, WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
+  }
 }
 
 int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOut* out, Params& p) {
@@ -3329,7 +3344,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
     Params pw = p;  // writers only: their staging area starts at the beginning of the dynamic shared memory
     pw.wr_off = 0;
     pw.wr_off_csr = e->wr_off_csr - e->wr_off;
-    sy_observe_kernel<0, WR_WARPS><<<grid, WR_WARPS * 32, e->obs_smem - (size_t)e->wr_off, s>>>(pw);
+    sy_observe_kernel<0, WR_WARPS, WV_ONES><<<grid, WR_WARPS * 32, e->obs_smem - (size_t)e->wr_off, s>>>(pw);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (p.belief_on) CUDA_TRY(cudaStreamWaitEvent(s, e->ev_split_belief, 0));
@@ -3477,6 +3492,24 @@ int sy_sample_actions_host(SyEnv* e, const SyState* st, uint32_t step_counter, v
   return SY_OK;
 }
 
+// K steps of the host-buffer loop driven from C: per step sy_sample_actions_host (the random policy's actions arrive in
+// HOST memory) followed by sy_step_host* with those host actions -- the same two calls, copies and synchronisations a
+// host-side policy loop makes, without an interpreter between them
+int sy_host_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, void* actions_dev, void* actions_host,
+                           int32_t bytes_per_action, const SyState* st, const SyObs* ob, const SyOut* out,
+                           const SyHostOut* ho, sy_stream_t stream) {
+  if (!e || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env or negative num_steps");
+  for (int32_t k = 0; k < num_steps; ++k) {
+    int rc = sy_sample_actions_host(e, st, step_counter0 + (uint32_t)k, actions_dev, actions_host, bytes_per_action, stream);
+    if (rc) return rc;
+    if (bytes_per_action == 8) rc = sy_step_host(e, (const int64_t*)actions_host, (int64_t*)actions_dev, st, ob, out, ho, stream);
+    else if (bytes_per_action == 4) rc = sy_step_host_i32(e, (const int32_t*)actions_host, (int32_t*)actions_dev, st, ob, out, ho, stream);
+    else rc = sy_step_host_i16(e, (const int16_t*)actions_host, (int16_t*)actions_dev, st, ob, out, ho, stream);
+    if (rc) return rc;
+  }
+  return SY_OK;
+}
+
 int sy_set_host_overlap(SyEnv* e, int32_t on) {
   if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
   if (on && !e->ev_main) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_main, cudaEventDisableTiming));
@@ -3499,6 +3532,43 @@ int sy_stats(SyEnv* e, int64_t* stats, sy_stream_t stream) {
   sy_fold_stats_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)e->d_stats_rep, reinterpret_cast<long long*>(stats));
   g_launches++;
   CUDA_TRY(cudaGetLastError());
+  return SY_OK;
+}
+
+// the one collective of the path.  NCCL is resolved at run time (dlopen of the libnccl the host process
+// already uses, e.g. the one bundled with PyTorch), so the library has no link-time dependency on it and a host that is
+// not PyTorch (a C++ / Go / Rust learner with its own ncclComm_t) gets the multi-GPU reduction too.
+namespace {
+typedef int (*NcclAllReduceFn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*NcclGetErrorStringFn)(int);
+NcclAllReduceFn g_nccl_allreduce = nullptr;
+NcclGetErrorStringFn g_nccl_errstr = nullptr;
+int resolve_nccl() {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (g_nccl_allreduce) return SY_OK;
+  void* h = nullptr;
+  const char* override_path = getenv("SY_NCCL_LIB");
+  const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  }
+  void* sym = h ? dlsym(h, "ncclAllReduce") : dlsym(RTLD_DEFAULT, "ncclAllReduce");  // already loaded by the host process?
+  if (!sym) return fail(SY_ERR_STATE, "sy_allreduce_stats: libnccl.so.2 not found (load NCCL in the host process or set SY_NCCL_LIB)");
+  g_nccl_allreduce = reinterpret_cast<NcclAllReduceFn>(sym);
+  g_nccl_errstr = reinterpret_cast<NcclGetErrorStringFn>(h ? dlsym(h, "ncclGetErrorString") : dlsym(RTLD_DEFAULT, "ncclGetErrorString"));
+  return SY_OK;
+}
+}  // namespace
+
+int sy_allreduce_stats(SyEnv* e, void* nccl_comm, int64_t* stats_local, int64_t* stats_global, sy_stream_t stream) {
+  if (!e || !nccl_comm || !stats_local || !stats_global) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / communicator / statistics vectors");
+  if (int rc = resolve_nccl()) return rc;
+  if (int rc = sy_stats(e, stats_local, stream)) return rc;  // fold the library's accumulators into the rank's cumulative vector
+  enum { NCCL_INT64 = 4, NCCL_SUM = 0 };  // nccl.h: ncclInt64, ncclSum
+  const int nrc = g_nccl_allreduce(stats_local, stats_global, SY_NUM_STATS, NCCL_INT64, NCCL_SUM, nccl_comm, (cudaStream_t)stream);
+  if (nrc != 0) return fail(SY_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl_errstr ? g_nccl_errstr(nrc) : "unknown NCCL error");
   return SY_OK;
 }
 

@@ -420,6 +420,28 @@ class BatchedScotlandYardEnv:
         keys = ("reward", "winner", "status") if compact else ("reward", "terminated", "truncated", "done", "winner", "status")
         return {k: host[k] for k in keys}
 
+    def host_rollout_random(self, num_steps: int, step_counter: Optional[int] = None, dtype=torch.int16,
+                            flags: str = "compact") -> Dict[str, torch.Tensor]:
+        """`num_steps` iterations of `step_host(sample_actions_host())` issued from C (sy_host_rollout_random): the
+        host-buffer loop with all of its per-step copies and synchronisations, without the interpreter between the calls.
+        Returns the pinned host results of the last step."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        host = self._host_buffers()
+        key, stage = {torch.int64: ("actions", self._actions_dev), torch.int32: ("actions32", self._actions_dev32),
+                      torch.int16: ("actions16", self._actions_dev16)}[dtype]
+        if step_counter is None:
+            step_counter = self._sample_counter
+            self._sample_counter += int(num_steps)
+        compact = flags == "compact"
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_host_rollout_random(
+                self._handle, int(num_steps), int(step_counter) & 0xFFFFFFFF, stage.data_ptr(), host[key].data_ptr(),
+                stage.element_size(), C.byref(self._state), C.byref(self._obs), C.byref(self._out),
+                C.byref(self._host_out_compact if compact else self._host_out), self._stream()))
+        keys = ("reward", "winner", "status") if compact else ("reward", "terminated", "truncated", "done", "winner", "status")
+        return {k: host[k] for k in keys}
+
     def set_host_overlap(self, on: bool = True):
         """Host loops with overlap: `step_host` then returns as soon as the step's results are in the pinned host
         tensors -- the observation kernel of that step may still be running on the stream (any later stream work,

@@ -1086,3 +1086,94 @@ def test_pointer_structs_of_another_abi_revision_are_rejected(torch_cuda):
     env.step(acts)  # the handle is still usable and the rejected calls changed nothing
     assert env.timestep.max().item() == 1 and before.shape == env.pos.shape
     env.close()
+
+
+@pytest.mark.gpu
+def test_allreduce_stats_through_the_c_abi(torch_cuda):
+    """sy_allreduce_stats: fold + one ncclAllReduce of the statistics vector on a raw ncclComm_t, here a
+    1-rank communicator created through NCCL's C API (a non-PyTorch host would hand over its own); the global vector equals
+    the local one, repeated calls do not double count, and the torch.distributed helper agrees."""
+    import ctypes as C
+    import glob
+
+    torch = torch_cuda
+    pkg = _pkg()
+    from student_mechanism_design_b200 import _cabi
+
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2")) + ["libnccl.so.2"]
+    nccl = C.CDLL(cands[0])
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_char * 128)]
+
+    uid, comm = UniqueId(), C.c_void_p()
+    nccl.ncclGetUniqueId.argtypes = [C.POINTER(UniqueId)]
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    assert nccl.ncclGetUniqueId(C.byref(uid)) == 0
+    assert nccl.ncclCommInitRank(C.byref(comm), 1, uid, 0) == 0
+    env = pkg.BatchedScotlandYardEnv(512, 3, 8, graph_nodes=30, graph_edges=55, seed=2, auto_reset=True)
+    env.reset()
+    lib = _cabi.load_library()
+    glob_vec = torch.zeros(_cabi.SY_NUM_STATS, dtype=torch.int64, device="cuda")
+    for rounds in range(2):
+        env.rollout_random(20)
+        _cabi.check(lib.sy_allreduce_stats(env._handle, comm, env.stats_vec.data_ptr(), glob_vec.data_ptr(), env._stream()))
+        torch.cuda.synchronize()
+        assert torch.equal(glob_vec, env.stats_vec)
+        assert int(glob_vec[0]) == 512 * 20 * (rounds + 1)  # cumulative env-steps, not double counted
+    assert env.stats()["env_steps"] == 512 * 40 and env.stats()["episodes"] == int(glob_vec[1])
+    assert lib.sy_allreduce_stats(env._handle, None, env.stats_vec.data_ptr(), glob_vec.data_ptr(), env._stream()) == 1
+    nccl.ncclCommDestroy(comm)
+    env.close()
+
+
+@pytest.mark.gpu
+def test_host_rollout_random_equals_the_python_host_loop(torch_cuda, tables):
+    """sy_host_rollout_random (the host-buffer loop issued from C, what bench.py's e2e leg times) == the same steps driven
+    from Python with sample_actions_host + step_host, in both overlap modes and for two concurrent half-batch handles on
+    their own streams and threads (the ping-pong of the e2e leg)."""
+    import threading
+
+    torch = torch_cuda
+    pkg = _pkg()
+    c = dict(N=30, E=55, P=3, money=10, G=2, B=128, kw=dict(belief=True, reveal_interval=4, tolls=1), mode="fp64")
+    K = 17
+    ref, _ = _make_pair(pkg, c, tables)
+    ref.reset()
+    for s in range(K):
+        out_ref = ref.step_host(ref.sample_actions_host(step_counter=s, dtype=torch.int16), flags="compact")
+    for overlap in (False, True):
+        env, _ = _make_pair(pkg, c, tables)
+        env.reset()
+        env.set_host_overlap(overlap)
+        out = env.host_rollout_random(K, step_counter=0, dtype=torch.int16, flags="compact")
+        torch.cuda.synchronize()
+        for k in ("reward", "winner", "status"):
+            assert out[k].numpy().tobytes() == out_ref[k].numpy().tobytes(), (overlap, k)
+        for k in ("pos", "money", "timestep", "visits", "belief_map", "action_mask", "node_features"):
+            assert getattr(env, k).cpu().numpy().tobytes() == getattr(ref, k).cpu().numpy().tobytes(), (overlap, k)
+        env.close()
+    # two half-batch handles driven concurrently reproduce the halves of the full batch (env_offset-keyed streams)
+    halves = [_make_pair(pkg, c, tables, B=64, env_offset=o)[0] for o in (0, 64)]
+    streams = [torch.cuda.Stream() for _ in halves]
+    for h, st in zip(halves, streams):
+        with torch.cuda.stream(st):
+            h.reset()
+            h.set_host_overlap(True)
+
+    def drive(h, st):
+        with torch.cuda.stream(st):
+            h.host_rollout_random(K, step_counter=0, dtype=torch.int16, flags="compact")
+            torch.cuda.current_stream().synchronize()
+
+    ts = [threading.Thread(target=drive, args=(h, st)) for h, st in zip(halves, streams)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for k in ("pos", "money", "timestep", "visits", "belief_map", "action_mask", "node_features", "reward"):
+        got = np.concatenate([getattr(h, k).cpu().numpy() for h in halves])
+        assert got.tobytes() == getattr(ref, k).cpu().numpy().tobytes(), ("halves", k)
+    for e in halves + [ref]:
+        e.close()

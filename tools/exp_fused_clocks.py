@@ -15,6 +15,7 @@ from student_mechanism_design_b200 import BatchedScotlandYardEnv, _cabi  # noqa:
 wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c3"]
 env = BatchedScotlandYardEnv(wl["B"], wl["P"], wl["money"], graph_nodes=wl["N"], graph_edges=wl["E"], seed=0, tolls=wl["toll"],
                              belief=wl["belief"], reveal_interval=wl["reveal"], auto_reset=True)
+env.set_option("step_kernel", "fused")
 env.reset()
 lib = _cabi.load_library()
 out = (C.c_ulonglong * 16)()
