@@ -290,11 +290,10 @@ def run_cuda_arm(args, wl):
         plib = _policy_cabi.load_library()
         mappo = MappoPolicy(env, obs_size=A, hidden_size=64, seed=0)
 
-        def choose(counter):
-            obs = (env.pos.float() / N).unsqueeze(1).expand(B, A, A).contiguous()  # all agents' nodes, obs_size = A
-            a, _ = mappo.act(obs, step_counter=counter)
-            actions.copy_(a)
-        policy_desc = f"MappoAgent actors (Linear({A},64)-ReLU-Linear(64,{N})-softmax, one per agent), masked sampling, fused sy_mappo_act"
+        def choose(counter):  # obs=None: MappoTrainer's observations (mappo_trainer.py:171-199) are built inside the kernel
+            mappo.act(None, step_counter=counter, out=actions)
+        policy_desc = (f"MappoAgent actors (Linear({A},64)-ReLU-Linear(64,{N})-softmax, one per agent) on the trainer's observations "
+                       "(MrX_pos / Polices_pos, built in the kernel), masked sampling, fused sy_mappo_act")
     else:
         def choose(counter):
             env.sample_actions(out=actions, step_counter=counter)
@@ -434,8 +433,7 @@ def run_cuda_arm(args, wl):
             if policy == "gnn":
                 acts = pol.act(args.epsilon, args.epsilon, step_counter=c)
             else:
-                obs = (eh.pos.float() / N).unsqueeze(1).expand(Bh, A, A).contiguous()
-                acts, _ = pol.act(obs, step_counter=c)
+                acts, _ = pol.act(None, step_counter=c)
             buf.copy_(acts, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             return buf

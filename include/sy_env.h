@@ -35,6 +35,7 @@ extern "C" {
 #define SY_NUM_REWARD_WEIGHTS 11 /* order = REWARD_WEIGHT_NAMES, src/reward_net.py:5-17 */
 #define SY_MAX_AGENTS 16
 #define SY_NUM_STATS 16
+#define SY_MAX_COPY_SEGMENTS 8
 #define SY_DEFAULT_ACTION (-1) /* yard.py:16 ; for police identical to `None` (yard.py:210-215) */
 
 enum {
@@ -303,6 +304,11 @@ int sy_stats(SyEnv* env, int64_t* stats, sy_stream_t stream);
  * src/eval/metrics.py:168-232 across workers; student_mechanism_design_b200.sharding.allreduce_stats is the
  * torch.distributed form of the same reduction. */
 int sy_allreduce_stats(SyEnv* env, void* nccl_comm, int64_t* stats_local, int64_t* stats_global, sy_stream_t stream);
+
+/* Trajectory recording for rollout loops (gnn_trainer.py:234-250 stores every transition): up to
+ * SY_MAX_COPY_SEGMENTS device-to-device copies dst[i] <- src[i] of bytes[i] bytes in ONE kernel launch on `stream`
+ * (HOST tables of DEVICE pointers), instead of one copy per stored tensor and step. */
+int sy_copy_segments(int32_t num_segments, void* const* dst, const void* const* src, const uint64_t* bytes, sy_stream_t stream);
 
 /* `num_steps` steps of the random-valid policy rollout the reference's trainers start from (gnn_trainer.py:201-250 with
  * RandomAgent, src/agent/random_agent.py:7): per step sy_sample_actions(step_counter0 + k) into `actions` (device,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SY_POLICY_ABI_VERSION 1
+#define SY_POLICY_ABI_VERSION 2
 #define SY_POLICY_MAX_FEATURES 16 /* K = node_feature_size = agents (utils.py:176) */
 
 enum { SY_POLICY_OK = 0, SY_POLICY_ERR_INVALID_ARGUMENT = 1, SY_POLICY_ERR_CUDA = 2 };
@@ -88,7 +88,10 @@ int sy_gnn_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const f
                uint32_t step_counter, int64_t* actions, float* q_taken, sy_policy_stream_t stream);
 
 /* MappoAgent.select_action for every (env, agent) (mappo_agent.py:87-142).
- * obs [B, A, obs_size] float32; params: per policy  W1 [H, obs_size], b1 [H], W2 [N, H], b2 [N]  (nn.Linear layout),
+ * obs [B, A, obs_size] float32, or NULL = the kernel builds MappoTrainer's own observations from the state
+ * (mappo_trainer.py:171-199: MrX sees obs["MrX_pos"], officer i the officers' nodes obs["Polices_pos"].sum(dim=1); raw
+ * node ids as float32, zero-padded to obs_size >= P columns) -- no observation tensor is materialised at all;
+ * params: per policy  W1 [H, obs_size], b1 [H], W2 [N, H], b2 [N]  (nn.Linear layout),
  * sy_mappo_param_count floats each; policy_of_agent [A] (HOST) = index of the AgentPolicy each agent uses
  * (mappo_trainer.py:124-147: MrX's agent has one policy, the police agent one per officer).
  * probs = softmax(logits) * mask; renormalised by (sum + 1e-8); sum <= 1e-8 -> uniform over the mask, empty mask ->
@@ -105,6 +108,15 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
  * sy_policy_check synchronises the stream and reports a (never expected) failure of the tensor-core kernel. */
 int sy_policy_set_option(const char* name, int32_t value);
 int sy_policy_check(sy_policy_stream_t stream);
+
+/* One node per (env, agent) from ANY policy's logits [B, A, N] (float32) restricted to the env's action_mask [B, A, N]
+ * (bool / uint8): the batched form of the trainers' choice among the valid moves (gnn_trainer.py:221-229,
+ * mappo_agent.py:121-140) for policies that are not the two built-in agents.  greedy != 0: first argmax over the legal
+ * nodes; else an exact sample of softmax(logits | mask) by Gumbel-max with Philox(seed; env_offset + env, step_counter,
+ * 5 + 16 * agent, node / 4).  actions int64 [B, A], -1 (DEFAULT_ACTION) for rows without a legal node. */
+int sy_masked_sample(const float* logits, const uint8_t* mask, int32_t num_envs, int32_t num_agents, int32_t num_nodes,
+                     int32_t env_offset, uint64_t seed, uint32_t step_counter, int32_t greedy, int64_t* actions,
+                     sy_policy_stream_t stream);
 
 /* CentralCritic.forward (mappo_agent.py:32-44): values [M] = W2 relu(W1 x + b1) + b2 for global_obs [M, D];
  * params: W1 [H, D], b1 [H], W2 [H], b2 [1]. */

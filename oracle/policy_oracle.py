@@ -122,3 +122,44 @@ def critic_value(x, sd, dtype=np.float64) -> float:
     f = lambda k: np.asarray(sd[k], dtype=dtype)  # noqa: E731
     h = np.maximum(f("critic.0.weight") @ np.asarray(x, dtype=dtype) + f("critic.0.bias"), 0)
     return float((f("critic.2.weight") @ h + f("critic.2.bias")).reshape(-1)[0])
+
+
+# ------------------------------------------------------------------------------------------ GNN, second restatement
+def gnn_forward_message_passing(x, edge_links, sd, epsilon=0.1, gamma=0.1):
+    """GNNModel.forward again, written INDEPENDENTLY of `gnn_forward` as literal message passing in Python floats (no
+    matrix algebra, no NumPy scatter): the way torch_geometric.nn.MessagePassing executes GCNConv --
+    add_remaining_self_loops, degree by counting incoming edges at the TARGET (flow = source_to_target), one message
+    norm(e) * lin(x)[source] per edge summed at its target -- and AntiSymmetricConv.forward's update line by line.
+    The two restatements must agree to 1e-12 (tests/test_policy_oracle.py); neither is pinned to the real module
+    (torch_geometric is absent here: parity unpinned, see oracle/gen_gnn_golden.py)."""
+    x = [[float(v) for v in row] for row in np.asarray(x, dtype=np.float64)]
+    n, K = len(x), len(x[0])
+    edges = [(int(s), int(d)) for s, d in np.asarray(edge_links)]
+    edges += [(v, v) for v in range(n)]  # self-loops (create_graph_data's edge lists never contain one)
+
+    def lin(mat, vec):  # nn.Linear without bias: y = W vec
+        return [sum(float(mat[c][k]) * vec[k] for k in range(len(vec))) for c in range(len(mat))]
+
+    def conv(x, W, bias, theta):
+        deg = [0.0] * n
+        for _, d in edges:
+            deg[d] += 1.0
+        xl = [lin(theta, row) for row in x]  # GCNConv: x = self.lin(x) first, then propagate
+        agg = [[0.0] * K for _ in range(n)]
+        for s, d in edges:
+            norm = deg[s] ** -0.5 * deg[d] ** -0.5
+            for c in range(K):
+                agg[d][c] += norm * xl[s][c]
+        anti = [[float(W[r][c]) - float(W[c][r]) - (gamma if r == c else 0.0) for c in range(K)] for r in range(K)]
+        out = []
+        for v in range(n):
+            h = lin(anti, x[v])  # x @ antisymmetric_W.t()
+            out.append([x[v][c] + epsilon * float(np.tanh(h[c] + agg[v][c] + float(bias[c]))) for c in range(K)])
+        return out
+
+    f = lambda k: np.asarray(sd[k], dtype=np.float64)  # noqa: E731
+    for layer in ("conv1", "conv2"):
+        x = conv(x, f(f"{layer}.W"), f(f"{layer}.bias"), f(f"{layer}.phi.lin.weight"))
+        x = [[max(v, 0.0) for v in row] for row in x]
+    ow, ob = f("output_layer.weight").reshape(-1), float(f("output_layer.bias").reshape(-1)[0])
+    return np.asarray([sum(ow[c] * row[c] for c in range(K)) + ob for row in x], dtype=np.float64)

@@ -6,7 +6,7 @@ import os
 
 from ._cabi import SyError
 
-SY_POLICY_ABI_VERSION = 1
+SY_POLICY_ABI_VERSION = 2
 SY_FEATURES_ENV, SY_FEATURES_REFERENCE = 0, 1
 LIB_PATH = os.environ.get("SY_POLICY_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsy_policy.so")
 
@@ -36,6 +36,8 @@ SIGNATURES = {
                                C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sy_policy_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "sy_policy_check": (C.c_int, [C.c_void_p]),
+    "sy_masked_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32,
+                                   C.c_int32, C.c_void_p, C.c_void_p]),
     "sy_mappo_values": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

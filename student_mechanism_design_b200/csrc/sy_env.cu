@@ -2187,6 +2187,28 @@ __global__ void __launch_bounds__(256) sy_sample_actions_kernel(const Params p, 
 
 __global__ void sy_advance_counter_kernel(unsigned* counter, unsigned by) { *counter += by; }
 
+// trajectory recording: up to SY_MAX_COPY_SEGMENTS device-to-device copies in ONE launch (blockIdx.y =
+// segment) instead of one copy kernel per stored tensor and step
+struct CopySegments {
+  void* dst[SY_MAX_COPY_SEGMENTS];
+  const void* src[SY_MAX_COPY_SEGMENTS];
+  unsigned long long bytes[SY_MAX_COPY_SEGMENTS];
+};
+__global__ void __launch_bounds__(256) sy_copy_segments_kernel(const CopySegments c) {
+  const int sgm = blockIdx.y;
+  const unsigned long long n = c.bytes[sgm];
+  uint8_t* d = static_cast<uint8_t*>(c.dst[sgm]);
+  const uint8_t* sr = static_cast<const uint8_t*>(c.src[sgm]);
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(sr)) & 15u) == 0) {
+    const unsigned long long nv = n >> 4;
+    for (unsigned long long i = tid; i < nv; i += nth) reinterpret_cast<uint4*>(d)[i] = reinterpret_cast<const uint4*>(sr)[i];
+    for (unsigned long long i = (nv << 4) + tid; i < n; i += nth) d[i] = sr[i];
+  } else {
+    for (unsigned long long i = tid; i < n; i += nth) d[i] = sr[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // graph table construction
 // ---------------------------------------------------------------------------------------------
@@ -3569,6 +3591,26 @@ int sy_allreduce_stats(SyEnv* e, void* nccl_comm, int64_t* stats_local, int64_t*
   enum { NCCL_INT64 = 4, NCCL_SUM = 0 };  // nccl.h: ncclInt64, ncclSum
   const int nrc = g_nccl_allreduce(stats_local, stats_global, SY_NUM_STATS, NCCL_INT64, NCCL_SUM, nccl_comm, (cudaStream_t)stream);
   if (nrc != 0) return fail(SY_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl_errstr ? g_nccl_errstr(nrc) : "unknown NCCL error");
+  return SY_OK;
+}
+
+int sy_copy_segments(int32_t num_segments, void* const* dst, const void* const* src, const uint64_t* bytes, sy_stream_t stream) {
+  if (num_segments < 0 || num_segments > SY_MAX_COPY_SEGMENTS || (num_segments && (!dst || !src || !bytes)))
+    return fail(SY_ERR_INVALID_ARGUMENT, "0..%d segments with non-NULL pointer tables", SY_MAX_COPY_SEGMENTS);
+  if (num_segments == 0) return SY_OK;
+  CopySegments c{};
+  unsigned long long longest = 0;
+  for (int i = 0; i < num_segments; ++i) {
+    if (bytes[i] && (!dst[i] || !src[i])) return fail(SY_ERR_INVALID_ARGUMENT, "segment %d has a NULL pointer", i);
+    c.dst[i] = dst[i];
+    c.src[i] = src[i];
+    c.bytes[i] = bytes[i];
+    longest = std::max<unsigned long long>(longest, bytes[i]);
+  }
+  const unsigned gx = (unsigned)std::min<unsigned long long>(std::max<unsigned long long>((longest / 16 + 255) / 256, 1), 148 * 8);
+  sy_copy_segments_kernel<<<dim3(gx, (unsigned)num_segments), 256, 0, (cudaStream_t)stream>>>(c);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
   return SY_OK;
 }
 

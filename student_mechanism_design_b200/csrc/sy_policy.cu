@@ -476,6 +476,17 @@ struct MappoParams {
   unsigned seed_lo, seed_hi, step;
 };
 
+
+// MappoTrainer's observation of an agent built from the env state (mappo_trainer.py:171-199) when the caller passes
+// obs == NULL: MrX sees his own node (obs["MrX_pos"], one float), police officer i the nodes of all officers
+// (obs["Polices_pos"].sum(dim=1), P floats) -- raw node ids as float32, zero-padded to obs_size columns.
+__device__ __forceinline__ float mappo_obs_value(const MappoParams& p, int b, int a, int o) {
+  if (p.obs) return __ldg(p.obs + ((size_t)b * p.st.num_agents + a) * p.obs_size + o);
+  const int A = p.st.num_agents;
+  if (a == 0) return o == 0 ? (float)__ldg(p.st.pos + (size_t)b * A) : 0.0f;
+  return o < A - 1 ? (float)__ldg(p.st.pos + (size_t)b * A + 1 + o) : 0.0f;
+}
+
 __global__ void __launch_bounds__(MP_THREADS, 3) sy_mappo_act_kernel(const MappoParams p, int64_t* __restrict__ actions,
                                                                       float* __restrict__ log_probs, float* __restrict__ probs_out) {
   extern __shared__ __align__(16) float mp_smem[];
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(MP_THREADS, 3) sy_mappo_act_kernel(const Mappo
   const int tid = threadIdx.x;
   for (int i = tid; i < MP_ROWS * D; i += MP_THREADS) {
     const int r = i / D, o = i - r * D;
-    obs_s[i] = r < nrows ? __ldg(p.obs + ((size_t)(row0 + r) * A + a) * D + o) : 0.0f;
+    obs_s[i] = r < nrows ? mappo_obs_value(p, row0 + r, a, o) : 0.0f;
   }
   __syncthreads();
   // hidden layer: relu(W1 obs + b1); with HP dividing the block every thread keeps one hidden unit
@@ -832,7 +843,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) sy_mappo_act_tc_kernel(const Ma
     unsigned* vmask = vmask_all + buf * TC_ROWS * 8;
     for (int i = tid; i < TC_ROWS * D; i += TC_THREADS) {
       const int r = i / D, o = i - r * D;
-      obs_s[i] = r < nrows ? __ldg(p.obs + ((size_t)(row0 + r) * A + a) * D + o) : 0.0f;
+      obs_s[i] = r < nrows ? mappo_obs_value(p, row0 + r, a, o) : 0.0f;
     }
     for (int i = tid; i < TC_ROWS * 8; i += TC_THREADS) vmask[i] = 0u;
     __syncthreads();
@@ -1072,6 +1083,59 @@ int gnn_launch_shape(const SyPolicyGraphs* g, const SyPolicyState* st, unsigned&
   return SY_POLICY_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// sy_masked_sample: one node per (env, agent) from arbitrary policy logits restricted to the env's action mask -- the
+// batched form of the trainers' "pick among the valid moves" (gnn_trainer.py:221-229, mappo_agent.py:121-140) for a
+// policy that is NOT one of the two built-in agents (e.g. a torch module producing logits [B, A, N]).
+// greedy: first argmax over the legal nodes.  Otherwise Gumbel-max: argmax_j (logit_j + g_j), g_j = -log(-log u_j),
+// u_j from Philox(seed; env, step, RNG_MASKED_SAMPLE + 16 * agent, j / 4) -- an exact sample of softmax(logits | mask)
+// without normalising or a second pass.  Rows without a legal node get -1 (DEFAULT_ACTION).  One warp per row.
+// ---------------------------------------------------------------------------------------------
+enum { RNG_MASKED_SAMPLE = 5 };
+__global__ void __launch_bounds__(256) sy_masked_sample_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ mask, int rows,
+                                                               int A, int N, int env_offset, unsigned seed_lo, unsigned seed_hi,
+                                                               unsigned step, int greedy, int64_t* __restrict__ actions) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int b = row / A, a = row - b * A;
+  const float* lg = logits + (size_t)row * N;
+  const uint8_t* mk = mask + (size_t)row * N;
+  float best = -INFINITY;
+  int arg = -1;
+  for (int j0 = lane * 4; j0 < N; j0 += 128) {  // a lane takes 4 consecutive nodes = one Philox block
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (!greedy) r = philox4x32(make_uint4((unsigned)(env_offset + b), step, (unsigned)(RNG_MASKED_SAMPLE + 16 * a), (unsigned)(j0 >> 2)), make_uint2(seed_lo, seed_hi));
+    const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + q;
+      if (j < N && mk[j]) {
+        float key = lg[j];
+        if (!greedy) {
+          const float u = ((float)(w[q] >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+          key -= __logf(-__logf(u));
+        }
+        if (key > best || arg < 0) {  // ascending j inside the lane: the first maximum wins
+          best = key;
+          arg = j;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (oa >= 0 && (arg < 0 || ob > best || (ob == best && oa < arg))) {
+      best = ob;
+      arg = oa;
+    }
+  }
+  if (lane == 0) actions[row] = (int64_t)arg;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1163,8 +1227,9 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
                  const float* params, const int32_t* policy_of_agent, int32_t max_degree, uint64_t seed, uint32_t step_counter,
                  int64_t* actions, float* log_probs, float* probs, sy_policy_stream_t stream) {
   if (int rc = check_common(graphs, state)) return rc;
-  if (!obs || !params || !policy_of_agent || !actions || !log_probs) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL MAPPO arguments");
+  if (!params || !policy_of_agent || !actions || !log_probs) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "NULL MAPPO arguments");
   if (obs_size < 1 || hidden < 1 || hidden > 1024) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad MAPPO layer sizes");
+  if (!obs && obs_size < state->num_agents - 1) return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "obs == NULL (trainer features) needs obs_size >= number of police");
   MappoParams p;
   std::memset(&p, 0, sizeof(p));
   p.g = *graphs;
@@ -1208,6 +1273,20 @@ int sy_mappo_act(const SyPolicyGraphs* graphs, const SyPolicyState* state, const
   CUDA_TRY(cudaFuncSetAttribute(sy_mappo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const dim3 grid((unsigned)((state->num_envs + MP_ROWS - 1) / MP_ROWS), (unsigned)state->num_agents);
   sy_mappo_act_kernel<<<grid, MP_THREADS, smem, (cudaStream_t)stream>>>(p, actions, log_probs, probs);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_POLICY_OK;
+}
+
+int sy_masked_sample(const float* logits, const uint8_t* mask, int32_t num_envs, int32_t num_agents, int32_t num_nodes,
+                     int32_t env_offset, uint64_t seed, uint32_t step_counter, int32_t greedy, int64_t* actions,
+                     sy_policy_stream_t stream) {
+  if (!logits || !mask || !actions || num_envs < 1 || num_agents < 1 || num_nodes < 1)
+    return fail(SY_POLICY_ERR_INVALID_ARGUMENT, "bad sy_masked_sample arguments");
+  const int rows = num_envs * num_agents;
+  sy_masked_sample_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(logits, mask, rows, num_agents, num_nodes, env_offset,
+                                                                                       (unsigned)(seed & 0xFFFFFFFFu), (unsigned)(seed >> 32),
+                                                                                       step_counter, greedy, actions);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   return SY_POLICY_OK;

@@ -248,21 +248,31 @@ class MappoPolicy(_PolicyBase):
         w2, b2 = cls._linear(1, hidden, gen)
         return {"critic.0.weight": w1, "critic.0.bias": b1, "critic.2.weight": w2, "critic.2.bias": b2}
 
-    def act(self, obs: torch.Tensor, step_counter: Optional[int] = None, return_probs: bool = False):
-        """obs float32 [B, A, obs_size] -> (actions int64 [B, A], log_probs float32 [B, A][, probs [B, A, N]])."""
+    def act(self, obs: Optional[torch.Tensor] = None, step_counter: Optional[int] = None, return_probs: bool = False,
+            out: Optional[torch.Tensor] = None):
+        """obs float32 [B, A, obs_size] -> (actions int64 [B, A], log_probs float32 [B, A][, probs [B, A, N]]).
+        obs=None: the kernel builds MappoTrainer's own observations from the env state (mappo_trainer.py:171-199: MrX
+        sees his node, every officer the officers' nodes; raw node ids, zero-padded to obs_size >= P) without any
+        observation tensor being materialised."""
         e = self.env
-        if tuple(obs.shape) != (e.num_envs, e.num_agents, self.obs_size) or obs.dtype != torch.float32:
-            raise ValueError(f"obs must be float32 {(e.num_envs, e.num_agents, self.obs_size)}")  # mappo_agent.py:21-28
-        obs = obs.contiguous()
+        if obs is None:
+            if self.obs_size < e.number_of_agents:
+                raise ValueError("obs=None (trainer features) needs obs_size >= number of police")
+        else:
+            if tuple(obs.shape) != (e.num_envs, e.num_agents, self.obs_size) or obs.dtype != torch.float32:
+                raise ValueError(f"obs must be float32 {(e.num_envs, e.num_agents, self.obs_size)}")  # mappo_agent.py:21-28
+            obs = obs.contiguous()
         if step_counter is None:
             step_counter = self.step_counter
             self.step_counter += 1
-        acts = torch.empty(e.num_envs, e.num_agents, dtype=torch.int64, device=e.device)
-        lp = torch.empty(e.num_envs, e.num_agents, dtype=torch.float32, device=e.device)
+        acts = out if out is not None else torch.empty(e.num_envs, e.num_agents, dtype=torch.int64, device=e.device)
+        if getattr(self, "_lp", None) is None:
+            self._lp = torch.empty(e.num_envs, e.num_agents, dtype=torch.float32, device=e.device)
+        lp = self._lp if out is not None else torch.empty(e.num_envs, e.num_agents, dtype=torch.float32, device=e.device)
         pr = torch.empty(e.num_envs, e.num_agents, self.N, dtype=torch.float32, device=e.device) if return_probs else None
         with torch.cuda.device(e.device):
             graphs = self._graphs()
-            pc.check(self._lib.sy_mappo_act(C.byref(graphs), C.byref(self._state()), obs.data_ptr(), self.obs_size,
+            pc.check(self._lib.sy_mappo_act(C.byref(graphs), C.byref(self._state()), _ptr(obs), self.obs_size,
                                             self.hidden, self.params.data_ptr(), self.policy_of_agent.ctypes.data,
                                             self._tables.max_degree if self.tensor_cores else 0,
                                             e.seed & 0xFFFFFFFFFFFFFFFF, int(step_counter) & 0xFFFFFFFF, acts.data_ptr(),

@@ -181,3 +181,90 @@ def test_mappo_matches_oracle_and_reference_goldens(torch_cuda):
             a_ref = int(gold[f"c{ci}_action"][t])
             np.testing.assert_allclose(po.categorical_log_prob(got, a_ref, np.float32), gold[f"c{ci}_logp"][t], rtol=2e-5, atol=2e-6)
             env.close()
+
+
+@pytest.mark.gpu
+def test_masked_sample_kernel(torch_cuda):
+    """sy_masked_sample: greedy == torch's first argmax over the legal nodes; sampling == Gumbel-max with
+    the documented Philox noise (recomputed on the CPU), rows without a legal node -> -1, frequencies follow
+    softmax(logits | mask)."""
+    import sy_oracle as so
+
+    torch = torch_cuda
+    pkg = _pkg()
+    from student_mechanism_design_b200.rollout import masked_sample, masked_sample_device
+
+    g = torch.Generator().manual_seed(1)
+    B, A, N = 16, 3, 37
+    logits = torch.randn(B, A, N, generator=g)
+    logits[1, 0, 5] = logits[1, 0, 9] = 7.0  # a tie: the first maximum wins
+    mask = torch.rand(B, A, N, generator=g) < 0.3
+    mask[1, 0, 5] = mask[1, 0, 9] = True
+    mask[0, 1] = False
+    lg, mk = logits.cuda(), mask.cuda()
+    greedy = masked_sample_device(lg, mk, greedy=True).cpu()
+    assert torch.equal(greedy, masked_sample(logits, mask, greedy=True)) and greedy[0, 1] == -1 and greedy[1, 0] == 5
+    seed, step, off = 1234567, 9, 100
+    got = masked_sample_device(lg, mk, seed=seed, step_counter=step, env_offset=off).cpu().numpy()
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    for b in range(B):
+        for a in range(A):
+            legal = np.nonzero(mask[b, a].numpy())[0]
+            if len(legal) == 0:
+                assert got[b, a] == -1
+                continue
+            keys = np.full(N, -np.inf)
+            for j in legal:
+                r = so.philox4x32((off + b, step, 5 + 16 * a, j >> 2), key)[j & 3]
+                u = ((r >> 8) + 0.5) / 16777216.0
+                keys[j] = float(logits[b, a, j]) - np.log(-np.log(u))
+            assert got[b, a] in legal and keys[got[b, a]] >= keys.max() - 1e-4, (b, a)
+    # distribution: 1 row replicated over many envs and steps
+    l1 = torch.tensor([0.0, 1.0, 2.0, 9.0, -1.0]).cuda().expand(4096, 1, 5).contiguous()
+    m1 = torch.tensor([True, True, True, False, True]).cuda().expand(4096, 1, 5).contiguous()
+    draws = torch.cat([masked_sample_device(l1, m1, seed=3, step_counter=s).flatten() for s in range(8)])
+    freq = torch.bincount(draws, minlength=5).float().cpu() / draws.numel()
+    want = torch.softmax(torch.tensor([0.0, 1.0, 2.0, -1e30, -1.0]), -1)
+    assert freq[3] == 0 and torch.allclose(freq, want, atol=0.015)
+
+
+@pytest.mark.gpu
+def test_mappo_trainer_observation_built_in_the_kernel(torch_cuda):
+    """sy_mappo_act with obs == NULL builds MappoTrainer's observations from the env state (mappo_trainer.py:171-199: MrX
+    <- MrX_pos, officer i <- Polices_pos.sum(dim=1)): bit-identical to passing that tensor explicitly, on both kernels
+    (tcgen05 and CUDA cores)."""
+    torch = torch_cuda
+    pkg = _pkg()
+    B, P, N = 300, 4, 60
+    env = pkg.BatchedScotlandYardEnv(B, P, 12, graph_nodes=N, graph_edges=110, seed=5, auto_reset=True)
+    env.reset()
+    env.rollout_random(3)
+    A = P + 1
+    pol = pkg.MappoPolicy(env, obs_size=A, hidden_size=64, seed=2)
+    obs = torch.zeros(B, A, A, device="cuda")
+    obs[:, 0, 0] = env.pos[:, 0].float()
+    obs[:, 1:, :P] = env.pos[:, 1:].float().unsqueeze(1).expand(B, P, P)
+    for tc in (True, False):
+        pol.tensor_cores = tc
+        a_ref, lp_ref, pr_ref = pol.act(obs, step_counter=4, return_probs=True)
+        a_new, lp_new, pr_new = pol.act(None, step_counter=4, return_probs=True)
+        assert torch.equal(a_ref, a_new) and torch.equal(lp_ref, lp_new) and torch.equal(pr_ref, pr_new), tc
+    env.close()
+
+
+@pytest.mark.gpu
+def test_copy_segments_records_a_transition_in_one_launch(torch_cuda):
+    torch = torch_cuda
+    _pkg()
+    from student_mechanism_design_b200.rollout import copy_segments
+
+    g = torch.Generator().manual_seed(0)
+    srcs = [torch.randint(0, 100, (1000, 7), generator=g, dtype=torch.int32).cuda(), torch.randn(333, generator=g).cuda(),
+            torch.randint(0, 2, (77,), generator=g, dtype=torch.uint8).cuda(),
+            torch.randint(0, 255, (121,), generator=g, dtype=torch.uint8).cuda()]
+    base = torch.zeros(4096, dtype=torch.uint8, device="cuda")
+    dsts = [torch.zeros_like(s) for s in srcs[:3]] + [base[3:3 + 121]]  # an unaligned destination: byte path
+    copy_segments(dsts, srcs)
+    torch.cuda.synchronize()
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
