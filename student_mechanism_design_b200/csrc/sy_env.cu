@@ -136,6 +136,8 @@ struct Params {
   int bel_fast, bel_off_out, bel_off_part, bel_off_pack, bel_off_ptr;  // belief fast path: dynamic smem layout (bytes)
   int wr_off, wr_off_csr, wr_img_stride, wr_stage_csr;  // writer warps: smem staging layout (bytes) and path flag
   int bel_share_csr;  // generic belief path gathers over the writers' staged CSR (+ 1/deg) instead of the global lists
+  int wr_img_rows;    // action_mask rows per writer image: A (a whole env) or 1 (large rows: saves shared memory)
+  int wr_off_pad;     // shared-CSR belief path: byte offset (from wr_off_csr) of the padded neighbour lists
   // bulk (TMA) writers: the tile's action_mask / node_features regions are contiguous byte streams cut into chunks of
   // wr_c_mask / wr_c_nf bytes (multiples of 16); each chunk is assembled in a per-warp shared-memory image and leaves
   // the SM with one cp.async.bulk.  0 = the LSU writers (unaligned caller buffers, or selected with sy_set_option)
@@ -1076,6 +1078,18 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
         s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
         s_perm[i] = __ldg(tb.deg_perm + (size_t)g0 * N + i);
       }
+      // padded neighbour lists for the belief gather: every node's list is a multiple of 4 node ids (pads point at the
+      // zero slot N), so the gather reads 4 ids with one 8-byte load and has no per-neighbour loop control
+      uint16_t* s_pptr = reinterpret_cast<uint16_t*>(dyn + p.wr_off_csr + p.wr_off_pad);  // [N + 1] list starts (entries)
+      uint16_t* s_pcol = s_pptr + ((N + 1 + 3) & ~3);                                        // 8-byte aligned
+      const int32_t* gpp = tb.pack_ptr + (size_t)g0 * (N + 1);
+      const int2* gpk = tb.nbr_pack + (size_t)g0 * tb.pack_stride;
+      const int npk = __ldg(gpp + N);
+      for (int i = tw; i <= N; i += WRW * 32) s_pptr[i] = (uint16_t)__ldg(gpp + i);
+      for (int k = tw; k < npk; k += WRW * 32) {
+        const int2 en = __ldg(gpk + k);  // {byte offset of the neighbour's row in the transposed tile, bits of 1/deg}; pads are {0, 0}
+        s_pcol[k] = en.y ? (uint16_t)((unsigned)en.x / (BSTRIDE * 4u)) : (uint16_t)N;
+      }
     }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
@@ -1083,36 +1097,51 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
   // the staged CSR is complete: release the belief warps that gather over it (arrive only: the writers do not wait)
   if (p.bel_share_csr) asm volatile("bar.arrive 3, %0;\n" ::"r"(THREADS) : "memory");
   int* fpos = s_fpos + w * SY_MAX_AGENTS;
-  const int lpa = 32 / A;
+  const int R = p.wr_img_rows;       // mask rows per image: A (whole env) or 1 (large rows)
+  const int lpa = R == 1 ? 32 : 32 / A;  // lanes that share one agent's neighbour list
   for (int e = w; e < nEnv; e += WRW) {
     const int b = tile0 + e;
-    uint8_t* mask = p.ob.action_mask + (size_t)b * A * N;
     float* nf = p.ob.node_features + (size_t)b * N * A;
-    const int phase = (int)(reinterpret_cast<uintptr_t>(mask) & 15u);
-    uint8_t* img = s_img + phase;  // same 16-byte phase as the destination
-    // ---- ones of this env into the shared-memory image (action_mask.py:65-76: adjacent and weight + toll <= budget)
-    const int ag = lane / lpa, sub = lane - ag * lpa;  // lpa lanes share one agent's neighbour list
-    if (ag < A && !(p.dbg_skip & 2)) {
-      const int u = s_pos[e * A + ag], m = s_money[e * A + ag], g = s_gid[e];
-      uint8_t* row = img + ag * N;
-      if (staged) {
-        const int r0 = s_rp[u], r1 = s_rp[u + 1];
-        for (int k = r0 + sub; k < r1; k += lpa)
-          if ((int)s_wgt[k] + p.toll <= m) row[s_col[k]] = 1;
-      } else {
-        const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1) + u;
-        const int r0 = __ldg(rp), r1 = __ldg(rp + 1);
-        const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
-        const uint8_t* wg = tb.wgt + (size_t)g * tb.nnz_stride;
-        for (int k = r0 + sub; k < r1; k += lpa)
-          if ((int)__ldg(wg + k) + p.toll <= m) row[__ldg(cl + k)] = 1;
+    // yard.py:279-290: one-hot positions; the MrX column stays blank while he is hidden
+    if (lane < A) fpos[lane] = (lane > 0 || s_rev[e] >= 0) ? s_pos[e * A + lane] * A + lane : -1;
+    for (int a0 = 0; a0 < A; a0 += R) {
+      uint8_t* mask = p.ob.action_mask + ((size_t)b * A + a0) * N;
+      const int phase = (int)(reinterpret_cast<uintptr_t>(mask) & 15u);
+      uint8_t* img = s_img + phase;  // same 16-byte phase as the destination
+      // ---- ones of these rows into the shared-memory image (action_mask.py:65-76: adjacent and weight + toll <= budget)
+      const int ag = a0 + lane / lpa, sub = lane % lpa;
+      if (ag < A && lane / lpa < R && !(p.dbg_skip & 2)) {
+        const int u = s_pos[e * A + ag], m = s_money[e * A + ag], g = s_gid[e];
+        uint8_t* row = img + (ag - a0) * N;
+        if (staged) {
+          const int r0 = s_rp[u], r1 = s_rp[u + 1];
+          for (int k = r0 + sub; k < r1; k += lpa)
+            if ((int)s_wgt[k] + p.toll <= m) row[s_col[k]] = 1;
+        } else {
+          const int32_t* rp = tb.row_ptr + (size_t)g * (N + 1) + u;
+          const int r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          const uint16_t* cl = tb.col + (size_t)g * tb.nnz_stride;
+          const uint8_t* wg = tb.wgt + (size_t)g * tb.nnz_stride;
+          for (int k = r0 + sub; k < r1; k += lpa)
+            if ((int)__ldg(wg + k) + p.toll <= m) row[__ldg(cl + k)] = 1;
+        }
       }
-      // yard.py:279-290: one-hot positions; the MrX column stays blank while he is hidden
-      if (sub == 0) fpos[ag] = (ag > 0 || s_rev[e] >= 0) ? u * A + ag : -1;
+      __syncwarp();
+      warp_copy_bytes(mask, img, min(R, A - a0) * N, lane);
+      if (a0 + R < A) {  // more rows of this env follow: clear the image for them
+        __syncwarp();
+        for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+      }
     }
     __syncwarp();
-    warp_copy_bytes(mask, img, A * N, lane);
-    if (p.ob.node_features_u8) {  // byte one-hot: same image-and-copy scheme as the mask (no byte-sized global stores)
+    if (p.ob.node_features_u8 && R != A) {
+      // large rows keep only one mask row in the image: the byte one-hot is zero-filled and its (at most A) ones stored as bytes
+      uint8_t* nf8 = p.ob.node_features_u8 + (size_t)b * N * A;
+      warp_zero_bytes(nf8, N * A, lane);
+      __syncwarp();
+      if (lane < A && fpos[lane] >= 0) nf8[fpos[lane]] = 1;
+    } else if (p.ob.node_features_u8) {  // byte one-hot: same image-and-copy scheme as the mask (no byte-sized global stores)
       __syncwarp();
       for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
       __syncwarp();
@@ -1389,6 +1418,17 @@ __device__ __forceinline__ bool stage_tile_inputs(const Params& p, unsigned char
         s_inv[i] = __ldg(tb.inv_deg + (size_t)g0 * N + i);
         s_perm[i] = __ldg(tb.deg_perm + (size_t)g0 * N + i);
       }
+      // padded neighbour lists of the belief gather (see writer_role)
+      uint16_t* s_pptr = reinterpret_cast<uint16_t*>(dyn + p.wr_off_csr + p.wr_off_pad);
+      uint16_t* s_pcol = s_pptr + ((N + 1 + 3) & ~3);
+      const int32_t* gpp = tb.pack_ptr + (size_t)g0 * (N + 1);
+      const int2* gpk = tb.nbr_pack + (size_t)g0 * tb.pack_stride;
+      const int npk = __ldg(gpp + N);
+      for (int i = tw; i <= N; i += NTHREADS) s_pptr[i] = (uint16_t)__ldg(gpp + i);
+      for (int k = tw; k < npk; k += NTHREADS) {
+        const int2 en = __ldg(gpk + k);
+        s_pcol[k] = en.y ? (uint16_t)((unsigned)en.x / (BSTRIDE * 4u)) : (uint16_t)N;
+      }
     }
   }
   return staged;
@@ -1459,6 +1499,8 @@ __device__ __forceinline__ void ce_flush(const Params& p, const CeAcc& acc, int 
 }
 
 struct SharedCsr {  // the writer warps' staged copy of the tile's graph (null rp: not available)
+  const uint16_t* pptr;  // padded neighbour lists: starts [N + 1] (multiples of 4) ...
+  const uint16_t* pcol;  // ... and node ids, pads = N (the zero slot of the row)
   const int* rp;
   const uint16_t* col;
   const float* inv;
@@ -1497,23 +1539,27 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
         _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
       }
     } else if (sc.rp) {
-      // gather over the staged CSR: same neighbour order and the same 1/deg values as the padded global lists, so the
-      // result is bit-identical; every operand comes from shared memory
+      // gather over the staged CSR, every operand from shared memory.  The row is pre-scaled once, conflict-free, to
+      // w[i] = b[i] / deg(i) / sum(b), so the random-access gather reads ONE value per neighbour (it was two: b[i] and
+      // 1/deg(i)) and the result needs no further normalisation: a third fewer (bank-conflicted) shared-memory reads on
+      // the path that bounds the large-N configurations.
       const float inv = 1.0f / tot;
+      _Pragma("unroll 4") for (int j = lane; j < N; j += 32) sb[j] *= sc.inv[j] * inv;  // (isolated nodes: 1/deg = 0, handled below)
+      if (lane == 0) sb[N] = 0.0f;  // what the pads of the neighbour lists read
+      __syncwarp();
       _Pragma("unroll 1") for (int jj = lane; jj < N; jj += 32) {
-        const int j = sc.perm[jj];
-        const int r0 = sc.rp[j], r1 = sc.rp[j + 1];
+        const int j = sc.perm[jj];  // degree order: the 32 lanes of a step walk lists of (nearly) equal length
+        const int r0 = sc.pptr[j], r1 = sc.pptr[j + 1];
         float a = 0.0f;
-        _Pragma("unroll 2") for (int k = r0; k < r1; ++k) {
-          const int i = sc.col[k];
-          a = fmaf(sb[i], sc.inv[i], a);
+        _Pragma("unroll 2") for (int k = r0; k < r1; k += 4) {  // 4 neighbour ids per 8-byte load, no per-neighbour control flow
+          const uint2 c4 = *reinterpret_cast<const uint2*>(sc.pcol + k);
+          a += (sb[c4.x & 0xffffu] + sb[c4.x >> 16]) + (sb[c4.y & 0xffffu] + sb[c4.y >> 16]);
         }
-        if (r0 == r1) a = sb[j];  // isolated node keeps its mass (belief_module.py:93-97)
-        const float v = a * inv;
+        if (r0 == r1) a = bel[j] * inv;  // isolated node keeps its mass (belief_module.py:93-97); bel[j] is still the input
         if (!score) {
-          bel[j] = v;
+          bel[j] = a;
         } else {
-          const float c = ce_clip(v);
+          const float c = ce_clip(a);
           S += c;
           if (j == x) vx = c;
         }
@@ -1614,13 +1660,15 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
   const int gfirst = __shfl_sync(FULL, g, 0);
   const bool fast = p.bel_fast && prop && __all_sync(FULL, !((prop >> lane) & 1u) || g == g0);
   if (!fast) {
-    float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * N;
-    SharedCsr sc{nullptr, nullptr, nullptr, nullptr};
+    float* sb = reinterpret_cast<float*>(dyn) + (size_t)w * (N + 1);  // + 1: the zero slot the padded lists point at
+    SharedCsr sc{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (p.bel_share_csr && __all_sync(FULL, lane >= nEnv || g == gfirst)) {  // the writers' `staged` condition
       sc.rp = reinterpret_cast<const int*>(dyn + p.wr_off_csr);
       sc.col = reinterpret_cast<const uint16_t*>(sc.rp + N + 1);
       sc.inv = reinterpret_cast<const float*>(dyn + p.wr_off_csr + (((N + 1) * 4 + p.tb.nnz_stride * 3 + 3) & ~3));
       sc.perm = reinterpret_cast<const uint16_t*>(sc.inv + N);
+      sc.pptr = reinterpret_cast<const uint16_t*>(dyn + p.wr_off_csr + p.wr_off_pad);
+      sc.pcol = sc.pptr + ((N + 1 + 3) & ~3);
     }
     for (int e = w; e < nEnv; e += BW) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
     ce_flush(p, ce, lane);
@@ -2571,7 +2619,7 @@ struct SyEnv {
   void* d_cov = nullptr;
   size_t bel_smem = 0;  // dynamic smem of the step / reset kernels (belief scratch)
   int bel_fast = 0, bel_off_out = 0, bel_off_part = 0, bel_off_pack = 0, bel_off_ptr = 0;
-  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0;
+  int wr_off = 0, wr_off_csr = 0, wr_img_stride = 0, wr_stage_csr = 0, bel_share_csr = 0, wr_img_rows = 0, wr_off_pad = 0;
   int wr_c_mask = 0, wr_c_nf32 = 0, wr_c_nf8 = 0, wr_img_bytes = 0;  // bulk writers: chunk sizes per stream, image size
   // fused persistent step kernel (sy_step_fused_kernel): plan made with the graph tables
   bool fused_ok = false;
@@ -2787,6 +2835,8 @@ int fill_params(const SyEnv* env, const SyState* st, const SyObs* ob, const SyOu
   p.wr_off_csr = env->wr_off_csr;
   p.wr_img_stride = env->wr_img_stride;
   p.wr_stage_csr = env->wr_stage_csr;
+  p.wr_img_rows = env->wr_img_rows;
+  p.wr_off_pad = env->wr_off_pad;
   p.bel_share_csr = (p.dbg_skip & 5) ? 0 : env->bel_share_csr;  // the hand-over barrier needs both roles
   p.st = *st;
   if (ob) p.ob = *ob;
@@ -3042,7 +3092,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   e->bel_smem = 0;
   e->bel_fast = 0;
   if (e->cfg.belief) {
-    size_t generic = (size_t)BEL_WARPS * N * sizeof(float);
+    size_t generic = (size_t)BEL_WARPS * (N + 1) * sizeof(float);
     auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t off_out = up16((size_t)N * BSTRIDE * sizeof(float));
     const size_t off_part = up16(2 * off_out);
@@ -3061,14 +3111,17 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     if (!e->bel_fast && THREADS / 32 > GEN_BEL_WARPS) {  // the generic path is the critical role: give it more warps
       e->bel_warps = GEN_BEL_WARPS;
       e->wr_warps = GEN_WR_WARPS;
-      generic = (size_t)e->bel_warps * N * sizeof(float);
+      generic = (size_t)e->bel_warps * (N + 1) * sizeof(float);
     }
     e->bel_smem = e->bel_fast && fast > generic ? fast : generic;
     if (e->bel_smem > 180 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes too large for the belief kernel's shared memory");
   }
   {  // writer staging area: pos, money [TILE, A], revealed, graph id [TILE], per-warp flat one-hot indices and
      // action_mask images, then (optionally) the graph's CSR
-    const size_t img_stride = (((size_t)e->A * N + 16) + 15) & ~(size_t)15;
+    // mask image of a writer warp: a whole env (A rows) or, for large rows, ONE row at a time -- the shared memory that
+    // saves pays for the padded neighbour lists of the large-N belief path
+    e->wr_img_rows = (size_t)e->A * N > 4096 ? 1 : e->A;
+    const size_t img_stride = (((size_t)e->wr_img_rows * N + 16) + 15) & ~(size_t)15;
     const size_t base_lsu = ((size_t)2 * TILE * e->A + 2 * TILE + e->wr_warps * SY_MAX_AGENTS) * sizeof(int) + e->wr_warps * img_stride;
     // bulk writers: one zero page + two chunk images for each of the (at most BULK_WARPS) streaming warps
     const int nbw = std::min(e->wr_warps, BULK_WARPS);
@@ -3081,11 +3134,13 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     // generic (large-N) belief path: it gathers over the same staged CSR, plus the 1/deg row, instead of walking the
     // neighbour lists in global memory (at N = 1000 they no longer fit the L1 left over by the shared-memory carve-out)
     const bool share = e->cfg.belief && !e->bel_fast;
-    const size_t csr = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + (share ? (size_t)N * (sizeof(float) + sizeof(uint16_t)) : 0) + 16;
+    const size_t csr_core = ((((size_t)(N + 1) * sizeof(int) + (size_t)nnz_stride * 3) + 3) & ~(size_t)3) + (share ? (size_t)N * (sizeof(float) + sizeof(uint16_t)) : 0);
+    e->wr_off_pad = (int)((csr_core + 15) & ~(size_t)15);
+    const size_t csr = (share ? (size_t)e->wr_off_pad + ((size_t)((N + 1 + 3) & ~3) + pack_stride) * sizeof(uint16_t) : csr_core) + 16;
     e->wr_off = (int)((e->bel_smem + 15) & ~(size_t)15);
     e->wr_img_stride = (int)img_stride;
     e->wr_off_csr = (int)(((size_t)e->wr_off + base + 15) & ~(size_t)15);
-    e->wr_stage_csr = (csr <= 32 * 1024 && (size_t)e->wr_off_csr + csr <= 200 * 1024) ? 1 : 0;
+    e->wr_stage_csr = (csr <= 48 * 1024 && pack_stride < 65536 && (size_t)e->wr_off_csr + csr <= 200 * 1024) ? 1 : 0;
     e->bel_share_csr = (share && e->wr_stage_csr) ? 1 : 0;
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");

@@ -76,7 +76,10 @@ class _PolicyBase:
         self._tables: Optional[_GraphTables] = None
 
     def _graphs(self) -> pc.SyPolicyGraphs:
-        if self._tables is None or self._tables.graphs_id != id(self.env.graphs):
+        # a refreshed device pool (env.regenerate_graphs) bumps the generation; `id(list)` alone can be recycled by a
+        # new list at the same address, so both are compared
+        if self._tables is None or self._tables.graphs_id != id(self.env.graphs) or \
+                self._tables.generation != self.env._gen["generation"]:
             self._tables = _GraphTables(self.env)
         return self._tables.struct
 
