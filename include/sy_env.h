@@ -178,8 +178,14 @@ void sy_destroy(SyEnv* env);
  *                       fill of node_features (63 % of a step's bytes, independent of the state) is handed to the TMA
  *                       engine by its own small kernel NEXT TO the dynamics kernel (second stream), then the belief
  *                       propagation and the writers of the ones run as two concurrent kernels; all joined on the
- *                       caller's stream before sy_step returns (events; capturable).  Measured slower. */
-enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2 };
+ *                       caller's stream before sy_step returns (events; capturable).  Measured slower.
+ *   SY_OPT_LAGGED_KERNEL 0 (default): a deferred step with pending observations is two launches (observation kernel, then
+ *                       dynamics kernel).  1: ONE launch (sy_step_lagged_kernel: the pending observation roles + the
+ *                       dynamics warps of the next step in the same CTA) and sy_rollout_random* step deferred; shapes
+ *                       whose lagged kernel would not fit two CTAs per SM keep two launches.  Measured slower at c3
+ *                       (DESIGN.md 4c): the dynamics warps take 21 us per tile next to the store stream and hold the
+ *                       CTA's slot. */
+enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3 };
 enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
 enum { SY_STEP_FUSED = 0, SY_STEP_TWO_KERNELS = 1, SY_STEP_AUTO = 2 };
 int sy_set_option(SyEnv* env, int32_t option, int32_t value);
@@ -233,6 +239,22 @@ int sy_reset(SyEnv* env, const uint8_t* reset_mask, const int32_t* init_pos, con
  * actions int64 [B, A] (device): target node per agent; -1 = DEFAULT_ACTION / None. */
 int sy_step(SyEnv* env, const int64_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
             sy_stream_t stream);
+
+/* Software-pipelined stepping for policies that read only the compact state (SyState.pos / money, SyObs.agent_budget /
+ * mrx_revealed: the random policy, both reference agents' action selection -- gnn_agent.py:45-82 builds its features from
+ * positions, mappo_agent.py:87-142 from the budget / position vector).  sy_step_deferred = the dynamics of yard.py:144-269
+ * exactly as sy_step (state, rewards, flags, statistics are those of the new state when it completes), but the three
+ * dense observation tensors -- action_mask, node_features, belief_map -- of the NEW state are left pending.  The next
+ * sy_step_deferred writes them while it runs the following step's dynamics (one launch: the latency-bound dynamics hide
+ * under the HBM-bound observation stream of the same 32-env tile), so after every deferred call the dense tensors
+ * describe the state BEFORE that call.  sy_flush_observations writes whatever is pending (no-op otherwise); sy_step,
+ * sy_step_host*, sy_reset flush implicitly, so mixing the calls is always correct.  Pending observations are written
+ * into the SyObs of the call that carries them.  With SY_OPT_LAGGED_KERNEL on, sy_rollout_random / sy_rollout_random_dev
+ * step deferred and flush once at the end.  sy_observations_pending: 1 while a flush is owed. */
+int sy_step_deferred(SyEnv* env, const int64_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
+                     sy_stream_t stream);
+int sy_flush_observations(SyEnv* env, const SyState* state, const SyObs* obs, sy_stream_t stream);
+int sy_observations_pending(SyEnv* env);
 
 /* HOST pointers (pinned memory recommended) that `sy_step_host` fills; any member may be NULL. */
 typedef struct SyHostOut {

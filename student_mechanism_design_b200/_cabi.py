@@ -86,6 +86,9 @@ SIGNATURES = {
     "sy_step_host_i16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                    C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),
     "sy_sample_actions_i16": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.c_uint32, C.c_void_p, C.c_void_p]),
+    "sy_step_deferred": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
+    "sy_flush_observations": (C.c_int, [C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.c_void_p]),
+    "sy_observations_pending": (C.c_int, [C.c_void_p]),
     "sy_step_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs), C.POINTER(SyOut), C.c_void_p]),
     "sy_step_host_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(SyState), C.POINTER(SyObs),
                                    C.POINTER(SyOut), C.POINTER(SyHostOut), C.c_void_p]),

@@ -161,6 +161,16 @@ struct Params {
 };
 
 
+#ifdef SY_FUSED_CLOCKS  // profiling builds: per-role time inside the fused kernel, summed over CTAs (sy_debug_fused_clocks)
+__device__ unsigned long long g_fused_clk[16];
+#define FCLK_ADD(slot, v) do { if (lane == 0) atomicAdd(&g_fused_clk[slot], (unsigned long long)(v)); } while (0)
+#define FCLK_NOW() clock64()
+#else
+#define FCLK_ADD(slot, v) do { } while (0)
+#define FCLK_NOW() 0ll
+#pragma nv_diag_suppress 177
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (same constants / counter layout as oracle/sy_oracle.py:philox4x32)
 // ---------------------------------------------------------------------------------------------
@@ -304,8 +314,24 @@ struct WarpTile {
 // pulled into registers (loops fully unrolled over MAXA with predicates, so indexing is static and the rule runs on
 // register compares instead of a chain of dependent shared-memory loads); an agent's own node does not change before
 // its own move, so all A edge-weight lookups are issued up front (one round trip).
+// the tile's graph as staged in shared memory by the observation writers of the same CTA (lagged kernel): row
+// pointers, neighbours, weights.  Under a saturated store stream every global load of the dynamics queues behind the
+// writers' stores in the SM's memory pipeline (~1 us per dependent round trip), so the edge-weight lookups of the
+// moves and the neighbour walk of the action draw read this copy instead of the L1/L2-resident pool tables.
+struct SharedGraph {
+  const int* rp;
+  const uint16_t* col;
+  const uint8_t* wgt;
+};
+__device__ __forceinline__ int edge_weight_sg(const SharedGraph& sg, int u, int v) {
+  int w = 0;
+  for (int k = sg.rp[u], r1 = sg.rp[u + 1]; k < r1; ++k) w = (sg.col[k] == v) ? (int)sg.wgt[k] : w;
+  return w;
+}
+
 template <int MAXA, typename PosT>
-__device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money, const int* act, int g, int t, int& spent, int& moves) {
+__device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money, const int* act, int g, int t, int& spent, int& moves,
+                                          const SharedGraph* sg = nullptr) {
   const Tables& tb = p.tb;
   const int N = p.N, P = p.P;
   int rp[MAXA], rm[MAXA], ra[MAXA], wpre[MAXA];
@@ -317,7 +343,8 @@ __device__ __forceinline__ int move_phase(const Params& p, PosT* pos, int* money
     ra[i] = valid ? act[i] : -1;
   }
 #pragma unroll
-  for (int i = 0; i < MAXA; ++i) wpre[i] = (i <= P && ra[i] >= 0) ? edge_weight(tb, N, g, rp[i], ra[i]) : 0;
+  for (int i = 0; i < MAXA; ++i)
+    wpre[i] = (i <= P && ra[i] >= 0) ? (sg ? edge_weight_sg(*sg, rp[i], ra[i]) : edge_weight(tb, N, g, rp[i], ra[i])) : 0;
   {  // MrX: legal target or stay; may not step onto a police node (yard.py:161-188)
     int tgt = rp[0];
     if (ra[0] >= 0 && wpre[0] > 0 && wpre[0] + p.toll <= rm[0]) tgt = ra[0];
@@ -522,9 +549,15 @@ struct LogicSmem {
 #ifndef SY_VISIT_PREFETCH
 #define SY_VISIT_PREFETCH 1
 #endif
-// one 32-env tile by LOGIC_THREADS threads (tid = 0 .. LOGIC_THREADS-1); BAR is the named barrier they share
-template <int MODE, int MAXA, int BAR>
-__device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm, int b0, int tid) {
+// one 32-env tile by LOGIC_THREADS threads (tid = 0 .. LOGIC_THREADS-1); BAR is the named barrier they share.
+// LAGT > 0 (sy_step_lagged_kernel): the observation roles of the same CTA are still describing the tile's PREVIOUS
+// state; the new state is only written back after all of them have taken their copy of the old one (named barrier
+// LAG_BAR, LAGT threads: the observation warps arrive, the dynamics warps wait -- long after the arrival in practice).
+constexpr int LAG_BAR = 4;
+constexpr int LAG_CSR_BAR = 6;  // lagged kernel: the writers' staged graph is complete (writers arrive, dynamics warps wait)
+template <int MODE, int MAXA, int BAR, int LAGT = 0, int CSRT = 0>
+__device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm, int b0, int tid, const SharedGraph* sgp = nullptr,
+                                           const int* sg_valid = nullptr) {
   constexpr int DS = LogicSmem<MAXA>::DS;
   const int lane = tid & 31, warp = tid >> 5;
   const int nEnv = min(32, p.B - b0);
@@ -580,6 +613,11 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   }
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(0);
+  const SharedGraph* sg = nullptr;
+  if constexpr (CSRT > 0) {
+    asm volatile("bar.sync %0, %1;\n" ::"n"(LAG_CSR_BAR), "n"(CSRT) : "memory");
+    if (*sg_valid) sg = sgp;  // the tile sits on one graph and the writers staged it (CTA-uniform)
+  }
   const bool live = lane < nEnv;
   const int b = b0 + lane;
   const int t = sm.t[lane], g = sm.gid[lane], frozen = sm.frozen[lane];
@@ -596,7 +634,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   //             round trip of the read-modify-write overlaps the moves
   int spent = 0, moves = 0;
   if (warp == 0) {
-    if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent, moves);
+    if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent, moves, sg);
   } else if (warp == 1 && p.auto_reset && active) {
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
     const unsigned ep = (unsigned)(sm.episode[lane] + 1);
@@ -751,6 +789,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
 
   // ---- P4: new state back to HBM (coalesced), visit rows of freshly reset envs cleared (yard.py:85); the last warp
   // (lightest reward share) reduces the tile's episode statistics, off warp 0's critical path
+  if constexpr (LAGT > 0) asm volatile("bar.sync %0, %1;\n" ::"n"(LAG_BAR), "n"(LAGT) : "memory");
   if (warp == LOGIC_WARPS - 1 && p.out.stats) {
     const int st = sm.status[lane];
     const bool fin = active && st != ST_RUNNING;
@@ -826,20 +865,40 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
       const int e = (i * p.inv_A) >> 16, a = i - e * A;
       const int gg = sm.gid[e], u = (int)sm.pos[e * HS + a], m = sm.money[e * AS + a];
-      const int nvalid = move_count(p.tb, N, gg, u, m, p.toll);
+      // a same-step auto-reset with resample_graph may have moved the env to another graph than the staged one
+      const bool use_sg = sg != nullptr && !p.resample_graph;
+      int nvalid;
+      if (use_sg && sm.cnt_staged) {
+        const int c = min(m - p.toll, p.tb.wcap);
+        nvalid = c > 0 ? (int)sm.cnt[u * (p.tb.wcap + 1) + c] : 0;
+      } else {
+        nvalid = move_count(p.tb, N, gg, u, m, p.toll);
+      }
       long long act = -1;
       if (nvalid > 0) {
         const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)(b0 + e));
         const uint4 r = philox4x32(make_uint4(env_id, ctr, RNG_ACTION, (unsigned)a), make_uint2(p.seed_lo, p.seed_hi));
         int pick = (int)__umulhi(r.x, (unsigned)nvalid);
-        const uint8_t* wg = p.tb.wgt + (size_t)gg * p.tb.nnz_stride;
-        for (int k = __ldg(p.tb.row_ptr + (size_t)gg * (N + 1) + u);; ++k) {  // the pick-th affordable neighbour exists
-          if (__ldg(wg + k) + p.toll <= m) {
-            if (pick == 0) {
-              act = __ldg(p.tb.col + (size_t)gg * p.tb.nnz_stride + k);
-              break;
+        if (use_sg) {
+          for (int k = sg->rp[u];; ++k) {  // the pick-th affordable neighbour exists
+            if ((int)sg->wgt[k] + p.toll <= m) {
+              if (pick == 0) {
+                act = sg->col[k];
+                break;
+              }
+              --pick;
             }
-            --pick;
+          }
+        } else {
+          const uint8_t* wg = p.tb.wgt + (size_t)gg * p.tb.nnz_stride;
+          for (int k = __ldg(p.tb.row_ptr + (size_t)gg * (N + 1) + u);; ++k) {  // the pick-th affordable neighbour exists
+            if (__ldg(wg + k) + p.toll <= m) {
+              if (pick == 0) {
+                act = __ldg(p.tb.col + (size_t)gg * p.tb.nnz_stride + k);
+                break;
+              }
+              --pick;
+            }
           }
         }
       }
@@ -1038,8 +1097,9 @@ __device__ __forceinline__ void warp_write_node_features(float* nf, int n, const
 // on one graph and its CSR fits -- the graph's row pointers / neighbours / weights.  Each env's action_mask rows are
 // assembled in a per-warp shared-memory image and copied out, node_features are zero-filled and the (at most A) chunks
 // with a one rewritten whole: no byte-sized stores anywhere (they cost 60 % extra time when tried).
-template <int WRW, bool PREFILLED = false>
-__device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
+template <int WRW, bool PREFILLED = false, int LAGT = 0, int CSRT = 0>
+__device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane,
+                                            int* lag_staged = nullptr) {
   const Tables& tb = p.tb;
   const int N = p.N, A = p.A;
   int* s_pos = reinterpret_cast<int*>(dyn + p.wr_off);  // [TILE * A]
@@ -1093,9 +1153,15 @@ __device__ __forceinline__ void writer_role(const Params& p, unsigned char* dyn,
     }
   }
   for (int i = lane * 16; i < p.wr_img_stride; i += 32 * 16) *reinterpret_cast<uint4*>(s_img + i) = make_uint4(0, 0, 0, 0);
+  if constexpr (CSRT > 0) {
+    if (tw == 0) *lag_staged = staged ? 1 : 0;
+  }
   named_barrier(2, WRW * 32);
   // the staged CSR is complete: release the belief warps that gather over it (arrive only: the writers do not wait)
   if (p.bel_share_csr) asm volatile("bar.arrive 3, %0;\n" ::"r"(THREADS) : "memory");
+  if constexpr (CSRT > 0) asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_CSR_BAR), "n"(CSRT) : "memory");  // ... and the dynamics warps
+  // the tile's state is in shared memory: the dynamics warps of a lagged step may replace it
+  if constexpr (LAGT > 0) asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_BAR), "n"(LAGT) : "memory");
   int* fpos = s_fpos + w * SY_MAX_AGENTS;
   const int R = p.wr_img_rows;       // mask rows per image: A (whole env) or 1 (large rows)
   const int lpa = R == 1 ? 32 : 32 / A;  // lanes that share one agent's neighbour list
@@ -1507,20 +1573,18 @@ struct SharedCsr {  // the writer warps' staged copy of the tile's graph (null r
   const uint16_t* perm;  // nodes by degree: the 32 lanes of a gather step walk lists of (nearly) equal length
 };
 
-__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int lane, CeAcc& ce, const SharedCsr sc) {
+__device__ void belief_env_generic(const Params& p, float* sb, int b, int op, int g, int x, int lane, CeAcc& ce, const SharedCsr sc) {
   const int N = p.N;
   const Tables& tb = p.tb;
   float* bel = p.st.belief + (size_t)b * N;
   const float unif = 1.0f / (float)N;
   const bool score = op == BEL_DELTA && p.belief_score && p.out.stats != nullptr;  // reveal: score the prediction, then collapse it
-  const int x = op == BEL_DELTA ? __ldcg(p.st.pos + (size_t)b * p.A) : -1;
   if (op == BEL_UNIFORM) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
   } else if (op == BEL_DELTA && !score) {
     _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = (j == x) ? 1.0f : 0.0f;
   } else if (op == BEL_PROPAGATE || score) {
     float S = 0.0f, vx = 0.0f;
-    const int g = __ldcg(p.st.graph_id + b);
     const int32_t* gptr = tb.pack_ptr + (size_t)g * (N + 1);
     const int2* gpack = tb.nbr_pack + (size_t)g * tb.pack_stride;
     __syncwarp();
@@ -1639,14 +1703,22 @@ __device__ void belief_env_generic(const Params& p, float* sb, int b, int op, in
   }
 }
 
-template <int BW>
+template <int BW, int LAGT = 0>
 __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn, int tile0, int nEnv, int w, int lane) {
   const int N = p.N;
   // every belief warp reads the same 32 flags / graph ids, so the branches below are uniform across the role
-  int op = BEL_KEEP, g = -1;
+  int op = BEL_KEEP, g = -1, xm = -1;
   if (lane < nEnv) {
     op = __ldcg(p.bel_flags + tile0 + lane);
     g = __ldcg(p.st.graph_id + tile0 + lane);
+    if (op == BEL_DELTA) xm = __ldcg(p.st.pos + (size_t)(tile0 + lane) * p.A);  // MrX's node (the reveal collapses the map onto it)
+  }
+  if constexpr (LAGT > 0) {
+    // everything this role reads of the tile's state is in registers (the count operand makes the arrival wait for the
+    // loads): the dynamics warps of the CTA may now replace the state
+    int dep;
+    asm volatile("and.b32 %0, %1, 0;\n" : "=r"(dep) : "r"(op | g | xm));
+    asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_BAR), "r"(LAGT + dep) : "memory");
   }
   // rows that go through the propagation: moving envs, plus revealed ones while their prediction is being scored
   const bool score = p.belief_score && p.out.stats != nullptr;
@@ -1670,7 +1742,8 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
       sc.pptr = reinterpret_cast<const uint16_t*>(dyn + p.wr_off_csr + p.wr_off_pad);
       sc.pcol = sc.pptr + ((N + 1 + 3) & ~3);
     }
-    for (int e = w; e < nEnv; e += BW) belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), lane, ce, sc);
+    for (int e = w; e < nEnv; e += BW)
+      belief_env_generic(p, sb, tile0 + e, __shfl_sync(FULL, op, e), __shfl_sync(FULL, g, e), __shfl_sync(FULL, xm, e), lane, ce, sc);
     ce_flush(p, ce, lane);
     return;
   }
@@ -1778,7 +1851,7 @@ __device__ __forceinline__ void belief_role(const Params& p, unsigned char* dyn,
     } else if (ope == BEL_UNIFORM) {
       _Pragma("unroll 1") for (int j = lane; j < N; j += 32) bel[j] = unif;
     } else {
-      const int x = __ldcg(p.st.pos + (size_t)(tile0 + e) * p.A);
+      const int x = __shfl_sync(FULL, xm, e);
       if (score) {
         float tot = 0.0f, vx = 0.0f, S = 0.0f;
 #pragma unroll
@@ -1819,9 +1892,11 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
   const int nEnv = min(TILE, p.B - tile0);
   const int nbw = BW;  // without a belief map the belief warps simply exit
   if (warp < nbw && !p.belief_on) return;
+  const long long t0 = FCLK_NOW();
   if (warp < nbw) {
     if constexpr (BW > 0) {
       if (!(p.dbg_skip & 4)) belief_role<BW>(p, dyn, tile0, nEnv, warp, lane);
+      if (warp == 0) FCLK_ADD(3, FCLK_NOW() - t0);
     }
   } else if (!(p.dbg_skip & 1)) {
     if constexpr (WRW > 0) {
@@ -1830,11 +1905,56 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
       } else {
         writer_role<WRW, WV == WV_ONES>(p, dyn, tile0, nEnv, warp - nbw, lane);
       }
+      if (warp == nbw) {
+        FCLK_ADD(1, FCLK_NOW() - t0);
+        FCLK_ADD(6, 1);
+      }
     }
   }
 }
 
 constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? 12 : BEL_WARPS, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
+
+// ---------------------------------------------------------------------------------------------
+// lagged step kernel (software-pipelined rollouts): ONE launch = the dense observations of the CURRENT state (the
+// roles of sy_observe_kernel, unchanged) and, on LOGIC_WARPS extra warps of the same CTA, the dynamics of the NEXT step
+// for the same 32-env tile.  The two halves belong to different steps, so neither waits for the other: the
+// latency-bound dynamics (a chain of dependent table lookups, ~13 us per tile) run in the shadow of the tile's
+// HBM-bound observation stream (~15 us per tile) instead of in a kernel of their own in front of it.  The only
+// ordering is write-after-read on the tile's state: the observation roles copy what they need first (registers /
+// shared memory) and arrive on LAG_BAR; the dynamics warps wait on it right before their state write-back.
+// A policy that needs only the compact state (positions, budgets, reveal flags: the random policy, both reference
+// agents) sees the new state after every launch; action_mask / node_features / belief_map trail it by one step until
+// sy_flush_observations (or any non-deferred call) brings them up to date.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, int MAXA, int BW, int WRW>
+__global__ void __launch_bounds__((BW + WRW + LOGIC_WARPS) * 32, 2) sy_step_lagged_kernel(const Params p) {
+  constexpr int NT = (BW + WRW + LOGIC_WARPS) * 32;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ LogicSmem<MAXA> lsm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile0 = blockIdx.x * TILE;
+  const int nEnv = min(TILE, p.B - tile0);
+  constexpr int CSRT = (WRW + LOGIC_WARPS) * 32;
+  __shared__ int staged_flag;
+  const long long t0 = FCLK_NOW();
+  if (warp < BW) {
+    if constexpr (BW > 0) belief_role<BW, NT>(p, dyn, tile0, nEnv, warp, lane);
+    if (warp == 0) FCLK_ADD(3, FCLK_NOW() - t0);
+  } else if (warp < BW + WRW) {
+    writer_role<WRW, false, NT, CSRT>(p, dyn, tile0, nEnv, warp - BW, lane, &staged_flag);
+    if (warp == BW) FCLK_ADD(1, FCLK_NOW() - t0);
+  } else {
+    const int* s_rp = reinterpret_cast<const int*>(dyn + p.wr_off_csr);
+    const uint16_t* s_col = reinterpret_cast<const uint16_t*>(s_rp + p.N + 1);
+    const SharedGraph sg{s_rp, s_col, reinterpret_cast<const uint8_t*>(s_col + p.tb.nnz_stride)};
+    logic_tile<MODE, MAXA, 5, NT, CSRT>(p, lsm, tile0, threadIdx.x - (BW + WRW) * 32, &sg, &staged_flag);
+    if (warp == BW + WRW) {
+      FCLK_ADD(4, FCLK_NOW() - t0);
+      FCLK_ADD(5, 1);
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // fused persistent step kernel: ONE launch per sy_step.  Every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -1852,15 +1972,6 @@ constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? 12 : BEL_WARPS, GEN_WR_WARPS 
 // under a stream that is HBM-bound from the first microsecond.
 // ---------------------------------------------------------------------------------------------
 constexpr int FUSED_WR = 2;
-#ifdef SY_FUSED_CLOCKS  // profiling builds: per-role time inside the fused kernel, summed over CTAs (sy_debug_fused_clocks)
-__device__ unsigned long long g_fused_clk[16];
-#define FCLK_ADD(slot, v) do { if (lane == 0) atomicAdd(&g_fused_clk[slot], (unsigned long long)(v)); } while (0)
-#define FCLK_NOW() clock64()
-#else
-#define FCLK_ADD(slot, v) do { } while (0)
-#define FCLK_NOW() 0ll
-#pragma nv_diag_suppress 177
-#endif
 
 __device__ __forceinline__ void publish_u32(unsigned* smem_word, unsigned v) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_word);
@@ -2637,6 +2748,14 @@ struct SyEnv {
   int opt_writer = SY_WRITER_LSU;  // sy_set_option(SY_OPT_WRITER_PATH) for the stand-alone observe kernel (sy_reset, two-kernel sy_step)
   int bel_warps = BEL_WARPS, wr_warps = WR_WARPS;  // role split of the observe kernel for this pool
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
+  // software-pipelined steps (sy_step_deferred): the dense observations of the current state have not been written yet;
+  // the next dynamics launch carries them (sy_step_lagged_kernel), sy_flush_observations / any plain call writes them
+  bool obs_pending = false;
+  bool lag_ok = false;  // the lagged kernel fits this shape with two CTAs per SM
+  // sy_set_option(SY_OPT_LAGGED_KERNEL): 1 = a deferred step with pending observations is ONE launch and the random
+  // rollouts step deferred.  Off by default: measured slower at c3 (0.156-0.166 vs 0.129 ms per step) -- the dynamics warps
+  // take 21 us per tile next to the store stream (13 us alone) and hold the CTA's slot after its observation roles are done
+  int opt_lagged = 0;
 };
 
 namespace {
@@ -2747,6 +2866,47 @@ int plan_fused(SyEnv* e, int nnz_stride) {
   const int ntiles = (e->cfg.num_envs + TILE - 1) / TILE;
   e->f_grid = std::min(ntiles, per_sm * sms);
   e->fused_ok = true;
+  return SY_OK;
+}
+
+template <int BW>
+FusedFn lagged_fn_bw(int reward_mode, int A) {
+  const bool f64 = reward_mode == SY_REWARD_FP64;
+  if (A <= 4) return f64 ? sy_step_lagged_kernel<SY_REWARD_FP64, 4, BW, WR_WARPS> : sy_step_lagged_kernel<SY_REWARD_FP32, 4, BW, WR_WARPS>;
+  if (A <= 8) return f64 ? sy_step_lagged_kernel<SY_REWARD_FP64, 8, BW, WR_WARPS> : sy_step_lagged_kernel<SY_REWARD_FP32, 8, BW, WR_WARPS>;
+  return f64 ? sy_step_lagged_kernel<SY_REWARD_FP64, 16, BW, WR_WARPS> : sy_step_lagged_kernel<SY_REWARD_FP32, 16, BW, WR_WARPS>;
+}
+FusedFn lagged_fn(const SyEnv* e) {
+  return e->cfg.belief ? lagged_fn_bw<BEL_WARPS>(e->cfg.reward_mode, e->A) : lagged_fn_bw<0>(e->cfg.reward_mode, e->A);
+}
+int lagged_threads(const SyEnv* e) { return ((e->cfg.belief ? BEL_WARPS : 0) + WR_WARPS + LOGIC_WARPS) * 32; }
+
+// eligibility of the lagged step kernel for this handle's shape: the default role split, and two CTAs per SM (with one
+// the observation stream loses more than the overlap gains: such shapes keep two launches)
+int plan_lagged(SyEnv* e) {
+  e->lag_ok = false;
+  if (e->bel_warps != BEL_WARPS || e->wr_warps != WR_WARPS) return SY_OK;
+  FusedFn fn = lagged_fn(e);
+  static std::mutex mu;
+  static size_t limit[64][12] = {};  // per device and instantiation: the attribute is only ever raised (see below)
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    const int slot = (e->cfg.belief ? 6 : 0) + (e->cfg.reward_mode == SY_REWARD_FP64 ? 3 : 0) + (e->A <= 4 ? 0 : (e->A <= 8 ? 1 : 2));
+    size_t& cur = limit[e->cfg.device & 63][slot];
+    if (e->obs_smem > cur) {
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem) != cudaSuccess) {
+        cudaGetLastError();
+        return SY_OK;
+      }
+      cur = e->obs_smem;
+    }
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, lagged_threads(e), e->obs_smem) != cudaSuccess) {
+    cudaGetLastError();
+    return SY_OK;
+  }
+  e->lag_ok = per_sm >= 2;
   return SY_OK;
 }
 
@@ -2964,6 +3124,10 @@ int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
       if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
       e->opt_writer = value;
       return SY_OK;
+    case SY_OPT_LAGGED_KERNEL:
+      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_LAGGED_KERNEL: 0 or 1");
+      e->opt_lagged = value;
+      return SY_OK;
     default:
       return fail(SY_ERR_INVALID_ARGUMENT, "unknown option %d", option);
   }
@@ -3151,6 +3315,7 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
   e->tb.nnz_stride = nnz_stride;
   e->tb.wcap = wcap;
   if (int rc = plan_fused(e, nnz_stride)) return rc;
+  if (int rc = plan_lagged(e)) return rc;
   e->graphs_loaded = true;
   return SY_OK;
 }
@@ -3291,6 +3456,12 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
   p.restart = restart;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (e->obs_pending) {  // deferred observations (belief propagation of the last step) first: a partial reset keeps the other envs
+    launch_observe(e, p, (unsigned)((p.B + TILE - 1) / TILE), s);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    e->obs_pending = false;
+  }
   sy_reset_kernel<<<(unsigned)((p.B + LOGIC_THREADS - 1) / LOGIC_THREADS), LOGIC_THREADS, 0, s>>>(p);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
@@ -3312,10 +3483,25 @@ bool fused_eligible(const SyEnv* e, const SyObs* ob) {
 }
 
 // next_actions (+ counter): a fused launch also draws the next step's random actions; *fused_sampled reports whether it did
+void launch_logic(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t ls) {
+  const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
+  if (p.A <= 4) {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+  } else if (p.A <= 8) {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+  } else {
+    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+  }
+}
+
+// defer: leave the dense observations of the new state pending (sy_step_deferred); the next call writes them
 int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
               sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr,
               int64_t* next_actions = nullptr, uint32_t next_counter = 0, const uint32_t* next_counter_base = nullptr,
-              bool* fused_sampled = nullptr) {
+              bool* fused_sampled = nullptr, bool defer = false) {
   if (!e || (!actions && !actions32 && !actions16)) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions");
   if (actions16 && e->cfg.num_nodes > 32767) return fail(SY_ERR_INVALID_ARGUMENT, "int16 actions need num_nodes <= 32767");
   e->aux_after_logic = false;
@@ -3332,7 +3518,6 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   p.actions16 = actions16;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
   const unsigned grid = (unsigned)((p.B + TILE - 1) / TILE);
   // Two plain launches.  Measured alternatives that did NOT pay on B200: issuing the step in chunks on two streams or a
   // persistent observe grid (the block scheduler drains the older grid first: no overlap), and one persistent kernel
@@ -3344,6 +3529,37 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
   // overlap gains.
   // Also measured: an L2 persisting access-policy window on the belief map (52 MB at c3) slowed the step to 166-255 us
   // (the carve-out starves the write stream of L2), so no residency hints are set.
+  if (defer || e->obs_pending) {
+    // Software-pipelined step.  Pending observations (of the state BEFORE this step) and this step's dynamics are
+    // independent pieces of work on the same tiles: one launch carries both (sy_step_lagged_kernel), the dynamics in the
+    // shadow of the observation stream.  Without pending observations (first deferred step) the dynamics run alone;
+    // a plain call (defer == false) then brings the observations up to date with the stand-alone kernel.
+    p.next_actions = reinterpret_cast<long long*>(next_actions);
+    p.next_counter = next_counter;
+    p.next_counter_base = next_counter_base;
+    if (e->obs_pending && e->lag_ok && e->opt_lagged && !p.wr_bulk && !p.dbg_skip) {
+      lagged_fn(e)<<<grid, lagged_threads(e), e->obs_smem, s>>>(p);
+    } else {
+      if (e->obs_pending) {
+        launch_observe(e, p, grid, s);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
+      launch_logic(e, p, grid, s);
+    }
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    e->obs_pending = true;
+    if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
+    if (fused_sampled) *fused_sampled = next_actions != nullptr;
+    if (!defer) {
+      launch_observe(e, p, grid, s);
+      g_launches++;
+      CUDA_TRY(cudaGetLastError());
+      e->obs_pending = false;
+    }
+    return SY_OK;
+  }
   if (fused_eligible(e, ob) && !p.dbg_skip) {
     // ONE persistent launch: dynamics, belief and the bulk-store observation stream of all tiles, software-pipelined
     p.next_actions = reinterpret_cast<long long*>(next_actions);
@@ -3395,17 +3611,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
     p.nf_prefilled = 1;
     ls = e->split_stream;
   }
-  if (p.dbg_skip & 32) {
-  } else if (p.A <= 4) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-  } else if (p.A <= 8) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-  } else {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-  }
+  if (!(p.dbg_skip & 32)) launch_logic(e, p, grid, ls);
   g_launches++;
   CUDA_TRY(cudaGetLastError());
   if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, ls));
@@ -3490,6 +3696,27 @@ extern "C" {
 int sy_step(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
   return step_impl(e, actions, nullptr, st, ob, out, stream);
 }
+
+int sy_step_deferred(SyEnv* e, const int64_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
+  return step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, nullptr, 0, nullptr, nullptr, true);
+}
+
+int sy_flush_observations(SyEnv* e, const SyState* st, const SyObs* ob, sy_stream_t stream) {
+  if (!e) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env");
+  if (!e->obs_pending) return SY_OK;
+  Params p;
+  int rc = fill_params(e, st, ob, nullptr, p);
+  if (rc) return rc;
+  if ((rc = check_obs(ob))) return rc;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  launch_observe(e, p, (unsigned)((p.B + TILE - 1) / TILE), (cudaStream_t)stream);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  e->obs_pending = false;
+  return SY_OK;
+}
+
+int sy_observations_pending(SyEnv* e) { return e && e->obs_pending ? 1 : 0; }
 
 int sy_step_i32(SyEnv* e, const int32_t* actions, const SyState* st, const SyObs* ob, const SyOut* out, sy_stream_t stream) {
   return step_impl(e, nullptr, actions, st, ob, out, stream);
@@ -3672,18 +3899,19 @@ int sy_copy_segments(int32_t num_segments, void* const* dst, const void* const* 
 int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,
                       const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions or negative num_steps");
-  bool have_actions = false;  // the fused step kernel draws the next step's actions itself
+  bool have_actions = false;  // the fused / lagged step kernels draw the next step's actions themselves
+  const bool pipelined = !fused_eligible(e, ob) && e->lag_ok && e->opt_lagged;  // deferred steps, one flush at the end
   for (int32_t k = 0; k < num_steps; ++k) {
     int rc;
     if (!have_actions && (rc = sy_sample_actions(e, st, step_counter0 + (uint32_t)k, actions, stream))) return rc;
     have_actions = false;
     const bool more = k + 1 < num_steps;
     if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, more ? actions : nullptr,
-                        step_counter0 + (uint32_t)k + 1u, nullptr, &have_actions)))
+                        step_counter0 + (uint32_t)k + 1u, nullptr, &have_actions, pipelined)))
       return rc;
     have_actions = have_actions && more;
   }
-  return SY_OK;
+  return sy_flush_observations(e, st, ob, stream);
 }
 
 int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_dev, int64_t* actions, const SyState* st,
@@ -3692,13 +3920,17 @@ int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_de
   cudaStream_t s = (cudaStream_t)stream;
   int rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
   if (rc) return rc;
-  if (fused_eligible(e, ob)) {
-    // one launch per step: the fused kernel's logic warps draw the next step's actions from the new state
+  const bool pipelined = !fused_eligible(e, ob) && e->lag_ok && e->opt_lagged;
+  if (fused_eligible(e, ob) || pipelined) {
+    // one launch per step: the dynamics warps of the fused / lagged kernel draw the next step's actions from the new
+    // state.  Pipelined: step k's launch also writes the observations of step k - 1; one flush closes the segment.
     for (int32_t k = 0; k < num_steps; ++k) {
       const bool more = k + 1 < num_steps;
-      if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, more ? actions : nullptr, (uint32_t)(k + 1), step_counter_dev)))
+      if ((rc = step_impl(e, actions, nullptr, st, ob, out, stream, nullptr, nullptr, more ? actions : nullptr, (uint32_t)(k + 1), step_counter_dev,
+                          nullptr, pipelined)))
         return rc;
     }
+    if ((rc = sy_flush_observations(e, st, ob, stream))) return rc;
   } else {
     // The sampler of step k + 1 only needs the state the dynamics of step k wrote, not its observations: it is forked
     // onto the library stream right behind the logic kernel (fork / join with events, capturable), so it runs next to

@@ -226,7 +226,7 @@ class BatchedScotlandYardEnv:
         return t
 
     OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1}), "step_kernel": (1, {"fused": 0, "two_kernels": 1, "auto": 2}),
-               "nf_fill": (2, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
+               "nf_fill": (2, {"off": 0, "on": 1}), "lagged_kernel": (3, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
 
     def set_option(self, name: str, value):
         """Tuning knobs of the handle (results are identical for every setting; include/sy_env.h SY_OPT_*):
@@ -307,6 +307,35 @@ class BatchedScotlandYardEnv:
         self._last_actions = a
         info = {"winner": self.winner, "done": self.done_flags}
         return self.observation(), self.reward, self.terminated, self.truncated, info
+
+    def step_deferred(self, actions):
+        """Software-pipelined `step` for policies that read only the compact state (`pos`, `money`, `agent_budget`,
+        `mrx_revealed`): the dynamics of yard.py:144-269 exactly as `step` (state, reward, flags are those of the new
+        state), while `action_mask` / `node_features` / `belief_map` of the new state are left pending and written by
+        the NEXT `step_deferred` in the same launch as its dynamics (sy_step_deferred).  After the call the dense
+        tensors describe the state before it; `flush_observations()` (or `step` / `reset`) brings them up to date.
+        Returns (reward, terminated, truncated, info)."""
+        if not self._is_reset:
+            raise _cabi.SyError("step() before reset()")
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.device == self.device and a.dtype == torch.int64 and a.is_contiguous()
+                and tuple(a.shape) == (self.num_envs, self.num_agents)):
+            a = self._dev(actions, torch.int64, (self.num_envs, self.num_agents))
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_step_deferred(self._handle, a.data_ptr(), C.byref(self._state), C.byref(self._obs),
+                                                   C.byref(self._out), self._stream()))
+        self._last_actions = a
+        return self.reward, self.terminated, self.truncated, {"winner": self.winner, "done": self.done_flags}
+
+    def flush_observations(self):
+        """Write the dense observations a `step_deferred` left pending (no-op when none are); returns the observation."""
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.sy_flush_observations(self._handle, C.byref(self._state), C.byref(self._obs), self._stream()))
+        return self.observation()
+
+    @property
+    def observations_pending(self) -> bool:
+        return bool(self._lib.sy_observations_pending(self._handle))
 
     def sample_actions(self, out: Optional[torch.Tensor] = None, step_counter: Optional[int] = None) -> torch.Tensor:
         """Uniform random valid action per agent on the device (-1 when an agent cannot move)."""

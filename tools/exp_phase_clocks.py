@@ -6,18 +6,19 @@ import torch
 from student_mechanism_design_b200 import BatchedScotlandYardEnv, _cabi
 lib = _cabi.load_library()
 names = ["P0 stage+barrier", "P1 moves (warp0)", "P1 barrier wait", "P2 rewards (warp0)", "P2 barrier wait", "P3 advance (warp0)", "P3 barrier wait", "P4 store"]
-for mode in ("two_kernels", "fused"):
+for mode in ("two_kernels", "fused", "lagged"):
     env = BatchedScotlandYardEnv(65536, 6, 20, graph_nodes=200, graph_edges=400, seed=0, tolls=1, belief=True, reveal_interval=5, auto_reset=True)
-    env.set_option("step_kernel", mode)
+    env.set_option("step_kernel", "two_kernels" if mode == "lagged" else mode)
+    step = env.step_deferred if mode == "lagged" else env.step
     env.reset()
     a = torch.empty(65536, 7, dtype=torch.int64, device="cuda")
     for s in range(20):
-        env.sample_actions(out=a, step_counter=s); env.step(a)
+        env.sample_actions(out=a, step_counter=s); step(a)
     buf = (ctypes.c_ulonglong * 8)()
     lib.sy_debug_phase_clocks(buf, 1)
     K = 50
     for s in range(K):
-        env.sample_actions(out=a, step_counter=20 + s); env.step(a)
+        env.sample_actions(out=a, step_counter=20 + s); step(a)
     lib.sy_debug_phase_clocks(buf, 0)
     tiles = 2048 * K
     tot = 0
