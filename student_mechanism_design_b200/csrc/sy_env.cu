@@ -516,10 +516,14 @@ __device__ __forceinline__ void store_state(const Params& p, const WarpTile& wt,
 // MAXA (4 / 8 / 16 >= A) bounds the fully unrolled per-agent loops so that their values stay in registers.
 // ---------------------------------------------------------------------------------------------
 #ifdef SY_PHASE_CLOCKS
-__device__ unsigned long long g_phase_clk[8];
+__device__ unsigned long long g_phase_clk[16];
+#define PHASE_SPAN(k, t0) do { if (lane == 0) atomicAdd(&g_phase_clk[k], (unsigned long long)(clock64() - (t0))); } while (0)
+#define PHASE_NOW() clock64()
 #define PHASE_MARK(k) do { if (tid == 0) { const long long _c = clock64(); atomicAdd(&g_phase_clk[k], (unsigned long long)(_c - _t0)); _t0 = _c; } } while (0)
 #else
 #define PHASE_MARK(k) do { } while (0)
+#define PHASE_SPAN(k, t0) do { } while (0)
+#define PHASE_NOW() 0ll
 #endif
 
 constexpr int CNT_SMEM = 2048;  // bytes of the move-count table staged in shared memory (N * (wcap + 1) <= this); the
@@ -633,16 +637,20 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   //   warps 2,3 visit counters at both nodes each police can end on (its node or its action target): the HBM
   //             round trip of the read-modify-write overlaps the moves
   int spent = 0, moves = 0;
+  [[maybe_unused]] const long long tp1 = PHASE_NOW();
   if (warp == 0) {
     if (active) sm.status[lane] = move_phase<MAXA>(p, pos, money, act, g, t, spent, moves, sg);
+    PHASE_SPAN(8, tp1);
   } else if (warp == 1 && p.auto_reset && active) {
     const unsigned env_id = (unsigned)(p.env_offset + (unsigned long long)b);
     const unsigned ep = (unsigned)(sm.episode[lane] + 1);
     sm.reset_gid[lane] = p.resample_graph ? philox_graph_choice(p, env_id, ep) : g;
     philox_start_positions(p, env_id, ep, sm.reset_pos + lane * HS, sm.dmat + lane * HS);
+    PHASE_SPAN(9, tp1);  // (lane-divergent branch: no warp-level synchronisation in here)
   }
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(1);
+  [[maybe_unused]] const long long tp2 = PHASE_NOW();
 
   // ---- P2a: every table lookup of the rewards, once: the A(A-1)/2 distinct distances between the env's agents (the
   // reference asks Pathfinder for each of them 2-4 times, reward_calculator.py:126-227) and the visit counters at the
@@ -687,6 +695,8 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     }
   }
   if (warp == 0) PHASE_MARK(1);
+  if (warp == 0) PHASE_SPAN(10, tp2);
+  if (warp == 3) PHASE_SPAN(11, tp2);
   named_barrier(BAR, LOGIC_THREADS);
   PHASE_MARK(2);
 
@@ -3027,9 +3037,9 @@ extern "C" {
 #ifdef SY_PHASE_CLOCKS
 int sy_debug_phase_clocks(unsigned long long* out8, int reset) {  // profiling builds only, not declared in sy_env.h
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, g_phase_clk, sizeof(unsigned long long) * 8);
+  cudaMemcpyFromSymbol(out8, g_phase_clk, sizeof(unsigned long long) * 16);
   if (reset) {
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long z[16] = {};
     cudaMemcpyToSymbol(g_phase_clk, z, sizeof(z));
   }
   return 0;
