@@ -395,7 +395,7 @@ def run_cuda_arm(args, wl):
     # release the GIL): while one half waits for its PCIe copies the other half's kernels run, so the host round trips of
     # the two halves hide behind each other's device work (ping-pong).  Every step of every half still moves its actions
     # host -> device and its results device -> host and synchronises before the next step of that half.
-    Ke = max(3, min(K, args.e2e_steps))
+    Ke = max(3, args.e2e_steps)  # its own step count (reported): a 20-step region would be 3 ms, a third of it thread start-up
     H = max(1, args.e2e_halves)
     while B % H:
         H -= 1
@@ -438,9 +438,10 @@ def run_cuda_arm(args, wl):
             torch.cuda.current_stream(dev).synchronize()
             return buf
 
-        def worker(h, steps, c0):
+        def worker(h, steps, c0, gate):
             try:
                 eh, pol = e2e_envs[h], e2e_policies[h]
+                gate.wait()  # all host threads exist before the clock starts
                 with torch.cuda.device(dev), torch.cuda.stream(e2e_streams[h]):
                     if pol is None and not args.e2e_python_loop:
                         # the same two C-ABI calls per step (sy_sample_actions_host, sy_step_host*), issued from C
@@ -453,13 +454,19 @@ def run_cuda_arm(args, wl):
                 errors.append(exc)
 
         def run(steps, c0):
-            ts = [threading.Thread(target=worker, args=(h, steps, c0)) for h in range(H)]
+            gate = threading.Barrier(H + 1)
+            ts = [threading.Thread(target=worker, args=(h, steps, c0, gate)) for h in range(H)]
             for t in ts:
                 t.start()
+            barrier()
+            t0 = time.perf_counter()
+            gate.wait()
             for t in ts:
                 t.join()
             if errors:
                 raise errors[0]
+            torch.cuda.synchronize(dev)
+            return (time.perf_counter() - t0) * 1e3
 
         for eh in e2e_envs:
             eh.set_host_overlap(not args.e2e_no_overlap)  # results return while the observation kernel of the step still runs
@@ -468,11 +475,7 @@ def run_cuda_arm(args, wl):
         ms = []
         for _ in range(passes):
             c += Ke + 3
-            barrier()
-            t0 = time.perf_counter()
-            run(Ke, c)
-            torch.cuda.synchronize(dev)
-            ms.append(max_over_ranks((time.perf_counter() - t0) * 1e3))
+            ms.append(max_over_ranks(run(Ke, c)))
         for eh in e2e_envs:
             eh.set_host_overlap(False)
         assert all(r["reward"].shape == (Bh, A) and not r["reward"].is_cuda for r in last)

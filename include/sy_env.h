@@ -184,8 +184,11 @@ void sy_destroy(SyEnv* env);
  *                       dynamics warps of the next step in the same CTA) and sy_rollout_random* step deferred; shapes
  *                       whose lagged kernel would not fit two CTAs per SM keep two launches.  Measured slower at c3
  *                       (DESIGN.md 4c): the dynamics warps take 21 us per tile next to the store stream and hold the
- *                       CTA's slot. */
-enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3 };
+ *                       CTA's slot.
+ *   SY_OPT_TAIL_SPLIT   1 (default): when the observation kernel's grid ends in a partly filled wave, the tiles of that
+ *                       wave are cut into 2 or 4 parts (one CTA each) so the wave is full and short; applies to the
+ *                       warp-per-env belief path (large N).  0: always one CTA per 32-env tile. */
+enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3, SY_OPT_TAIL_SPLIT = 4 };
 enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
 enum { SY_STEP_FUSED = 0, SY_STEP_TWO_KERNELS = 1, SY_STEP_AUTO = 2 };
 int sy_set_option(SyEnv* env, int32_t option, int32_t value);

@@ -146,6 +146,9 @@ struct Params {
   int f_off_sbuf, f_sbuf_stride, f_off_zero, f_off_imgs;  // fused kernel: staged tile state (x2), zero page, chunk images
   int f_off_nbr4;  // fused kernel: packed neighbour table [N] uint4 + flag (after the staged CSR)
   int wr_epc;      // fused kernel fast geometry: whole envs per chunk (0: chunks cut through envs / more than 32 pairs)
+  // observation kernel grid: CTAs [0, ob_full) take whole 32-env tiles; the tiles behind them -- the last, partly filled
+  // wave of the grid -- are cut into ob_split parts of 32 / ob_split envs each, one CTA per part (0 / 1: no split)
+  int ob_full, ob_split;
   int dbg_skip;  // profiling experiments only (SY_DEBUG_SKIP): 1 no observation writers, 4 no belief, 16 / 32 no observe / logic launch
   unsigned long long* stats_rep;  // [STAT_REPLICAS, SY_NUM_STATS] library-owned statistics accumulators
   uint8_t* bel_flags;  // [B] belief operation per env, logic/reset kernel -> observe kernel (library-owned)
@@ -1898,8 +1901,17 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
   static_assert((BW + WRW) * 32 == THREADS || BW == 0 || WRW == 0, "the role hand-over barrier counts THREADS");
   extern __shared__ __align__(16) unsigned char dyn[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile0 = blockIdx.x * TILE;
-  const int nEnv = min(TILE, p.B - tile0);
+  int tile0 = blockIdx.x * TILE;
+  int nEnv = min(TILE, p.B - tile0);
+  if (p.ob_split > 1 && (int)blockIdx.x >= p.ob_full) {
+    // tail of the grid: all CTAs last about equally long, so a last wave that fills only part of the chip costs a whole
+    // CTA lifetime; its tiles are cut into parts so that the wave is full and short (c4: 3.46 waves -> 3 + 0.5)
+    const int r = (int)blockIdx.x - p.ob_full, sub = TILE / p.ob_split;
+    const int t = p.ob_full + r / p.ob_split, part = r % p.ob_split;
+    tile0 = t * TILE + part * sub;
+    nEnv = min(sub, p.B - tile0);
+    if (nEnv <= 0) return;
+  }
   const int nbw = BW;  // without a belief map the belief warps simply exit
   if (warp < nbw && !p.belief_on) return;
   const long long t0 = FCLK_NOW();
@@ -2760,6 +2772,8 @@ struct SyEnv {
   size_t obs_smem = 0;  // dynamic smem of the observe kernel: belief scratch + writer staging
   // software-pipelined steps (sy_step_deferred): the dense observations of the current state have not been written yet;
   // the next dynamics launch carries them (sy_step_lagged_kernel), sy_flush_observations / any plain call writes them
+  int obs_slots = 0;        // resident CTAs of the observation kernel on this device (occupancy x SMs)
+  int opt_tail_split = 1;   // sy_set_option(SY_OPT_TAIL_SPLIT)
   bool obs_pending = false;
   bool lag_ok = false;  // the lagged kernel fits this shape with two CTAs per SM
   // sy_set_option(SY_OPT_LAGGED_KERNEL): 1 = a deferred step with pending observations is ONE launch and the random
@@ -2938,8 +2952,25 @@ int raise_observe_smem_limit(int device, size_t bytes) {
   return SY_OK;
 }
 
-void launch_observe(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t s) {
+void launch_observe(const SyEnv* e, const Params& p0, unsigned grid, cudaStream_t s) {
   const bool gen = e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS;
+  Params p = p0;
+  p.ob_full = (int)grid;
+  p.ob_split = 1;
+  if (e->obs_slots > 0 && e->opt_tail_split && !p.wr_bulk) {
+    const int full = (int)(grid / (unsigned)e->obs_slots) * e->obs_slots, rest = (int)grid - full;
+    // (fast belief path: lane = env, a part costs its belief warps what a whole tile costs: measured slower, no split)
+    const int kmax = (p.belief_on && e->bel_fast) ? 1 : 4;
+    int k = 1;
+    while (rest > 0 && k < kmax && rest * (k * 2) <= e->obs_slots) k *= 2;  // parts per tile that still fit one wave
+    // (measured at c4: the tail in halves 0.321 ms per step, no split 0.333, EVERY tile in halves 0.349, in quarters 0.384
+    //  -- a part pays the tile's fixed staging again)
+    if (k > 1) {
+      p.ob_full = full;
+      p.ob_split = k;
+      grid = (unsigned)(full + rest * k);
+    }
+  }
   if (p.wr_bulk) {
     if (gen) sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
     else sy_observe_kernel<BEL_WARPS, WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
@@ -3134,6 +3165,10 @@ int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
       if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
       e->opt_writer = value;
       return SY_OK;
+    case SY_OPT_TAIL_SPLIT:
+      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_TAIL_SPLIT: 0 or 1");
+      e->opt_tail_split = value;
+      return SY_OK;
     case SY_OPT_LAGGED_KERNEL:
       if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_LAGGED_KERNEL: 0 or 1");
       e->opt_lagged = value;
@@ -3319,6 +3354,15 @@ int finish_graph_tables(SyEnv* e, int G, int nnz_stride, int wcap, int pack_stri
     e->obs_smem = (size_t)e->wr_off_csr + (e->wr_stage_csr ? csr : 0);
     if (e->obs_smem > 220 * 1024) return fail(SY_ERR_INVALID_ARGUMENT, "num_nodes x agents too large for the observe kernel's shared memory");
     if (int rc = raise_observe_smem_limit(e->cfg.device, e->obs_smem)) return rc;
+    int per_sm = 0, sms = 0;
+    const bool gen = e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS;
+    cudaError_t oe = gen ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, THREADS, e->obs_smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sy_observe_kernel<BEL_WARPS, WR_WARPS>, THREADS, e->obs_smem);
+    if (oe != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm = 0;
+    }
+    e->obs_slots = per_sm * sms;
   }
   e->tb.G = G;
   e->tb.Ns = Ns;

@@ -175,6 +175,27 @@ def test_timed_path_graph_replay_matches_oracle(torch_cuda, writer):
     env.close()
 
 
+@pytest.mark.parametrize("case", ["generic_quarters", "fast_path", "no_belief", "off"])
+def test_observation_grid_tail_split(torch_cuda, case):
+    """The observation kernel cuts the tiles of a partly filled last wave into 2 or 4 parts (one CTA each): batches whose
+    tile count leaves such a tail -- 296 resident CTAs on a B200: 330 tiles = 1 wave + 34 tiles (quarters on the
+    warp-per-env belief path at N = 500 and without a belief map; the lane = env fast path at N = 200 keeps whole tiles), a
+    ragged last part -- and the same inputs with the split switched off."""
+    import student_mechanism_design_b200 as pkg
+
+    N, E, belief = (500, 1000, True) if case in ("generic_quarters", "off") else (200, 400, case != "no_belief")
+    B = 330 * 32 - 21  # last tile holds 11 envs: its second half and its last two quarters are empty
+    pool = pkg.generate_graph_pool(2, N, E, seed=0)
+    env = pkg.BatchedScotlandYardEnv(B, 4, 15, graphs=pool, seed=31, auto_reset=True, tolls=1, belief=belief, reveal_interval=4,
+                                     keep_reward64=True)
+    env.set_option("tail_split", "off" if case == "off" else "on")
+    cfg = so.OracleConfig(num_police=4, agent_money=15, toll=1, belief=belief, reveal_interval=4)
+    gid = ((np.arange(B) // 32) % 2).astype(np.int32)
+    ob = oc.CBatch(cfg, pool, B, seed=31, auto_reset=True, threads=_threads(), graph_id=gid)
+    _rollout_against_oracle(env, ob, 8, belief, dense_every=1)
+    env.close()
+
+
 def test_two_handles_of_different_shapes_coexist(torch_cuda):
     """A large belief env, then a small env created next to it, then the first one stepped again: the observe kernel's
     dynamic shared-memory attribute is per function, not per handle (round-1 advisor finding)."""

@@ -13,3 +13,5 @@ timeout 300 python bench.py --steps 10 --warmup 4 --passes 1 --no-cpu-baseline -
 python tools/ncu_launches.py gpurun_out/r02_launches_c3.csv
 python tools/exp_two_steps.py c3 > gpurun_out/plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"sy_observe|sy_logic" -s 8 -c 2 -o gpurun_out/r02_step_c3 -f python tools/exp_two_steps.py c3 > gpurun_out/ncu2.log 2>&1
 tail -2 gpurun_out/ncu2.log
+python tools/exp_two_steps.py c4 > gpurun_out/plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"sy_observe|sy_logic" -s 8 -c 2 -o gpurun_out/r02_step_c4 -f python tools/exp_two_steps.py c4 > gpurun_out/ncu3.log 2>&1
+tail -2 gpurun_out/ncu3.log
