@@ -70,7 +70,7 @@ class BatchedScotlandYardEnv:
                  auto_reset: bool = False, resample_graph: bool = False, env_offset: int = 0, max_timestep: int = 250,
                  device="cuda:0", reward_tables=None, keep_reward64: bool = False, collect_stats: bool = True,
                  graph_offset: int = 0, max_edges_per_node: int = 4, max_weight: int = 5,
-                 node_features_dtype: torch.dtype = torch.float32, reveal_skip_prob: float = 0.0):
+                 node_features_dtype: torch.dtype = torch.float32, reveal_skip_prob: float = 0.0, guard_bytes: int = 0):
         if not torch.cuda.is_available():
             raise _cabi.SyError("BatchedScotlandYardEnv needs a CUDA device; there is no CPU fallback")
         self._lib = _cabi.load_library()
@@ -156,7 +156,23 @@ class BatchedScotlandYardEnv:
                                                      wgt.ctypes.data, stride, stream))
 
             dev = self.device
-            z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+            # guard_bytes > 0 (memory-safety tests; compute-sanitizer is not available on the GPU pool): every buffer the
+            # kernels write sits between two canary bands inside its own allocation; check_guards() verifies them
+            self._guards = []
+            guard = (int(guard_bytes) + 255) & ~255
+
+            def z(*shape, dtype):
+                if not guard:
+                    return torch.zeros(*shape, dtype=dtype, device=dev)
+                n = 1
+                for d in shape:
+                    n *= int(d)
+                nbytes = n * torch.empty((), dtype=dtype).element_size()
+                raw = torch.full((2 * guard + ((nbytes + 255) & ~255),), 0xA5, dtype=torch.uint8, device=dev)
+                raw[guard:guard + nbytes].zero_()
+                self._guards.append((raw, guard, nbytes))
+                return raw[guard:guard + nbytes].view(dtype).view(*shape)
+
             self.pos = z(B, A, dtype=torch.int32)
             self.money = z(B, A, dtype=torch.int32)
             self.timestep = z(B, dtype=torch.int32)
@@ -203,6 +219,15 @@ class BatchedScotlandYardEnv:
         winner = block[7 * n: 7 * n + B].view(torch.int8)
         status = block[7 * n + B: 7 * n + 2 * B]  # uint8 [B]: bit 0 terminated, 1 truncated, 2 frozen (done = any)
         return reward, flags[0], flags[1], flags[2], winner, status
+
+    def check_guards(self):
+        """(guard_bytes > 0) Raise if a kernel wrote outside any state / observation / result buffer."""
+        for i, (raw, guard, nbytes) in enumerate(getattr(self, "_guards", [])):
+            lo, hi = raw[:guard], raw[guard + nbytes:]
+            if not (bool((lo == 0xA5).all()) and bool((hi == 0xA5).all())):
+                bad_lo = int((lo != 0xA5).sum())
+                bad_hi = int((hi != 0xA5).sum())
+                raise _cabi.SyError(f"guard band of buffer {i} ({nbytes} bytes) overwritten: {bad_lo} bytes below, {bad_hi} above")
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
