@@ -1935,10 +1935,7 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
   }
 }
 
-#ifndef SY_GEN_BEL_WARPS
-#define SY_GEN_BEL_WARPS 12
-#endif
-constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? SY_GEN_BEL_WARPS : BEL_WARPS, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
+constexpr int GEN_BEL_WARPS = THREADS / 32 >= 16 ? 12 : BEL_WARPS, GEN_WR_WARPS = THREADS / 32 - GEN_BEL_WARPS;  // split of the large-N configuration
 
 // ---------------------------------------------------------------------------------------------
 // lagged step kernel (software-pipelined rollouts): ONE launch = the dense observations of the CURRENT state (the
