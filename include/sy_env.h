@@ -179,18 +179,20 @@ void sy_destroy(SyEnv* env);
  *                       engine by its own small kernel NEXT TO the dynamics kernel (second stream), then the belief
  *                       propagation and the writers of the ones run as two concurrent kernels; all joined on the
  *                       caller's stream before sy_step returns (events; capturable).  Measured slower.
- *   SY_OPT_LAGGED_KERNEL 0 (default): a deferred step with pending observations is two launches (observation kernel, then
- *                       dynamics kernel).  1: ONE launch (sy_step_lagged_kernel: the pending observation roles + the
- *                       dynamics warps of the next step in the same CTA) and sy_rollout_random* step deferred; shapes
- *                       whose lagged kernel would not fit two CTAs per SM keep two launches.  Measured slower at c3
- *                       (DESIGN.md 4c): the dynamics warps take 21 us per tile next to the store stream and hold the
- *                       CTA's slot.
+ *   SY_OPT_LAGGED_KERNEL SY_LAGGED_AUTO (default): a deferred step with pending observations is ONE launch
+ *                       (sy_step_lagged_kernel: the pending observation roles + the dynamics warps of the next step in
+ *                       the same CTA) and sy_rollout_random* step deferred WHEN the batch's 32-env tiles fit one wave of
+ *                       that kernel (<= ~9 500 envs): a step then costs max(dynamics, observations) instead of their
+ *                       sum (c2: 11.8 -> 8.8 us per step).  SY_LAGGED_ON: at every batch size (measured slower beyond one
+ *                       wave).  SY_LAGGED_OFF: pending observations and dynamics as two launches, rollouts
+ *                       step plainly.
  *   SY_OPT_TAIL_SPLIT   1 (default): when the observation kernel's grid ends in a partly filled wave, the tiles of that
  *                       wave are cut into 2 or 4 parts (one CTA each) so the wave is full and short; applies to the
  *                       warp-per-env belief path (large N).  0: always one CTA per 32-env tile. */
 enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3, SY_OPT_TAIL_SPLIT = 4 };
 enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
 enum { SY_STEP_FUSED = 0, SY_STEP_TWO_KERNELS = 1, SY_STEP_AUTO = 2 };
+enum { SY_LAGGED_OFF = 0, SY_LAGGED_ON = 1, SY_LAGGED_AUTO = 2 };
 int sy_set_option(SyEnv* env, int32_t option, int32_t value);
 /* new Philox key for subsequent (auto-)resets and action sampling (torchrl `set_seed`) */
 int sy_set_seed(SyEnv* env, uint64_t seed);
@@ -252,8 +254,8 @@ int sy_step(SyEnv* env, const int64_t* actions, const SyState* state, const SyOb
  * under the HBM-bound observation stream of the same 32-env tile), so after every deferred call the dense tensors
  * describe the state BEFORE that call.  sy_flush_observations writes whatever is pending (no-op otherwise); sy_step,
  * sy_step_host*, sy_reset flush implicitly, so mixing the calls is always correct.  Pending observations are written
- * into the SyObs of the call that carries them.  With SY_OPT_LAGGED_KERNEL on, sy_rollout_random / sy_rollout_random_dev
- * step deferred and flush once at the end.  sy_observations_pending: 1 while a flush is owed. */
+ * into the SyObs of the call that carries them.  Where the lagged kernel is in use (SY_OPT_LAGGED_KERNEL), sy_rollout_random /
+ * sy_rollout_random_dev step deferred and flush once at the end.  sy_observations_pending: 1 while a flush is owed. */
 int sy_step_deferred(SyEnv* env, const int64_t* actions, const SyState* state, const SyObs* obs, const SyOut* out,
                      sy_stream_t stream);
 int sy_flush_observations(SyEnv* env, const SyState* state, const SyObs* obs, sy_stream_t stream);

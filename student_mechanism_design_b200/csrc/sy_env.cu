@@ -2776,10 +2776,14 @@ struct SyEnv {
   int opt_tail_split = 1;   // sy_set_option(SY_OPT_TAIL_SPLIT)
   bool obs_pending = false;
   bool lag_ok = false;  // the lagged kernel fits this shape with two CTAs per SM
-  // sy_set_option(SY_OPT_LAGGED_KERNEL): 1 = a deferred step with pending observations is ONE launch and the random
-  // rollouts step deferred.  Off by default: measured slower at c3 (0.156-0.166 vs 0.129 ms per step) -- the dynamics warps
-  // take 21 us per tile next to the store stream (13 us alone) and hold the CTA's slot after its observation roles are done
-  int opt_lagged = 0;
+  // sy_set_option(SY_OPT_LAGGED_KERNEL): SY_LAGGED_AUTO = a deferred step with pending observations is ONE launch (and the
+  // random rollouts step deferred) when the batch's tiles fit one wave of the lagged kernel, where a step costs
+  // max(dynamics, observations) instead of their sum: c2 (1 024 envs) 11.8 -> 8.8 us per step, c3-shaped batches of 4 096 /
+  // 9 472 envs 28.1 -> 17.0 / 33.8 -> 23.1 us.  Larger batches keep two launches: the dynamics warps take 21 us per tile next
+  // to the store stream (13 us alone) and hold the CTA's slot after its observation roles are done, which every further
+  // wave pays again (16 384 envs 44.4 vs 40.8 us, 65 536 envs 156 vs 129 us).
+  int opt_lagged = SY_LAGGED_AUTO;
+  int lag_slots = 0;  // resident CTAs of the lagged kernel (occupancy x SMs)
 };
 
 namespace {
@@ -2931,6 +2935,12 @@ int plan_lagged(SyEnv* e) {
     return SY_OK;
   }
   e->lag_ok = per_sm >= 2;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->cfg.device) != cudaSuccess) {
+    cudaGetLastError();
+    sms = 0;
+  }
+  e->lag_slots = per_sm * sms;
   return SY_OK;
 }
 
@@ -3170,7 +3180,8 @@ int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
       e->opt_tail_split = value;
       return SY_OK;
     case SY_OPT_LAGGED_KERNEL:
-      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_LAGGED_KERNEL: 0 or 1");
+      if (value != SY_LAGGED_OFF && value != SY_LAGGED_ON && value != SY_LAGGED_AUTO)
+        return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_LAGGED_KERNEL: 0 (off), 1 (on) or 2 (auto)");
       e->opt_lagged = value;
       return SY_OK;
     default:
@@ -3551,6 +3562,13 @@ void launch_logic(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t l
   }
 }
 
+// the lagged kernel carries pending observations: always (option on), or when the batch is one wave of it (auto)
+bool use_lagged(const SyEnv* e) {
+  if (!e->lag_ok || e->opt_lagged == SY_LAGGED_OFF) return false;
+  if (e->opt_lagged == SY_LAGGED_ON) return true;
+  return (e->cfg.num_envs + TILE - 1) / TILE <= e->lag_slots;
+}
+
 // defer: leave the dense observations of the new state pending (sy_step_deferred); the next call writes them
 int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const SyState* st, const SyObs* ob, const SyOut* out,
               sy_stream_t stream, cudaEvent_t after_logic = nullptr, const int16_t* actions16 = nullptr,
@@ -3591,7 +3609,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
     p.next_actions = reinterpret_cast<long long*>(next_actions);
     p.next_counter = next_counter;
     p.next_counter_base = next_counter_base;
-    if (e->obs_pending && e->lag_ok && e->opt_lagged && !p.wr_bulk && !p.dbg_skip) {
+    if (e->obs_pending && use_lagged(e) && !p.wr_bulk && !p.dbg_skip) {
       lagged_fn(e)<<<grid, lagged_threads(e), e->obs_smem, s>>>(p);
     } else {
       if (e->obs_pending) {
@@ -3954,7 +3972,7 @@ int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64
                       const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions or negative num_steps");
   bool have_actions = false;  // the fused / lagged step kernels draw the next step's actions themselves
-  const bool pipelined = !fused_eligible(e, ob) && e->lag_ok && e->opt_lagged;  // deferred steps, one flush at the end
+  const bool pipelined = use_lagged(e) && e->opt_writer != SY_WRITER_BULK && e->opt_fused != SY_STEP_FUSED;  // deferred steps, one flush at the end
   for (int32_t k = 0; k < num_steps; ++k) {
     int rc;
     if (!have_actions && (rc = sy_sample_actions(e, st, step_counter0 + (uint32_t)k, actions, stream))) return rc;
@@ -3974,7 +3992,7 @@ int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_de
   cudaStream_t s = (cudaStream_t)stream;
   int rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
   if (rc) return rc;
-  const bool pipelined = !fused_eligible(e, ob) && e->lag_ok && e->opt_lagged;
+  const bool pipelined = use_lagged(e) && e->opt_writer != SY_WRITER_BULK && e->opt_fused != SY_STEP_FUSED;
   if (fused_eligible(e, ob) || pipelined) {
     // one launch per step: the dynamics warps of the fused / lagged kernel draw the next step's actions from the new
     // state.  Pipelined: step k's launch also writes the observations of step k - 1; one flush closes the segment.

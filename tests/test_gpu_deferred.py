@@ -171,3 +171,38 @@ def test_rollout_random_is_pipelined_and_flushed(torch_cuda):
     _compare(env, ob, want, True, "after rollout_random")
     assert launches == T + 2, launches  # sampler, dynamics, (T - 1) lagged launches, flush
     env.close()
+
+
+@pytest.mark.parametrize("shape", ["c2", "c3_one_wave"])
+def test_small_batch_rollout_graph_is_pipelined_by_default(torch_cuda, shape):
+    """Batches of at most one wave of the lagged kernel: capture_rollout / sy_rollout_random_dev step deferred by default
+    (lagged_kernel = auto) -- one launch per step -- and the replayed CUDA graph leaves state AND observations equal to
+    the oracle's (BASELINE config 2 as benchmarked, and a c3-shaped batch of 296 tiles minus a ragged tail)."""
+    torch = torch_cuda
+    if shape == "c2":
+        env, ob = _pair(50, 110, 3, 10, 1024, 2, toll=0, belief=False, reveal=5)
+        belief = False
+    else:
+        env, ob = _pair(200, 400, 6, 20, 296 * 32 - 7, 3, toll=1, belief=True, reveal=5)
+        belief = True
+    env.set_option("lagged_kernel", "auto")
+    env.reset()
+    seg, replays = 6, 5
+    lib = __import__("student_mechanism_design_b200").load_library()
+    graph, counter = env.capture_rollout(seg)  # warm-up segment, then capture
+    torch.cuda.synchronize()
+    n0 = lib.sy_launch_count()
+    env.rollout_random(seg, step_counter=seg)  # the same call outside a graph, for the launch count
+    torch.cuda.synchronize()
+    assert lib.sy_launch_count() - n0 == seg + 2  # sampler, dynamics, (seg - 1) lagged launches, flush
+    counter.fill_(2 * seg)
+    for _ in range(replays):
+        graph.replay()
+    torch.cuda.synchronize()
+    total = seg * (2 + replays)
+    want = None
+    for s in range(total):
+        want = ob.step(ob.sample_actions(s))
+    _compare(env, ob, want, belief, "after pipelined graph replays")
+    assert not env.observations_pending
+    env.close()
