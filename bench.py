@@ -387,8 +387,9 @@ def run_cuda_arm(args, wl):
         counter += 1
     barrier()
     sampler.active = False
-    step_kernel_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in kev)
-    policy_ms = statistics.mean(c.elapsed_time(a) for a, _, c in kev)
+    # median: a host hiccup between the two launches of a call (this loop is driven from Python) must not read as kernel time
+    step_kernel_ms = statistics.median(a.elapsed_time(b) for a, b, _ in kev)
+    policy_ms = statistics.median(c.elapsed_time(a) for a, _, c in kev)
 
     # ---- end to end through the host-buffer API
     # The rank's batch is driven as `--e2e-halves` half-batch envs (own handle, own stream, own host thread; ctypes calls

@@ -2775,6 +2775,7 @@ struct SyEnv {
   int obs_slots = 0;        // resident CTAs of the observation kernel on this device (occupancy x SMs)
   int opt_tail_split = 1;   // sy_set_option(SY_OPT_TAIL_SPLIT)
   bool obs_pending = false;
+  int64_t* pending_stats = nullptr;  // SyOut.stats of the step whose observations are pending (flush / reset have no SyOut)
   bool lag_ok = false;  // the lagged kernel fits this shape with two CTAs per SM
   // sy_set_option(SY_OPT_LAGGED_KERNEL): SY_LAGGED_AUTO = a deferred step with pending observations is ONE launch (and the
   // random rollouts step deferred) when the batch's tiles fit one wave of the lagged kernel, where a step costs
@@ -3522,7 +3523,9 @@ int sy_reset(SyEnv* e, const uint8_t* reset_mask, const int32_t* init_pos, const
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (e->obs_pending) {  // deferred observations (belief propagation of the last step) first: a partial reset keeps the other envs
-    launch_observe(e, p, (unsigned)((p.B + TILE - 1) / TILE), s);
+    Params pf = p;
+    pf.out.stats = e->pending_stats;
+    launch_observe(e, pf, (unsigned)((p.B + TILE - 1) / TILE), s);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     e->obs_pending = false;
@@ -3622,6 +3625,7 @@ int step_impl(SyEnv* e, const int64_t* actions, const int32_t* actions32, const 
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     e->obs_pending = true;
+    e->pending_stats = p.out.stats;  // the observation kernel that follows scores the belief at reveals iff this step collected statistics
     if (after_logic) CUDA_TRY(cudaEventRecord(after_logic, s));
     if (fused_sampled) *fused_sampled = next_actions != nullptr;
     if (!defer) {
@@ -3780,6 +3784,7 @@ int sy_flush_observations(SyEnv* e, const SyState* st, const SyObs* ob, sy_strea
   int rc = fill_params(e, st, ob, nullptr, p);
   if (rc) return rc;
   if ((rc = check_obs(ob))) return rc;
+  p.out.stats = e->pending_stats;
   CUDA_TRY(cudaSetDevice(e->cfg.device));
   launch_observe(e, p, (unsigned)((p.B + TILE - 1) / TILE), (cudaStream_t)stream);
   g_launches++;

@@ -24,7 +24,7 @@ def _pair(N, E, P, money, B, seed, *, toll, belief, reveal, graphs=1, auto_reset
     pool = pkg.generate_graph_pool(graphs, N, E, seed=0)
     kw = {} if max_timestep is None else {"max_timestep": max_timestep}
     env = pkg.BatchedScotlandYardEnv(B, P, money, graphs=pool, seed=seed, auto_reset=auto_reset, tolls=toll, belief=belief,
-                                     reveal_interval=reveal, keep_reward64=True, reward_mode=reward_mode, **kw)
+                                     belief_ce=belief, reveal_interval=reveal, keep_reward64=True, reward_mode=reward_mode, **kw)
     env.set_option("lagged_kernel", "on" if lagged else "off")
     cfg = so.OracleConfig(num_police=P, agent_money=money, toll=toll, belief=belief, reveal_interval=reveal,
                           reward_mode=reward_mode, **kw)
@@ -112,6 +112,32 @@ def test_deferred_shapes(torch_cuda, shape):
         env, ob = _pair(30, 60, 2, 6, 300, 8, toll=1, belief=True, reveal=2, auto_reset=False, max_timestep=6)
         _deferred_rollout(env, ob, 14, True, auto_reset=False)
     env.close()
+
+
+def test_statistics_of_deferred_steps_equal_plain_steps(torch_cuda):
+    """Every statistic -- incl. the belief cross-entropy at reveal steps, which the OBSERVATION kernel accumulates -- is the
+    same whether the steps run plainly, deferred with a final flush (the flush has no SyOut: it inherits the statistics
+    flag of the step it completes), or deferred with a partial reset in between."""
+    envs = []
+    for _ in range(3):
+        e, _ob = _pair(40, 80, 3, 8, 500, 17, toll=1, belief=True, reveal=3)
+        e.reset()
+        envs.append(e)
+    plain, deferred, mixed = envs
+    for s in range(20):
+        acts = plain.sample_actions(step_counter=s)
+        plain.step(acts)
+        deferred.step_deferred(acts)
+        mixed.step_deferred(acts) if s % 5 else mixed.step(acts)
+    deferred.flush_observations()
+    mixed.flush_observations()
+    want = plain.stats()
+    assert want["reveals"] > 0
+    for e in (deferred, mixed):
+        assert e.stats() == want
+        assert e.belief_map.cpu().numpy().tobytes() == plain.belief_map.cpu().numpy().tobytes()
+    for e in envs:
+        e.close()
 
 
 def test_partial_reset_with_pending_observations(torch_cuda):
