@@ -188,8 +188,12 @@ void sy_destroy(SyEnv* env);
  *                       step plainly.
  *   SY_OPT_TAIL_SPLIT   1 (default): when the observation kernel's grid ends in a partly filled wave, the tiles of that
  *                       wave are cut into 2 or 4 parts (one CTA each) so the wave is full and short; applies to the
- *                       warp-per-env belief path (large N).  0: always one CTA per 32-env tile. */
-enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3, SY_OPT_TAIL_SPLIT = 4 };
+ *                       warp-per-env belief path (large N).  0: always one CTA per 32-env tile.
+ *   SY_OPT_ROLLOUT_KERNEL 1 (default): where the lagged kernel is in use and the batch is at most one CTA per SM
+ *                       (<= ~4 700 envs), sy_rollout_random* run the whole rollout as ONE launch (sy_rollout_lagged_kernel: a CTA owns its tile for all steps;
+ *                       envs are independent, so nothing is synchronised across CTAs).  0: one launch per step. */
+enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3, SY_OPT_TAIL_SPLIT = 4,
+       SY_OPT_ROLLOUT_KERNEL = 5 };
 enum { SY_WRITER_BULK = 0, SY_WRITER_LSU = 1 };
 enum { SY_STEP_FUSED = 0, SY_STEP_TWO_KERNELS = 1, SY_STEP_AUTO = 2 };
 enum { SY_LAGGED_OFF = 0, SY_LAGGED_ON = 1, SY_LAGGED_AUTO = 2 };

@@ -564,7 +564,7 @@ constexpr int LAG_BAR = 4;
 constexpr int LAG_CSR_BAR = 6;  // lagged kernel: the writers' staged graph is complete (writers arrive, dynamics warps wait)
 template <int MODE, int MAXA, int BAR, int LAGT = 0, int CSRT = 0>
 __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm, int b0, int tid, const SharedGraph* sgp = nullptr,
-                                           const int* sg_valid = nullptr) {
+                                           const int* sg_valid = nullptr, unsigned extra_ctr = 0, bool draw_next = true) {
   constexpr int DS = LogicSmem<MAXA>::DS;
   const int lane = tid & 31, warp = tid >> 5;
   const int nEnv = min(32, p.B - b0);
@@ -871,10 +871,10 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
     if (n % LOGIC_WARPS == warp)
       warp_zero_bytes(reinterpret_cast<uint8_t*>(p.st.visits + (size_t)(b0 + e) * N), N * (int)sizeof(uint16_t), lane);
   }
-  if (p.next_actions) {
+  if (p.next_actions && draw_next) {
     // the next step's random valid actions from the NEW state still held in shared memory: the same draw as
     // sy_sample_actions_kernel (Philox(seed; env, step counter, agent) -> the pick-th affordable neighbour)
-    const unsigned ctr = p.next_counter + (p.next_counter_base ? *p.next_counter_base : 0u);
+    const unsigned ctr = p.next_counter + (p.next_counter_base ? *p.next_counter_base : 0u) + extra_ctr;
     for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
       const int e = (i * p.inv_A) >> 16, a = i - e * A;
       const int gg = sm.gid[e], u = (int)sm.pos[e * HS + a], m = sm.money[e * AS + a];
@@ -1978,6 +1978,54 @@ __global__ void __launch_bounds__((BW + WRW + LOGIC_WARPS) * 32, 2) sy_step_lagg
   }
 }
 
+// K random-policy steps in ONE launch (sy_rollout_random* on batches of at most one wave): the lagged kernel's CTA in a
+// loop.  Envs are independent and a CTA owns its 32-env tile for the whole rollout, so nothing is exchanged between CTAs
+// and no grid-wide synchronisation exists: iteration `it` writes the observations of the state after `it` steps while
+// the dynamics warps run step it + 1 (and draw the actions of step it + 2 from the new state); a CTA-wide barrier closes
+// the iteration (the new state is visible to the CTA's own roles, shared memory may be reused).  K + 1 iterations: the
+// first without observations (they are current on entry), the last without dynamics.
+constexpr int ROLL_BAR = 7;
+template <int MODE, int MAXA, int BW, int WRW>
+__global__ void __launch_bounds__((BW + WRW + LOGIC_WARPS) * 32, 2) sy_rollout_lagged_kernel(const Params p, const int K) {
+  constexpr int NT = (BW + WRW + LOGIC_WARPS) * 32;
+  constexpr int CSRT = (WRW + LOGIC_WARPS) * 32;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ LogicSmem<MAXA> lsm;
+  __shared__ int staged_flag;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile0 = blockIdx.x * TILE;
+  const int nEnv = min(TILE, p.B - tile0);
+  for (int it = 0; it <= K; ++it) {
+    const bool do_obs = it > 0, do_logic = it < K;
+    if (warp < BW) {
+      if constexpr (BW > 0) {
+        if (do_obs) belief_role<BW, NT>(p, dyn, tile0, nEnv, warp, lane);
+        else asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_BAR), "n"(NT) : "memory");
+      }
+    } else if (warp < BW + WRW) {
+      if (do_obs) {
+        writer_role<WRW, false, NT, CSRT>(p, dyn, tile0, nEnv, warp - BW, lane, &staged_flag);
+      } else {
+        if (threadIdx.x == BW * 32) staged_flag = 0;  // nothing staged: the dynamics read the pool tables
+        asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_CSR_BAR), "n"(CSRT) : "memory");
+        asm volatile("bar.arrive %0, %1;\n" ::"n"(LAG_BAR), "n"(NT) : "memory");
+      }
+    } else {
+      if (do_logic) {
+        const int* s_rp = reinterpret_cast<const int*>(dyn + p.wr_off_csr);
+        const uint16_t* s_col = reinterpret_cast<const uint16_t*>(s_rp + p.N + 1);
+        const SharedGraph sg{s_rp, s_col, reinterpret_cast<const uint8_t*>(s_col + p.tb.nnz_stride)};
+        // (the last step draws nothing: `actions` keeps the actions of the last step, as sy_rollout_random documents)
+        logic_tile<MODE, MAXA, 5, NT, CSRT>(p, lsm, tile0, threadIdx.x - (BW + WRW) * 32, &sg, &staged_flag, (unsigned)it, it + 1 < K);
+      } else {  // complete the two hand-shakes of the observation roles
+        asm volatile("bar.sync %0, %1;\n" ::"n"(LAG_CSR_BAR), "n"(CSRT) : "memory");
+        asm volatile("bar.sync %0, %1;\n" ::"n"(LAG_BAR), "n"(NT) : "memory");
+      }
+    }
+    asm volatile("bar.sync %0, %1;\n" ::"n"(ROLL_BAR), "n"(NT) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused persistent step kernel: ONE launch per sy_step.  Every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 // with three warp-specialised roles that run at their own pace:
@@ -2785,6 +2833,7 @@ struct SyEnv {
   // wave pays again (16 384 envs 44.4 vs 40.8 us, 65 536 envs 156 vs 129 us).
   int opt_lagged = SY_LAGGED_AUTO;
   int lag_slots = 0;  // resident CTAs of the lagged kernel (occupancy x SMs)
+  int opt_rollout_kernel = 1;  // sy_set_option(SY_OPT_ROLLOUT_KERNEL): random rollouts of single-wave batches as ONE launch
 };
 
 namespace {
@@ -2905,6 +2954,17 @@ FusedFn lagged_fn_bw(int reward_mode, int A) {
   if (A <= 8) return f64 ? sy_step_lagged_kernel<SY_REWARD_FP64, 8, BW, WR_WARPS> : sy_step_lagged_kernel<SY_REWARD_FP32, 8, BW, WR_WARPS>;
   return f64 ? sy_step_lagged_kernel<SY_REWARD_FP64, 16, BW, WR_WARPS> : sy_step_lagged_kernel<SY_REWARD_FP32, 16, BW, WR_WARPS>;
 }
+using RolloutFn = void (*)(const Params, const int);
+template <int BW>
+RolloutFn rollout_fn_bw(int reward_mode, int A) {
+  const bool f64 = reward_mode == SY_REWARD_FP64;
+  if (A <= 4) return f64 ? sy_rollout_lagged_kernel<SY_REWARD_FP64, 4, BW, WR_WARPS> : sy_rollout_lagged_kernel<SY_REWARD_FP32, 4, BW, WR_WARPS>;
+  if (A <= 8) return f64 ? sy_rollout_lagged_kernel<SY_REWARD_FP64, 8, BW, WR_WARPS> : sy_rollout_lagged_kernel<SY_REWARD_FP32, 8, BW, WR_WARPS>;
+  return f64 ? sy_rollout_lagged_kernel<SY_REWARD_FP64, 16, BW, WR_WARPS> : sy_rollout_lagged_kernel<SY_REWARD_FP32, 16, BW, WR_WARPS>;
+}
+RolloutFn rollout_fn(const SyEnv* e) {
+  return e->cfg.belief ? rollout_fn_bw<BEL_WARPS>(e->cfg.reward_mode, e->A) : rollout_fn_bw<0>(e->cfg.reward_mode, e->A);
+}
 FusedFn lagged_fn(const SyEnv* e) {
   return e->cfg.belief ? lagged_fn_bw<BEL_WARPS>(e->cfg.reward_mode, e->A) : lagged_fn_bw<0>(e->cfg.reward_mode, e->A);
 }
@@ -2923,7 +2983,8 @@ int plan_lagged(SyEnv* e) {
     const int slot = (e->cfg.belief ? 6 : 0) + (e->cfg.reward_mode == SY_REWARD_FP64 ? 3 : 0) + (e->A <= 4 ? 0 : (e->A <= 8 ? 1 : 2));
     size_t& cur = limit[e->cfg.device & 63][slot];
     if (e->obs_smem > cur) {
-      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem) != cudaSuccess) {
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem) != cudaSuccess ||
+          cudaFuncSetAttribute(rollout_fn(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->obs_smem) != cudaSuccess) {
         cudaGetLastError();
         return SY_OK;
       }
@@ -3175,6 +3236,10 @@ int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
     case SY_OPT_WRITER_PATH:
       if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
       e->opt_writer = value;
+      return SY_OK;
+    case SY_OPT_ROLLOUT_KERNEL:
+      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_ROLLOUT_KERNEL: 0 or 1");
+      e->opt_rollout_kernel = value;
       return SY_OK;
     case SY_OPT_TAIL_SPLIT:
       if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_TAIL_SPLIT: 0 or 1");
@@ -3973,9 +4038,51 @@ int sy_copy_segments(int32_t num_segments, void* const* dst, const void* const* 
   return SY_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// the whole rollout as ONE launch of sy_rollout_lagged_kernel (batches of at most one wave, observations current on entry;
+// `actions` holds the first step's draw).  The draw of step k + 1 uses counter next_counter + k (+ *base).
+int rollout_one_launch(SyEnv* e, int32_t num_steps, int64_t* actions, uint32_t next_counter, const uint32_t* next_counter_base,
+                       const SyState* st, const SyObs* ob, const SyOut* out, cudaStream_t s) {
+  if (!out) return fail(SY_ERR_INVALID_ARGUMENT, "SyOut is NULL");
+  if (out->struct_bytes != sizeof(SyOut)) return fail(SY_ERR_INVALID_ARGUMENT, "SyOut size mismatch");
+  if (!out->reward || !out->terminated || !out->truncated || !out->done || !out->winner)
+    return fail(SY_ERR_INVALID_ARGUMENT, "SyOut has NULL members");
+  Params p;
+  int rc = fill_params(e, st, ob, out, p);
+  if (rc) return rc;
+  if ((rc = check_obs(ob))) return rc;
+  p.actions = reinterpret_cast<const long long*>(actions);
+  p.next_actions = reinterpret_cast<long long*>(actions);
+  p.next_counter = next_counter;
+  p.next_counter_base = next_counter_base;
+  CUDA_TRY(cudaSetDevice(e->cfg.device));
+  e->aux_after_logic = false;
+  rollout_fn(e)<<<(unsigned)((p.B + TILE - 1) / TILE), lagged_threads(e), e->obs_smem, s>>>(p, (int)num_steps);
+  g_launches++;
+  CUDA_TRY(cudaGetLastError());
+  return SY_OK;
+}
+bool one_launch_rollout(const SyEnv* e, const SyObs* ob) {
+  // at most one CTA per SM: there the launches it saves outweigh the CTA-wide barrier per step (c2, 32 tiles: 8.8 -> 6.8 us
+  // per step; c3-shaped 148 tiles 17.3 -> 16.4 us; 192 tiles 22.0 -> 22.4 us, 296 tiles 23.2 -> 24.8 us)
+  return use_lagged(e) && e->opt_writer != SY_WRITER_BULK && e->opt_fused != SY_STEP_FUSED && e->opt_rollout_kernel &&
+         2 * ((e->cfg.num_envs + TILE - 1) / TILE) <= e->lag_slots && ob != nullptr;
+}
+}  // namespace
+
+extern "C" {
+
 int sy_rollout_random(SyEnv* e, int32_t num_steps, uint32_t step_counter0, int64_t* actions, const SyState* st, const SyObs* ob,
                       const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions or negative num_steps");
+  if (num_steps >= 2 && one_launch_rollout(e, ob)) {
+    int rc = sy_flush_observations(e, st, ob, stream);
+    if (!rc) rc = sy_sample_actions(e, st, step_counter0, actions, stream);
+    if (!rc) rc = rollout_one_launch(e, num_steps, actions, step_counter0 + 1u, nullptr, st, ob, out, (cudaStream_t)stream);
+    return rc;
+  }
   bool have_actions = false;  // the fused / lagged step kernels draw the next step's actions themselves
   const bool pipelined = use_lagged(e) && e->opt_writer != SY_WRITER_BULK && e->opt_fused != SY_STEP_FUSED;  // deferred steps, one flush at the end
   for (int32_t k = 0; k < num_steps; ++k) {
@@ -3995,7 +4102,18 @@ int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_de
                           const SyObs* ob, const SyOut* out, sy_stream_t stream) {
   if (!e || !actions || !step_counter_dev || num_steps < 0) return fail(SY_ERR_INVALID_ARGUMENT, "NULL env / actions / counter or negative num_steps");
   cudaStream_t s = (cudaStream_t)stream;
-  int rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
+  int rc = SY_OK;
+  if (num_steps >= 2 && one_launch_rollout(e, ob)) {
+    rc = sy_flush_observations(e, st, ob, stream);
+    if (!rc) rc = sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev);
+    if (!rc) rc = rollout_one_launch(e, num_steps, actions, 1u, step_counter_dev, st, ob, out, s);
+    if (rc) return rc;
+    sy_advance_counter_kernel<<<1, 1, 0, s>>>(step_counter_dev, (unsigned)num_steps);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return SY_OK;
+  }
+  rc = num_steps > 0 ? sample_impl<long long>(e, st, 0u, reinterpret_cast<long long*>(actions), stream, step_counter_dev) : SY_OK;
   if (rc) return rc;
   const bool pipelined = use_lagged(e) && e->opt_writer != SY_WRITER_BULK && e->opt_fused != SY_STEP_FUSED;
   if (fused_eligible(e, ob) || pipelined) {

@@ -252,7 +252,7 @@ class BatchedScotlandYardEnv:
 
     OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1}), "step_kernel": (1, {"fused": 0, "two_kernels": 1, "auto": 2}),
                "nf_fill": (2, {"off": 0, "on": 1}), "lagged_kernel": (3, {"off": 0, "on": 1, "auto": 2}),
-               "tail_split": (4, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
+               "tail_split": (4, {"off": 0, "on": 1}), "rollout_kernel": (5, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
 
     def set_option(self, name: str, value):
         """Tuning knobs of the handle (results are identical for every setting; include/sy_env.h SY_OPT_*):
@@ -261,7 +261,8 @@ class BatchedScotlandYardEnv:
         (TMA bulk stores); `nf_fill` = "off" (default) | "on" (split step: TMA fill kernel next to the dynamics);
         `lagged_kernel` = "auto" (default: deferred steps and the random rollouts run observations of step k + dynamics of
         step k+1 as one launch when the batch is one wave of that kernel, <= ~9 500 envs) | "on" | "off"; `tail_split` =
-        "on" (default) | "off" (the observation grid's partly filled last wave cut into parts)."""
+        "on" (default) | "off" (the observation grid's partly filled last wave cut into parts); `rollout_kernel` = "on"
+        (default) | "off" (random rollouts of single-wave batches as ONE launch for all steps)."""
         opt, values = self.OPTIONS[name]
         _cabi.check(self._lib.sy_set_option(self._handle, opt, values[value] if isinstance(value, str) else int(value)))
         self.options = dict(getattr(self, "options", {}), **{name: value})

@@ -199,19 +199,26 @@ def test_rollout_random_is_pipelined_and_flushed(torch_cuda):
     env.close()
 
 
-@pytest.mark.parametrize("shape", ["c2", "c3_one_wave"])
-def test_small_batch_rollout_graph_is_pipelined_by_default(torch_cuda, shape):
-    """Batches of at most one wave of the lagged kernel: capture_rollout / sy_rollout_random_dev step deferred by default
-    (lagged_kernel = auto) -- one launch per step -- and the replayed CUDA graph leaves state AND observations equal to
-    the oracle's (BASELINE config 2 as benchmarked, and a c3-shaped batch of 296 tiles minus a ragged tail)."""
+@pytest.mark.parametrize("shape,one_launch", [("c2", True), ("c2", False), ("c3_one_cta_per_sm", True), ("c3_one_wave", False), ("p15", True)])
+def test_small_batch_rollout_graph_is_pipelined_by_default(torch_cuda, shape, one_launch):
+    """Batches of at most one wave of the lagged kernel: capture_rollout / sy_rollout_random_dev run pipelined by default
+    (lagged_kernel = auto) -- the whole segment as ONE launch (sy_rollout_lagged_kernel) up to one CTA per SM, one lagged
+    launch per step above that or with rollout_kernel = off -- and the replayed CUDA graph leaves state AND observations
+    equal to the oracle's (BASELINE config 2 as benchmarked, c3-shaped batches of 148 and 296 tiles minus a ragged tail,
+    15 police on a graph pool)."""
     torch = torch_cuda
-    if shape == "c2":
+    if shape == "p15":
+        env, ob = _pair(120, 230, 15, 12, 777, 3, toll=1, belief=True, reveal=4, graphs=3)
+        belief = True
+    elif shape == "c2":
         env, ob = _pair(50, 110, 3, 10, 1024, 2, toll=0, belief=False, reveal=5)
         belief = False
-    else:
-        env, ob = _pair(200, 400, 6, 20, 296 * 32 - 7, 3, toll=1, belief=True, reveal=5)
+    else:  # 148 tiles: still ONE launch per rollout; 296 tiles: one lagged launch per step even with the option on
+        tiles = 148 if shape == "c3_one_cta_per_sm" else 296
+        env, ob = _pair(200, 400, 6, 20, tiles * 32 - 7, 3, toll=1, belief=True, reveal=5)
         belief = True
     env.set_option("lagged_kernel", "auto")
+    env.set_option("rollout_kernel", "off" if shape == "c2" and not one_launch else "on")
     env.reset()
     seg, replays = 6, 5
     lib = __import__("student_mechanism_design_b200").load_library()
@@ -220,7 +227,8 @@ def test_small_batch_rollout_graph_is_pipelined_by_default(torch_cuda, shape):
     n0 = lib.sy_launch_count()
     env.rollout_random(seg, step_counter=seg)  # the same call outside a graph, for the launch count
     torch.cuda.synchronize()
-    assert lib.sy_launch_count() - n0 == seg + 2  # sampler, dynamics, (seg - 1) lagged launches, flush
+    # one launch: sampler + the rollout kernel; per step: sampler, dynamics, (seg - 1) lagged launches, flush
+    assert lib.sy_launch_count() - n0 == (2 if one_launch else seg + 2)
     counter.fill_(2 * seg)
     for _ in range(replays):
         graph.replay()
