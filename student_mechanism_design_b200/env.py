@@ -402,9 +402,12 @@ class BatchedScotlandYardEnv:
     def capture_rollout(self, num_steps: int, actions: Optional[torch.Tensor] = None):
         """A CUDA graph of `num_steps` random-policy steps whose step counter lives on the device, so every
         `graph.replay()` continues the rollout with fresh draws (sy_rollout_random_dev).  Small batches are
-        launch-latency bound; replaying a graph removes most of that.  Returns (graph, counter tensor)."""
+        launch-latency bound; replaying a graph removes most of that.  Returns (graph, counter tensor).  The captured
+        launches assume that no observations are pending (what holds when this returns): call `flush_observations()`
+        before a replay that follows `step_deferred`."""
         if not self._is_reset:
             raise _cabi.SyError("step() before reset()")
+        self.flush_observations()
         if actions is None:
             actions = torch.empty(self.num_envs, self.num_agents, dtype=torch.int64, device=self.device)
         counter = torch.tensor([self._sample_counter], dtype=torch.int32, device=self.device)  # read as uint32
