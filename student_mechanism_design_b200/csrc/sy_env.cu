@@ -268,6 +268,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialisation attribute may start while
+// its predecessor in the stream still runs; pdl_wait() blocks until that predecessor has completed and its writes are
+// visible (a no-op for plainly launched kernels), pdl_launch_dependents() lets the successor's CTAs be scheduled early
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -576,6 +581,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
   // ---- P0: stage the tile (coalesced) and the head of the two float64 tables
   for (int i = tid; i < EXP_SMEM; i += LOGIC_THREADS) sm.rt.exp_neg[i] = i < p.tb.n_exp ? __ldg(p.tb.exp_neg + i) : 0.0;
   for (int i = tid; i < COV_SMEM; i += LOGIC_THREADS) sm.rt.coverage[i] = __ldg(p.tb.coverage + min(i, p.tb.n_cov - 1));
+  if constexpr (LAGT == 0) pdl_wait();  // everything above is independent of the state the previous kernel wrote
   for (int i = tid; i < nEnv * A; i += LOGIC_THREADS) {
     const int e = (i * p.inv_A) >> 16, a = i - e * A;  // i / A without a division (i < 512, A <= 16)
     const size_t o = (size_t)b0 * A + i;
@@ -924,6 +930,7 @@ __device__ __forceinline__ void logic_tile(const Params& p, LogicSmem<MAXA>& sm,
 template <int MODE, int MAXA>
 __global__ void __launch_bounds__(LOGIC_THREADS, SY_LOGIC_MIN_CTAS) sy_logic_kernel(const Params p) {
   __shared__ LogicSmem<MAXA> sm;
+  pdl_launch_dependents();  // the observation kernel's CTAs may take the slots the last wave of this grid leaves free
   logic_tile<MODE, MAXA, 3>(p, sm, blockIdx.x * 32, threadIdx.x);
 }
 
@@ -1913,6 +1920,8 @@ __global__ void __launch_bounds__((BW + WRW) * 32) sy_observe_kernel(const Param
     if (nEnv <= 0) return;
   }
   const int nbw = BW;  // without a belief map the belief warps simply exit
+  pdl_launch_dependents();
+  pdl_wait();  // the dynamics kernel's state (CTAs of this grid may have been scheduled before it finished)
   if (warp < nbw && !p.belief_on) return;
   const long long t0 = FCLK_NOW();
   if (warp < nbw) {
@@ -2833,6 +2842,7 @@ struct SyEnv {
   // wave pays again (16 384 envs 44.4 vs 40.8 us, 65 536 envs 156 vs 129 us).
   int opt_lagged = SY_LAGGED_AUTO;
   int lag_slots = 0;  // resident CTAs of the lagged kernel (occupancy x SMs)
+  int opt_pdl = 0;  // sy_set_option(SY_OPT_PDL): dynamics / observation kernels launched with programmatic stream serialisation
   int opt_rollout_kernel = 1;  // sy_set_option(SY_OPT_ROLLOUT_KERNEL): random rollouts of single-wave batches as ONE launch
 };
 
@@ -3024,6 +3034,23 @@ int raise_observe_smem_limit(int device, size_t bytes) {
   return SY_OK;
 }
 
+// <<<>>> with the programmatic-serialisation attribute (pdl): the kernel may be scheduled while its predecessor in the
+// stream still runs; it calls pdl_wait() before it touches anything that predecessor writes
+template <typename K>
+void launch_ex(K kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, const Params& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 void launch_observe(const SyEnv* e, const Params& p0, unsigned grid, cudaStream_t s) {
   const bool gen = e->bel_warps == GEN_BEL_WARPS && GEN_BEL_WARPS != BEL_WARPS;
   Params p = p0;
@@ -3047,8 +3074,8 @@ void launch_observe(const SyEnv* e, const Params& p0, unsigned grid, cudaStream_
     if (gen) sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
     else sy_observe_kernel<BEL_WARPS, WR_WARPS, WV_BULK><<<grid, THREADS, e->obs_smem, s>>>(p);
   } else {
-    if (gen) sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
-    else sy_observe_kernel<BEL_WARPS, WR_WARPS><<<grid, THREADS, e->obs_smem, s>>>(p);
+    if (gen) launch_ex(sy_observe_kernel<GEN_BEL_WARPS, GEN_WR_WARPS>, grid, THREADS, e->obs_smem, s, e->opt_pdl != 0, p);
+    else launch_ex(sy_observe_kernel<BEL_WARPS, WR_WARPS>, grid, THREADS, e->obs_smem, s, e->opt_pdl != 0, p);
   }
 }
 
@@ -3236,6 +3263,10 @@ int sy_set_option(SyEnv* e, int32_t option, int32_t value) {
     case SY_OPT_WRITER_PATH:
       if (value != SY_WRITER_BULK && value != SY_WRITER_LSU) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_WRITER_PATH: 0 (bulk) or 1 (LSU)");
       e->opt_writer = value;
+      return SY_OK;
+    case SY_OPT_PDL:
+      if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_PDL: 0 or 1");
+      e->opt_pdl = value;
       return SY_OK;
     case SY_OPT_ROLLOUT_KERNEL:
       if (value != 0 && value != 1) return fail(SY_ERR_INVALID_ARGUMENT, "SY_OPT_ROLLOUT_KERNEL: 0 or 1");
@@ -3617,16 +3648,16 @@ bool fused_eligible(const SyEnv* e, const SyObs* ob) {
 
 // next_actions (+ counter): a fused launch also draws the next step's random actions; *fused_sampled reports whether it did
 void launch_logic(const SyEnv* e, const Params& p, unsigned grid, cudaStream_t ls) {
-  const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64;
+  const bool f64 = e->cfg.reward_mode == SY_REWARD_FP64, pdl = e->opt_pdl != 0;
   if (p.A <= 4) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 4><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    if (f64) launch_ex(sy_logic_kernel<SY_REWARD_FP64, 4>, grid, LOGIC_THREADS, 0, ls, pdl, p);
+    else launch_ex(sy_logic_kernel<SY_REWARD_FP32, 4>, grid, LOGIC_THREADS, 0, ls, pdl, p);
   } else if (p.A <= 8) {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 8><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    if (f64) launch_ex(sy_logic_kernel<SY_REWARD_FP64, 8>, grid, LOGIC_THREADS, 0, ls, pdl, p);
+    else launch_ex(sy_logic_kernel<SY_REWARD_FP32, 8>, grid, LOGIC_THREADS, 0, ls, pdl, p);
   } else {
-    if (f64) sy_logic_kernel<SY_REWARD_FP64, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
-    else sy_logic_kernel<SY_REWARD_FP32, 16><<<grid, LOGIC_THREADS, 0, ls>>>(p);
+    if (f64) launch_ex(sy_logic_kernel<SY_REWARD_FP64, 16>, grid, LOGIC_THREADS, 0, ls, pdl, p);
+    else launch_ex(sy_logic_kernel<SY_REWARD_FP32, 16>, grid, LOGIC_THREADS, 0, ls, pdl, p);
   }
 }
 

@@ -252,7 +252,8 @@ class BatchedScotlandYardEnv:
 
     OPTIONS = {"writer_path": (0, {"bulk": 0, "lsu": 1}), "step_kernel": (1, {"fused": 0, "two_kernels": 1, "auto": 2}),
                "nf_fill": (2, {"off": 0, "on": 1}), "lagged_kernel": (3, {"off": 0, "on": 1, "auto": 2}),
-               "tail_split": (4, {"off": 0, "on": 1}), "rollout_kernel": (5, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
+               "tail_split": (4, {"off": 0, "on": 1}), "rollout_kernel": (5, {"off": 0, "on": 1}),
+               "pdl": (6, {"off": 0, "on": 1})}  # include/sy_env.h SY_OPT_*
 
     def set_option(self, name: str, value):
         """Tuning knobs of the handle (results are identical for every setting; include/sy_env.h SY_OPT_*):

@@ -46,6 +46,9 @@ def _pair(N, E, P, money, B, seed, *, toll, belief, reveal, graphs=1, writer=Non
     if writer == "lsu_lagged":  # rollouts: software-pipelined deferred steps through the lagged kernel
         env.set_option("lagged_kernel", "on")
         writer = "lsu"
+    if writer == "lsu_pdl":  # dynamics / observation kernels launched with programmatic stream serialisation
+        env.set_option("pdl", "on")
+        writer = "lsu"
     if writer is not None:
         env.set_option("step_kernel", "fused" if writer == "fused" else "two_kernels")
         if writer != "fused":
@@ -110,7 +113,7 @@ def _rollout_against_oracle(env, ob, steps, belief, dense_every=1):
     return done
 
 
-@pytest.mark.parametrize("writer", ["lsu", "fused", "bulk", "split"])
+@pytest.mark.parametrize("writer", ["lsu", "lsu_pdl", "fused", "bulk", "split"])
 def test_config3_full_size_matches_oracle(torch_cuda, writer):
     """BASELINE config 3 exactly as benchmarked: 200 nodes / 400 edges / 6 police, budget 20, toll 1, belief on,
     reveal every 5, 65 536 envs, same-step auto-reset, 25 steps -- every tile of the 2 048-tile grid and all statistics
@@ -148,7 +151,7 @@ def test_config3_ragged_batch_graph_pool(torch_cuda):
     env.close()
 
 
-@pytest.mark.parametrize("writer", ["lsu", "lsu_lagged", "fused", "split"])
+@pytest.mark.parametrize("writer", ["lsu", "lsu_lagged", "lsu_pdl", "fused", "split"])
 def test_timed_path_graph_replay_matches_oracle(torch_cuda, writer):
     """The path bench.py times -- capture_rollout (sy_rollout_random_dev: device-resident step counter; "lsu", the
     default at this size: two launches per step, the sampler of step k+1 forked next to the observation kernel of step
