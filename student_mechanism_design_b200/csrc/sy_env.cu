@@ -21,6 +21,11 @@
 //                      warps run the belief propagation as a lane = env SpMM over a transposed smem tile (LDGSTS).
 // The step is bound by the HBM writes of the observations; graph tables are a few hundred
 // KB and are read through L1/L2 with ld.global.nc.
+// Batches of at most one wave of tiles are latency bound instead, and take single-launch forms (DESIGN.md section 4,
+// "Which kernels a call launches"):
+//   sy_step_fused_kernel      sy_step as one persistent launch (dynamics -> TMA bulk-store writers + belief per CTA)
+//   sy_step_lagged_kernel     sy_step_deferred: observation roles of step k + dynamics warps of step k+1 in one CTA
+//   sy_rollout_lagged_kernel  sy_rollout_random*: all K steps in one launch, a CTA owns its tile throughout
 #include "../../include/sy_env.h"
 
 #include <cuda_runtime.h>
@@ -4160,7 +4165,9 @@ int sy_rollout_random_dev(SyEnv* e, int32_t num_steps, uint32_t* step_counter_de
   } else {
     // The sampler of step k + 1 only needs the state the dynamics of step k wrote, not its observations: it is forked
     // onto the library stream right behind the logic kernel (fork / join with events, capturable), so it runs next to
-    // the observation kernel of step k instead of after it.
+    // the observation kernel of step k instead of after it.  (Drawing the actions at the end of the dynamics kernel
+    // instead, as the single-launch kernels do, was measured slower here: c3 0.1319 vs 0.1294 ms per step, c4 0.3175 vs
+    // 0.3145 -- it lengthens the latency-bound kernel, while the forked sampler hides under the store stream.)
     if (!e->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     if (!e->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
     for (int32_t k = 0; k < num_steps; ++k) {
