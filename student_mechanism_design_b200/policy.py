@@ -185,6 +185,7 @@ class GNNPolicy(_PolicyBase):
         return (acts, qt) if return_q else acts
 
     returns_actions = True  # RolloutCollector: the kernel already does the masked epsilon-greedy selection
+    reads_state_only = True  # ... from positions, budgets, reveal flags and the graph pool: no dense observation is read
     epsilon = (0.0, 0.0)    # (MrX, police) exploration rates used by __call__
 
     def __call__(self, obs=None):

@@ -112,6 +112,9 @@ class RolloutCollector:
         env, buf = self.env, self.buf
         obs = env.observation()
         on_device = env.device.type == "cuda"
+        # a policy that reads only the compact state (GNNPolicy: positions, budgets, reveal flags, the graph pool) lets
+        # the env step software-pipelined: the dense observations trail by one step and are flushed once at the end
+        deferred = bool(getattr(self.policy, "reads_state_only", False)) and hasattr(env, "step_deferred")
         for t in range(self.T):
             # the state BEFORE the step: one launch for the three tensors
             self._copy([buf["pos"][t], buf["money"][t], buf["mrx_revealed"][t]], [env.pos, env.money, env.mrx_revealed])
@@ -123,13 +126,18 @@ class RolloutCollector:
             else:
                 actions = masked_sample(self.policy(obs), env.action_mask, self.gen, self.greedy, env.DEFAULT_ACTION)
             self._step += 1
-            obs, reward, terminated, truncated, _ = env.step(actions)
+            if deferred:
+                reward, terminated, truncated, _ = env.step_deferred(actions)
+            else:
+                obs, reward, terminated, truncated, _ = env.step(actions)
             # the step's results: one launch (the per-env flags come from the status byte: bit 0 terminated, 1 truncated)
             dst, src = [buf["reward"][t], buf["status"][t]], [reward, env.status]
             if actions.data_ptr() != buf["actions"][t].data_ptr():
                 dst.append(buf["actions"][t])
                 src.append(actions.contiguous())
             self._copy(dst, src)
+        if deferred:
+            env.flush_observations()
         buf["terminated"] = (buf["status"] & 1).bool()
         buf["truncated"] = (buf["status"] & 2).bool()
         return buf

@@ -116,6 +116,18 @@ def test_gnn_policy_in_the_rollout_collector(torch_cuda):
     w = W[pos0.long(), acts.clamp_min(0)]
     assert bool((((w > 0) & (w <= money0)) | (acts == -1)).all())
     assert bool((acts >= 0).any()) and env.stats()["episodes"] > 0
+    # the collector stepped deferred (GNNPolicy reads only the compact state) and flushed: a twin env stepped plainly with
+    # the recorded actions ends in the same state AND the same dense observations
+    assert not env.observations_pending
+    twin = pkg.BatchedScotlandYardEnv(512, 3, 12, graph_nodes=40, graph_edges=75, seed=4, auto_reset=True)
+    twin.reset()
+    for t in range(30):
+        assert torch.equal(twin.pos, pos0[t]) and torch.equal(twin.money, money0[t])
+        twin.step(acts[t].contiguous())
+        assert torch.equal(twin.reward, traj["reward"][t])
+    for k in ("pos", "money", "timestep", "visits", "action_mask", "node_features", "agent_budget", "mrx_revealed"):
+        assert torch.equal(getattr(twin, k), getattr(env, k)), k
+    twin.close()
     env.close()
 
 
