@@ -172,6 +172,8 @@ void sy_destroy(SyEnv* env);
  *                       over the tiles of a CTA; in sy_rollout_random* its dynamics warps also draw the next step's
  *                       actions.  Needs 16-byte aligned observation buffers and a belief map of <= ~400 nodes (else the
  *                       call falls back to two kernels).  SY_STEP_TWO_KERNELS: dynamics kernel, then observation kernel.
+ *                       (With the default SY_OPT_LAGGED_KERNEL the random rollouts of such batches take the lagged
+ *                       kernels instead; an explicit SY_STEP_FUSED keeps the fused kernel there too.)
  *   SY_OPT_WRITER_PATH  writers of the two-kernel path's observation kernel: SY_WRITER_LSU (default) = 16-byte
  *                       streaming stores; SY_WRITER_BULK = zero-page bulk fill + chunk images + bulk stores.
  *   SY_OPT_NF_FILL      0 (default).  1: split step for batches of >= 8192 envs with float32 node_features: the zero
@@ -190,10 +192,11 @@ void sy_destroy(SyEnv* env);
  *                       wave are cut into 2 or 4 parts (one CTA each) so the wave is full and short; applies to the
  *                       warp-per-env belief path (large N).  0: always one CTA per 32-env tile.
  *   SY_OPT_ROLLOUT_KERNEL 1 (default): where the lagged kernel is in use and the batch is at most one CTA per SM
- *                       (<= ~4 700 envs), sy_rollout_random* run the whole rollout as ONE launch (sy_rollout_lagged_kernel: a CTA owns its tile for all steps;
- *                       envs are independent, so nothing is synchronised across CTAs).  0: one launch per step.
- *   SY_OPT_PDL          0 (default).  1: the dynamics and observation kernels of the two-launch path are launched with programmatic
- *                       stream serialisation (griddepcontrol): a kernel's CTAs may be scheduled, and run their
+ *                       (<= ~4 700 envs), sy_rollout_random* run the whole rollout as ONE launch
+ *                       (sy_rollout_lagged_kernel: a CTA owns its tile for all steps; envs are independent, so nothing is
+ *                       synchronised across CTAs).  0: one launch per step.
+ *   SY_OPT_PDL          0 (default).  1: the dynamics and observation kernels of the two-launch path are launched with
+ *                       programmatic stream serialisation (griddepcontrol): a kernel's CTAs may be scheduled, and run their
  *                       state-independent prologue, while the previous kernel of the stream drains.  Measured: c3 sy_step
  *                       0.1341 -> 0.1321 ms, replayed graph 0.1292 -> 0.1287; c4 and 16 384-env batches slower. */
 enum { SY_OPT_WRITER_PATH = 0, SY_OPT_STEP_KERNEL = 1, SY_OPT_NF_FILL = 2, SY_OPT_LAGGED_KERNEL = 3, SY_OPT_TAIL_SPLIT = 4,
